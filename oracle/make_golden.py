@@ -1,0 +1,222 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference on CPU.
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container (needs /root/reference):
+
+    python oracle/make_golden.py
+
+The reference (LI-Yiquan/3DPointCloudAttack) is imported from /root/reference with the
+work-arounds SURVEY.md section 8c lists (they touch the *environment*, never the
+reference's arithmetic):
+  * torch.Tensor.cuda -> identity, so the L3 wrappers that hard-code `.cuda()`
+    (attack/CW/CW_utils/dist_utils.py:29,68,105,156) run on CPU;
+  * stubs for modules missing here (matplotlib, seaborn, open3d) and for the removed
+    torch.autograd.gradcheck.zero_gradients, so attack/GeoA3/loss_utils.py imports.
+
+Every vector stores the inputs, the reference outputs and (where the output is
+differentiable) the reference autograd gradients for a fixed upstream gradient.
+torch 2.11.0+cu128 CPU, fp32, torch.set_num_threads(1) for a fixed summation order.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+
+
+def _prepare_reference():
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    torch.Tensor.cuda = lambda self, *a, **k: self          # CPU box: .cuda() is a no-op
+    import importlib
+    importlib.import_module("torch.autograd.gradcheck")
+    gc = sys.modules["torch.autograd.gradcheck"]
+    if not hasattr(gc, "zero_gradients"):
+        gc.zero_gradients = lambda x: None
+    for name in ("matplotlib", "matplotlib.pyplot", "seaborn", "open3d"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    sys.modules["matplotlib"].use = lambda *a, **k: None
+    sys.modules["seaborn"].set = lambda *a, **k: None
+    import os as _os
+    _real_popen = _os.popen
+
+    class _Fake:
+        def read(self):
+            return "24 80"
+
+    _os.popen = lambda cmd, *a, **k: _Fake() if "stty" in cmd else _real_popen(cmd, *a, **k)
+
+
+def face_fixture(n, seed):
+    """AddData/face0424.txt normalised as pointnet/bosphorus_dataset.py:74-76, random n-subset."""
+    raw = np.loadtxt(os.path.join(REF, "AddData", "face0424.txt"), delimiter=",")[:, :3]
+    rs = np.random.RandomState(seed)
+    pts = raw[rs.permutation(raw.shape[0])[:n]]
+    pts = pts - pts.mean(0, keepdims=True)
+    pts = pts / np.max(np.sqrt((pts ** 2).sum(1)))
+    return pts.astype(np.float32)
+
+
+def t(a, grad=False):
+    x = torch.from_numpy(np.ascontiguousarray(a)).clone()
+    x.requires_grad_(grad)
+    return x
+
+
+def n(x):
+    return x.detach().cpu().numpy()
+
+
+def save(name, **kw):
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **kw)
+    print("wrote", name, {k: getattr(v, "shape", None) for k, v in kw.items()})
+
+
+def main():
+    torch.set_num_threads(1)
+    _prepare_reference()
+    rs = np.random.RandomState(20261018)
+
+    face = face_fixture(1024, 0)                                  # [1024,3]
+    ori = np.stack([face, face_fixture(1024, 1)])                 # [2,1024,3]
+    adv = (ori + 0.01 * rs.randn(*ori.shape)).astype(np.float32)
+    adv0 = (ori + 1e-7 * rs.randn(*ori.shape)).astype(np.float32)  # CW iteration-0 state
+    gB = np.array([0.7, -1.3], np.float32)
+    gB2 = np.array([1.9, 0.4], np.float32)
+
+    # ---------------- a1: utils/dis_utils_torch.py ------------------------------------
+    from utils import dis_utils_torch as D
+    a_cf = np.ascontiguousarray(adv.transpose(0, 2, 1)); b_cf = np.ascontiguousarray(ori.transpose(0, 2, 1))
+    out = {}
+    for fn in ("chamfer", "sgd_hausdorff_dis", "bid_hausdorff_dis"):
+        a_, b_ = t(a_cf, True), t(b_cf, True)
+        v = getattr(D, fn)(a_, b_)
+        v.backward()
+        out[fn] = n(v); out[fn + "_ga"] = n(a_.grad); out[fn + "_gb"] = n(b_.grad)
+    out["pairwise_distances"] = n(D.pairwise_distances(t(a_cf[:, :, :96]), t(b_cf[:, :, :80])))
+    # the commented-out 3-point example at utils/dis_utils_torch.py:30-35
+    ka = np.array([[[1, 1, 1], [1, 1, 1], [1, 1, 1]]], np.float32)
+    kb = np.array([[[2, 2, 3], [2, 2, 2], [2, 2, 2]]], np.float32)
+    out["ka"] = ka; out["kb"] = kb
+    out["k_euclidean"] = n(D.euclidean_distances(t(ka), t(kb)))
+    out["k_chamfer"] = n(D.chamfer(t(ka), t(kb)))
+    out["k_sgd"] = n(D.sgd_hausdorff_dis(t(ka), t(kb)))
+    out["k_bid"] = n(D.bid_hausdorff_dis(t(ka), t(kb)))
+    save("a1_dis_utils_torch", a=a_cf, b=b_cf, **out)
+
+    # ---------------- a2: attack/CW/CW_utils/distance.py -------------------------------
+    from attack.CW.CW_utils import distance as CD
+    for tag, P_, G_ in (("face", adv, ori), ("iter0", adv0, ori),
+                        ("ragged", adv[:, :700], ori[:, :1000])):
+        out = {}
+        for name, mod in (("chamfer", CD.chamfer), ("hausdorff", CD.hausdorff)):
+            p_, g_ = t(P_, True), t(G_, True)
+            l1, l2 = mod(p_, g_)
+            ((l1 * t(gB)).sum() + (l2 * t(gB2)).sum()).backward()
+            out[name + "_l1"] = n(l1); out[name + "_l2"] = n(l2)
+            out[name + "_gp"] = n(p_.grad); out[name + "_gg"] = n(g_.grad)
+        Pm = CD.chamfer.batch_pairwise_dist(t(G_), t(P_))            # [B, N2(gts), N1(preds)]
+        m1, i1 = torch.min(Pm, 1); m2, i2 = torch.min(Pm, 2)
+        out.update(col_min=n(m1), col_arg=n(i1), row_min=n(m2), row_arg=n(i2),
+                   P_block=n(Pm[:, :64, :48]))
+        save("a2_distance_" + tag, preds=P_, gts=G_, g1=gB, g2=gB2, **out)
+
+    # SIadv variant returns (loss1+loss2)/2
+    from attack.SIadv.utils import set_distance as SD
+    save("a2_set_distance", preds=adv, gts=ori,
+         chamfer=n(SD.chamfer(t(adv), t(ori))), hausdorff=n(SD.hausdorff(t(adv), t(ori))))
+
+    # tie case: duplicated points -> torch.min(dim) picks the first index
+    dup_g = ori[:, :256].copy(); dup_g[:, 128:] = dup_g[:, :128]
+    dup_p = adv[:, :256].copy(); dup_p[:, 64:128] = dup_p[:, :64]
+    Pm = CD.chamfer.batch_pairwise_dist(t(dup_g), t(dup_p))
+    m1, i1 = torch.min(Pm, 1); m2, i2 = torch.min(Pm, 2)
+    save("a2_distance_ties", preds=dup_p, gts=dup_g, col_min=n(m1), col_arg=n(i1), row_min=n(m2), row_arg=n(i2))
+
+    # ---------------- L3 wrappers: attack/CW/CW_utils/dist_utils.py --------------------
+    from attack.CW.CW_utils import dist_utils as DU
+    w = np.array([2.0, 0.5], np.float32)
+    out = {}
+    for method in ("adv2ori", "ori2adv", "avg"):
+        for cls in ("ChamferDist", "HausdorffDist"):
+            a_ = t(adv, True)
+            v = getattr(DU, cls)(method=method)(a_, t(ori), weights=t(w), batch_avg=False)
+            (v * t(gB)).sum().backward()
+            out[f"{cls}_{method}"] = n(v); out[f"{cls}_{method}_g"] = n(a_.grad)
+    a_ = t(adv, True)
+    v = DU.ChamferDist()(a_, t(ori)); v.backward()
+    out["ChamferDist_default_mean"] = n(v); out["ChamferDist_default_mean_g"] = n(a_.grad)
+    for k, alpha in ((5, 1.05), (16, 1.05)):
+        a_ = t(adv, True)
+        v = DU.KNNDist(k=k, alpha=alpha)(a_, weights=t(w), batch_avg=False)
+        (v * t(gB)).sum().backward()
+        out[f"KNNDist_k{k}"] = n(v); out[f"KNNDist_k{k}_g"] = n(a_.grad)
+    a_ = t(adv, True)
+    v = DU.ChamferkNNDist(knn_k=16)(a_, t(ori), weights=t(w), batch_avg=True); v.backward()
+    out["ChamferkNNDist_k16"] = n(v); out["ChamferkNNDist_k16_g"] = n(a_.grad)
+    save("l3_dist_utils", adv=adv, ori=ori, weights=w, gB=gB, **out)
+
+    # ---------------- a3: attack/GeoA3/knn_utils.py -------------------------------------
+    from attack.GeoA3 import knn_utils as KU
+    out = {}
+    for tag, p1, p2, K in (("cross1", adv, ori, 1), ("self17", adv, adv, 17), ("cross4", ori, adv, 4)):
+        a_, b_ = t(p1, True), (None if p2 is p1 else t(p2, True))
+        r = KU.knn_points(a_, a_ if b_ is None else b_, K=K, return_nn=True)
+        gw = t(rs.randn(*r.dists.shape).astype(np.float32))
+        (r.dists * gw).sum().backward()
+        out.update({tag + "_dists": n(r.dists), tag + "_idx": n(r.idx), tag + "_nn": n(r.knn),
+                    tag + "_gw": n(gw), tag + "_g1": n(a_.grad)})
+        if b_ is not None:
+            out[tag + "_g2"] = n(b_.grad)
+    feat = rs.randn(2, 1024, 5).astype(np.float32)
+    idx = out["self17_idx"]
+    out["gather_x"] = feat
+    out["gather_out"] = n(KU.knn_gather(t(feat), torch.from_numpy(idx)))
+    save("a3_knn_utils", adv=adv, ori=ori, **out)
+
+    # ---------------- a4: attack/GeoA3/loss_utils.py ------------------------------------
+    from attack.GeoA3 import loss_utils as LU
+    adv_cf = np.ascontiguousarray(adv.transpose(0, 2, 1)); ori_cf = np.ascontiguousarray(ori.transpose(0, 2, 1))
+    nrm = rs.randn(2, 3, 1024).astype(np.float32); nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    out = {}
+    for fn in ("chamfer_loss", "pseudo_chamfer_loss", "hausdorff_loss"):
+        a_ = t(adv_cf, True)
+        v = getattr(LU, fn)(a_, t(ori_cf)); (v * t(gB)).sum().backward()
+        out[fn] = n(v); out[fn + "_g"] = n(a_.grad)
+    a_ = t(adv_cf, True)
+    v = LU.kNN_smoothing_loss(a_, 16); (v * t(gB)).sum().backward()
+    out["kNN_smoothing_loss"] = n(v); out["kNN_smoothing_loss_g"] = n(a_.grad)
+    ori_kappa = LU._get_kappa_ori(t(ori_cf), t(nrm), 16)
+    a_ = t(adv_cf, True)
+    adv_kappa, normal_curr = LU._get_kappa_adv(a_, t(ori_cf), t(nrm), 16)
+    v = LU.curvature_loss(a_, t(ori_cf), adv_kappa, ori_kappa); (v * t(gB)).sum().backward()
+    out.update(ori_kappa=n(ori_kappa), adv_kappa=n(adv_kappa), normal_curr=n(normal_curr),
+               curvature_loss=n(v), curvature_loss_g=n(a_.grad))
+    save("a4_geoa3_losses", adv=adv_cf, ori=ori_cf, normal=nrm, gB=gB, **out)
+
+    # ---------------- a6: model/dgcnn.py, model/curvenet_util.py ------------------------
+    from model import dgcnn, curvenet_util
+    f64c = rs.randn(2, 64, 256).astype(np.float32)
+    save("a6_knn_graph", x3=adv_cf, f64=f64c,
+         dgcnn_k20=n(dgcnn.knn(t(adv_cf), 20)), dgcnn_f64_k20=n(dgcnn.knn(t(f64c), 20)),
+         curvenet_k20=n(curvenet_util.knn(t(adv_cf), 20)),
+         curvenet_normal_k20=n(curvenet_util.normal_knn(t(adv_cf), 20)))
+
+    # ---------------- a7: model/pointnet2_utils.py --------------------------------------
+    from model import pointnet2_utils as P2
+    xyz = adv; new_xyz = adv[:, ::2][:, :512].copy()
+    save("a7_pointnet2_utils", xyz=xyz, new_xyz=new_xyz,
+         sqdist_block=n(P2.square_distance(t(new_xyz[:, :64]), t(xyz[:, :96]))),
+         ball_r02_n32=n(P2.query_ball_point(0.2, 32, t(xyz), t(new_xyz))),
+         ball_r04_n64=n(P2.query_ball_point(0.4, 64, t(xyz[:, :512]), t(new_xyz[:, :128]))),
+         ball_r002_n8=n(P2.query_ball_point(0.02, 8, t(xyz), t(new_xyz[:, :64]))))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,288 @@
+"""CPU oracle for the point-set distance path -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module.  The product (3dpointcloudattack_b200/) never does and
+fails loudly when its CUDA library is missing.
+
+Two layers:
+
+* thin ctypes bindings over oracle/pcd_oracle.c (the fp32, op-order-faithful
+  arithmetic: see the header of that file for the three addition orders), and
+* numpy restatements of every reference symbol on the path, each citing the
+  reference file:line it follows (paths relative to /root/reference).
+
+Parity status: PINNED.  oracle/make_golden.py imports the unmodified reference from
+/root/reference, runs it on seeded inputs on CPU (torch 2.11.0) and stores inputs and
+outputs under tests/golden/; tests/test_oracle_golden.py checks this module against
+those vectors (distance matrices and indices bit-exact, reductions to 1e-6).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from collections import namedtuple
+
+import numpy as np
+
+FORM_ROW_COL, FORM_COL_ROW, FORM_SUM_FIRST = 0, 1, 2
+NORM_MULSUM, NORM_FMA = 0, 1
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "libpcd_oracle.so")
+        if not os.path.exists(path):
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("_orc_build", os.path.join(_HERE, "build.py"))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            mod.build()
+        _LIB = ctypes.CDLL(path)
+    return _LIB
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+# --------------------------------------------------------------------------- C bindings
+def norms(kind, pts):
+    """pts [B,N,C] point-major -> [B,N] squared norms in the given rounding order."""
+    pts = _f32(pts)
+    B, N, C = pts.shape
+    out = np.empty((B, N), np.float32)
+    lib().orc_norms(ctypes.c_int(kind), _p(pts), ctypes.c_int64(B * N), ctypes.c_int(C), _p(out))
+    return out
+
+
+def pairwise(form, rows, cols, nrow, ncol):
+    rows, cols, nrow, ncol = _f32(rows), _f32(cols), _f32(nrow), _f32(ncol)
+    B, N, C = rows.shape
+    M = cols.shape[1]
+    out = np.empty((B, N, M), np.float32)
+    lib().orc_pairwise(ctypes.c_int(form), _p(rows), _p(cols), _p(nrow), _p(ncol),
+                       ctypes.c_int(B), ctypes.c_int(N), ctypes.c_int(M), ctypes.c_int(C), _p(out))
+    return out
+
+
+NN1 = namedtuple("NN1", "row_min row_arg col_min col_arg")
+
+
+def nn1(form, rows, cols, nrow, ncol):
+    """Row/column minima with lowest-index argmin, no [B,N,M] matrix."""
+    rows, cols, nrow, ncol = _f32(rows), _f32(cols), _f32(nrow), _f32(ncol)
+    B, N, C = rows.shape
+    M = cols.shape[1]
+    rmin = np.empty((B, N), np.float32); rarg = np.empty((B, N), np.int32)
+    cmin = np.empty((B, M), np.float32); carg = np.empty((B, M), np.int32)
+    lib().orc_nn1(ctypes.c_int(form), _p(rows), _p(cols), _p(nrow), _p(ncol),
+                  ctypes.c_int(B), ctypes.c_int(N), ctypes.c_int(M), ctypes.c_int(C),
+                  _p(rmin), _p(rarg), _p(cmin), _p(carg))
+    return NN1(rmin, rarg, cmin, carg)
+
+
+def knn(form, rows, cols, nrow, ncol, K):
+    """K smallest per row, ascending by (distance, index)."""
+    rows, cols, nrow, ncol = _f32(rows), _f32(cols), _f32(nrow), _f32(ncol)
+    B, N, C = rows.shape
+    M = cols.shape[1]
+    assert 1 <= K <= M
+    d = np.empty((B, N, K), np.float32); i = np.empty((B, N, K), np.int32)
+    lib().orc_knn(ctypes.c_int(form), _p(rows), _p(cols), _p(nrow), _p(ncol),
+                  ctypes.c_int(B), ctypes.c_int(N), ctypes.c_int(M), ctypes.c_int(C),
+                  ctypes.c_int(K), _p(d), _p(i))
+    return d, i
+
+
+def ball_query(radius, nsample, xyz, new_xyz):
+    """model/pointnet2_utils.py:84-104 -> idx [B,S,nsample] int64."""
+    xyz, new_xyz = _f32(xyz), _f32(new_xyz)
+    B, N, C = xyz.shape
+    S = new_xyz.shape[1]
+    nrow = norms(NORM_MULSUM, new_xyz); ncol = norms(NORM_MULSUM, xyz)
+    r2 = np.float32(float(radius) ** 2)       # python float radius**2, compared in fp32 (line 99)
+    out = np.empty((B, S, nsample), np.int32)
+    lib().orc_ball_query(_p(new_xyz), _p(xyz), _p(nrow), _p(ncol), ctypes.c_int(B), ctypes.c_int(S),
+                         ctypes.c_int(N), ctypes.c_int(C), ctypes.c_float(r2), ctypes.c_int(nsample), _p(out))
+    return out.astype(np.int64)
+
+
+# ------------------------------------------------------------------ a1: utils/dis_utils_torch.py
+def _cf_to_pm(a):
+    """[B,C,N] channel-first -> [B,N,C] point-major contiguous."""
+    return _f32(np.transpose(np.asarray(a), (0, 2, 1)))
+
+
+def dis_pairwise_raw(a, b):
+    """Pre-clamp, pre-sqrt matrix of torch.cdist's mm path (utils/dis_utils_torch.py:8-11;
+    ATen _euclidean_dist: x1_=[-2*x1, |x1|^2, 1], x2_=[x2, 1, |x2|^2], x1_ @ x2_^T)."""
+    A, Bm = _cf_to_pm(a), _cf_to_pm(b)
+    return pairwise(FORM_ROW_COL, A, Bm, norms(NORM_MULSUM, A), norms(NORM_MULSUM, Bm))
+
+
+def dis_pairwise_distances(a, b):
+    """utils/dis_utils_torch.py:8-11 -> [B,N,M] L2 (clamp_min(0).sqrt())."""
+    return np.sqrt(np.maximum(dis_pairwise_raw(a, b), np.float32(0)))
+
+
+def dis_chamfer(a, b):
+    """utils/dis_utils_torch.py:14-16.  Divisors are a.shape[1], b.shape[1] (= 3 for
+    [B,3,N] input -- reference quirk) and only sample 0 is returned."""
+    Mx = dis_pairwise_distances(a, b)
+    return (Mx.min(1).sum(1, dtype=np.float32) / np.float32(a.shape[1])
+            + Mx.min(2).sum(1, dtype=np.float32) / np.float32(b.shape[1]))[0]
+
+
+def dis_sgd_hausdorff(a, b):
+    """utils/dis_utils_torch.py:19-22: max_i min_j M[0]."""
+    return dis_pairwise_distances(a, b)[0].min(1).max()
+
+
+def dis_bid_hausdorff(a, b):
+    """utils/dis_utils_torch.py:25-28."""
+    return np.maximum(dis_sgd_hausdorff(a, b), dis_sgd_hausdorff(b, a))
+
+
+# ------------------------------------------------------- a2: attack/CW/CW_utils/distance.py
+def batch_pairwise_dist(x, y):
+    """attack/CW/CW_utils/distance.py:15-32: P = rx^T + ry - 2*zz, norms = diag of bmm."""
+    x, y = _f32(x), _f32(y)
+    return pairwise(FORM_SUM_FIRST, x, y, norms(NORM_FMA, x), norms(NORM_FMA, y))
+
+
+def _nn1_cw(preds, gts):
+    gts, preds = _f32(gts), _f32(preds)
+    return nn1(FORM_SUM_FIRST, gts, preds, norms(NORM_FMA, gts), norms(NORM_FMA, preds))
+
+
+def chamfer_distance(preds, gts):
+    """attack/CW/CW_utils/distance.py:40-50 -> (loss1[B], loss2[B]).
+    P = batch_pairwise_dist(gts, preds): rows = gts, cols = preds;
+    loss1 = mean over preds of min over gts (column minima), loss2 = mean of row minima."""
+    r = _nn1_cw(preds, gts)
+    return r.col_min.mean(1, dtype=np.float32), r.row_min.mean(1, dtype=np.float32)
+
+
+def hausdorff_distance(preds, gts):
+    """attack/CW/CW_utils/distance.py:58-70."""
+    r = _nn1_cw(preds, gts)
+    return r.col_min.max(1), r.row_min.max(1)
+
+
+def chamfer_distance_grads(preds, gts, g1, g2):
+    """d(sum_b g1[b]*loss1[b] + g2[b]*loss2[b]) / d(preds, gts) in float64, closed form
+    through the argmin indices (what autograd does through torch.min(dim))."""
+    preds64, gts64 = np.asarray(preds, np.float64), np.asarray(gts, np.float64)
+    r = _nn1_cw(preds, gts)
+    B, N1, _ = preds64.shape
+    N2 = gts64.shape[1]
+    gp = np.zeros_like(preds64); gg = np.zeros_like(gts64)
+    for b in range(B):
+        # loss1: each pred j -> nearest gt col_arg[j]
+        w = g1[b] / N1
+        diff = preds64[b] - gts64[b][r.col_arg[b]]
+        gp[b] += 2 * w * diff
+        np.add.at(gg[b], r.col_arg[b], -2 * w * diff)
+        # loss2: each gt i -> nearest pred row_arg[i]
+        w = g2[b] / N2
+        diff = gts64[b] - preds64[b][r.row_arg[b]]
+        gg[b] += 2 * w * diff
+        np.add.at(gp[b], r.row_arg[b], -2 * w * diff)
+    return gp, gg
+
+
+def hausdorff_distance_grads(preds, gts, g1, g2):
+    """Same for attack/CW/CW_utils/distance.py:58-70: torch.max(mins, dim=1) routes the
+    gradient to the first maximal entry."""
+    preds64, gts64 = np.asarray(preds, np.float64), np.asarray(gts, np.float64)
+    r = _nn1_cw(preds, gts)
+    gp = np.zeros_like(preds64); gg = np.zeros_like(gts64)
+    for b in range(preds64.shape[0]):
+        j = int(np.argmax(r.col_min[b])); i = int(r.col_arg[b, j])
+        diff = preds64[b, j] - gts64[b, i]
+        gp[b, j] += 2 * g1[b] * diff; gg[b, i] -= 2 * g1[b] * diff
+        i = int(np.argmax(r.row_min[b])); j = int(r.row_arg[b, i])
+        diff = gts64[b, i] - preds64[b, j]
+        gg[b, i] += 2 * g2[b] * diff; gp[b, j] -= 2 * g2[b] * diff
+    return gp, gg
+
+
+# ------------------------------------------------------------- a3: attack/GeoA3/knn_utils.py
+def knn_points(p1, p2, K=1):
+    """attack/GeoA3/knn_utils.py:10-55.  dist[i,j] = (|p1_j|^2 + inner_ij) + |p2_i|^2 --
+    the reference's broadcast lays p1's norms along the COLUMN axis and p2's along the ROW
+    axis (requires P1 == P2).  Returns (dists[B,P1,K] ascending, idx[B,P1,K] int64)."""
+    p1, p2 = _f32(p1), _f32(p2)
+    if p1.shape[1] != p2.shape[1]:
+        raise RuntimeError("reference broadcast requires P1 == P2")
+    ncol = norms(NORM_MULSUM, p1)    # indexed by j
+    nrow = norms(NORM_MULSUM, p2)    # indexed by i
+    d, i = knn(FORM_COL_ROW, p1, p2, nrow, ncol, K)
+    return d, i.astype(np.int64)
+
+
+def knn_points_matrix(p1, p2):
+    p1, p2 = _f32(p1), _f32(p2)
+    return pairwise(FORM_COL_ROW, p1, p2, norms(NORM_MULSUM, p2), norms(NORM_MULSUM, p1))
+
+
+def knn_gather(x, idx):
+    """attack/GeoA3/knn_utils.py:58-86: x[B,M,U], idx[B,L,K] -> [B,L,K,U]."""
+    x = np.asarray(x)
+    B = x.shape[0]
+    return x[np.arange(B)[:, None, None], idx]
+
+
+# ------------------------------------- a5: attack/CW/CW_utils/dist_utils.py:125-160 (KNNDist)
+def knn_dist_matrix(pc):
+    pc = _f32(pc)
+    n = norms(NORM_MULSUM, pc)
+    return pairwise(FORM_COL_ROW, pc, pc, n, n)
+
+
+def knn_dist_loss(pc, k=5, alpha=1.05):
+    """attack/CW/CW_utils/dist_utils.py:125-160 with weights=None -> loss[B]."""
+    pc = _f32(pc)
+    n = norms(NORM_MULSUM, pc)
+    d, _ = knn(FORM_COL_ROW, pc, pc, n, n, k + 1)
+    value = d[..., 1:].mean(-1, dtype=np.float32)                    # [B,K]
+    mean = value.mean(-1, dtype=np.float32)
+    std = value.std(-1, ddof=1, dtype=np.float64).astype(np.float32)  # torch.std: unbiased
+    thr = mean + np.float32(alpha) * std
+    mask = (value > thr[:, None]).astype(np.float32)
+    return (value * mask).mean(1, dtype=np.float32), value, mask
+
+
+# ---------------------------------------------- a6: model/dgcnn.py:194-200, curvenet_util.py
+def dgcnn_knn(x, k):
+    """model/dgcnn.py:194-200: x[B,C,N] -> idx[B,N,k] int64, nearest first, self included.
+    pairwise = (-xx - inner) - xx^T is the exact negation of FORM_COL_ROW, so top-k largest
+    of it = k smallest here."""
+    pm = _cf_to_pm(x)
+    n = norms(NORM_MULSUM, pm)
+    _, i = knn(FORM_COL_ROW, pm, pm, n, n, k)
+    return i.astype(np.int64)
+
+
+def dgcnn_neg_matrix(x):
+    pm = _cf_to_pm(x)
+    n = norms(NORM_MULSUM, pm)
+    return -pairwise(FORM_COL_ROW, pm, pm, n, n)
+
+
+# --------------------------------------------------- a7: model/pointnet2_utils.py:19-38
+def square_distance(src, dst):
+    src, dst = _f32(src), _f32(dst)
+    return pairwise(FORM_ROW_COL, src, dst, norms(NORM_MULSUM, src), norms(NORM_MULSUM, dst))
+
+
+def query_ball_point(radius, nsample, xyz, new_xyz):
+    return ball_query(radius, nsample, xyz, new_xyz)

@@ -1,0 +1,136 @@
+"""CPU: the oracle (oracle/pcd_oracle.{c,py}) against vectors produced by the unmodified
+reference (oracle/make_golden.py).  This is what pins the oracle."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, rel_inf
+from oracle import pcd_oracle as O
+
+
+def test_a1_known_answer_example():
+    # utils/dis_utils_torch.py:30-35 (commented example); values recorded in SURVEY.md section 4
+    g = load_golden("a1_dis_utils_torch")
+    assert np.isclose(g["k_chamfer"], 3.7032, atol=1e-4)
+    assert np.isclose(g["k_sgd"], 1.7321, atol=1e-4)
+    assert np.isclose(g["k_bid"], 2.4495, atol=1e-4)
+    # N, M <= 25 makes torch.cdist take its direct kernel (<= 2.4e-7 from the mm path)
+    np.testing.assert_allclose(O.dis_chamfer(g["ka"], g["kb"]), g["k_chamfer"], rtol=1e-6)
+    np.testing.assert_allclose(O.dis_sgd_hausdorff(g["ka"], g["kb"]), g["k_sgd"], rtol=1e-6)
+    np.testing.assert_allclose(O.dis_bid_hausdorff(g["ka"], g["kb"]), g["k_bid"], rtol=1e-6)
+
+
+def test_a1_dis_utils_torch():
+    g = load_golden("a1_dis_utils_torch")
+    a, b = g["a"], g["b"]
+    M = O.dis_pairwise_distances(a[:, :, :96], b[:, :, :80])
+    # torch's vectorised CPU sqrt is not correctly rounded (99.4 % of lanes): <= 1 ulp
+    assert np.abs(M - g["pairwise_distances"]).max() <= 1.2e-7 * np.abs(M).max()
+    assert (M == g["pairwise_distances"]).mean() > 0.98
+    np.testing.assert_allclose(O.dis_chamfer(a, b), g["chamfer"], rtol=2e-6)
+    np.testing.assert_allclose(O.dis_sgd_hausdorff(a, b), g["sgd_hausdorff_dis"], rtol=2e-7)
+    np.testing.assert_allclose(O.dis_bid_hausdorff(a, b), g["bid_hausdorff_dis"], rtol=2e-7)
+
+
+@pytest.mark.parametrize("tag", ["face", "iter0", "ragged", "ties"])
+def test_a2_nn1_bit_exact(tag):
+    g = load_golden("a2_distance_" + tag)
+    r = O._nn1_cw(g["preds"], g["gts"])
+    assert np.array_equal(r.row_min, g["row_min"])
+    assert np.array_equal(r.col_min, g["col_min"])
+    assert np.array_equal(r.row_arg, g["row_arg"])       # lowest-index == torch.min(dim)
+    assert np.array_equal(r.col_arg, g["col_arg"])
+    if "P_block" in g:
+        P = O.batch_pairwise_dist(g["gts"], g["preds"])
+        assert np.array_equal(P[:, :64, :48], g["P_block"])
+
+
+@pytest.mark.parametrize("tag", ["face", "iter0", "ragged"])
+def test_a2_losses_and_grads(tag):
+    g = load_golden("a2_distance_" + tag)
+    l1, l2 = O.chamfer_distance(g["preds"], g["gts"])
+    np.testing.assert_allclose(l1, g["chamfer_l1"], rtol=2e-6, atol=1e-12)
+    np.testing.assert_allclose(l2, g["chamfer_l2"], rtol=2e-6, atol=1e-12)
+    h1, h2 = O.hausdorff_distance(g["preds"], g["gts"])
+    assert np.array_equal(h1, g["hausdorff_l1"]) and np.array_equal(h2, g["hausdorff_l2"])
+    if tag == "iter0":
+        return   # |adv-ori| ~ 1e-7: the reference's own fp32 gradient is rounding noise there
+    gp, gg = O.chamfer_distance_grads(g["preds"], g["gts"], g["g1"], g["g2"])
+    assert rel_inf(g["chamfer_gp"], gp) < 1e-5 and rel_inf(g["chamfer_gg"], gg) < 1e-5
+    gp, gg = O.hausdorff_distance_grads(g["preds"], g["gts"], g["g1"], g["g2"])
+    assert rel_inf(g["hausdorff_gp"], gp) < 1e-5 and rel_inf(g["hausdorff_gg"], gg) < 1e-5
+
+
+def test_a2_set_distance_variant():
+    g = load_golden("a2_set_distance")
+    l1, l2 = O.chamfer_distance(g["preds"], g["gts"])
+    np.testing.assert_allclose((l1 + l2) / 2, g["chamfer"], rtol=2e-6)
+    h1, h2 = O.hausdorff_distance(g["preds"], g["gts"])
+    np.testing.assert_allclose((h1 + h2) / 2, g["hausdorff"], rtol=1e-7)
+
+
+def assert_idx_equal_up_to_ties(idx, ref_idx, dists, matrix):
+    """torch.topk does not break exact-distance ties by lowest index (the real face scans sit
+    on a pixel grid, so exact ties occur); inside a group of equal distances the reference's
+    choice is arbitrary.  Contract: the reference's picks have bit-identical distances at every
+    rank, and wherever the two differ our pick is the lower index."""
+    ref_d = np.take_along_axis(matrix, ref_idx.astype(np.int64), axis=2)
+    assert np.array_equal(ref_d, dists)
+    diff = idx != ref_idx
+    assert diff.mean() < 0.01
+    for b, r, c in np.argwhere(diff):
+        tied = dists[b, r] == dists[b, r, c]
+        lo = np.flatnonzero(matrix[b, r] == dists[b, r, c])
+        assert sorted(idx[b, r][tied]) == sorted(lo[:tied.sum()])      # ours = lowest indices
+
+
+def test_a3_knn_points():
+    g = load_golden("a3_knn_utils")
+    for tag, p1, p2, K in (("cross1", g["adv"], g["ori"], 1), ("self17", g["adv"], g["adv"], 17),
+                           ("cross4", g["ori"], g["adv"], 4)):
+        d, i = O.knn_points(p1, p2, K)
+        assert np.array_equal(d, g[tag + "_dists"]), tag
+        assert_idx_equal_up_to_ties(i, g[tag + "_idx"], d, O.knn_points_matrix(p1, p2))
+        assert np.array_equal(O.knn_gather(p2, g[tag + "_idx"]), g[tag + "_nn"])
+    assert np.array_equal(O.knn_gather(g["gather_x"], g["self17_idx"]), g["gather_out"])
+    with pytest.raises(RuntimeError):
+        O.knn_points(g["adv"][:, :100], g["ori"][:, :90], 1)
+
+
+def test_a5_knn_dist():
+    g = load_golden("l3_dist_utils")
+    for k in (5, 16):
+        loss, _, _ = O.knn_dist_loss(g["adv"], k=k, alpha=1.05)
+        np.testing.assert_allclose(loss * g["weights"], g[f"KNNDist_k{k}"], rtol=3e-6)
+
+
+def test_a6_knn_graph():
+    g = load_golden("a6_knn_graph")
+    pm = O._cf_to_pm(g["x3"]); nrm = O.norms(O.NORM_MULSUM, pm)
+    mat = -O.dgcnn_neg_matrix(g["x3"])
+    d20, i20 = O.knn(O.FORM_COL_ROW, pm, pm, nrm, nrm, 20)
+    d21, i21 = O.knn(O.FORM_COL_ROW, pm, pm, nrm, nrm, 21)
+    assert np.array_equal(i20, O.dgcnn_knn(g["x3"], 20))
+    assert_idx_equal_up_to_ties(i20, g["dgcnn_k20"], d20, mat)
+    assert_idx_equal_up_to_ties(i21, g["curvenet_k20"], d21, mat)          # CurveNet asks for k+1
+    assert_idx_equal_up_to_ties(i20, g["curvenet_normal_k20"], d20, mat)
+    # C = 64: the reference's GEMM / sum order is library-blocked (not sequential); indices
+    # still agree on generic data because top-k gaps dwarf the 1e-5 rounding differences.
+    assert (O.dgcnn_knn(g["f64"], 20) == g["dgcnn_f64_k20"]).mean() > 0.999
+
+
+def test_a7_pointnet2_utils():
+    g = load_golden("a7_pointnet2_utils")
+    xyz, new_xyz = g["xyz"], g["new_xyz"]
+    assert np.array_equal(O.square_distance(new_xyz[:, :64], xyz[:, :96]), g["sqdist_block"])
+    assert np.array_equal(O.query_ball_point(0.2, 32, xyz, new_xyz), g["ball_r02_n32"])
+    assert np.array_equal(O.query_ball_point(0.4, 64, xyz[:, :512], new_xyz[:, :128]), g["ball_r04_n64"])
+    assert np.array_equal(O.query_ball_point(0.02, 8, xyz, new_xyz[:, :64]), g["ball_r002_n8"])
+
+
+def test_topk_tie_rule_is_lowest_index():
+    # torch.topk is not lowest-index on ties (SURVEY.md section 7 hard part 4); the oracle is.
+    pc = np.zeros((1, 6, 3), np.float32)
+    pc[0, :, 0] = [0, 1, 1, 1, 5, 1]
+    d, i = O.knn(O.FORM_COL_ROW, pc, pc, O.norms(0, pc), O.norms(0, pc), 3)
+    assert i[0, 0].tolist() == [0, 1, 2]
+    assert i[0, 1].tolist() == [1, 2, 3]
