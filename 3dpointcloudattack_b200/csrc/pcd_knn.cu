@@ -1,0 +1,622 @@
+// pcd_knn.cu -- k-NN select sweep and ordered ball query for sm_100a.
+//
+// k-NN (pcd_knn_forward): every warp owns RQ query rows; its 32 lanes sweep the candidate
+// columns of a shared-memory tile (TMA bulk copies for xyz clouds, channel-chunked tiles for
+// C-channel DGCNN features).  Candidates that beat the row's current K-th distance are
+// ballot-compacted into a per-row staging buffer; each time 32 are staged they are bitonic
+// sorted across the warp and merged into the row's sorted top-K list, which lives in
+// registers (one 64-bit (ordered distance, index) key per lane and list).  Keys order by
+// distance first and index second, so exact ties resolve to the LOWEST index (the stable
+// restatement of torch.topk the oracle uses).
+//
+// Reference semantics: attack/GeoA3/knn_utils.py:10-55, attack/CW/CW_utils/dist_utils.py:133-143,
+// model/dgcnn.py:194-200, model/curvenet_util.py:10-26, model/pointnet2_utils.py:84-104.
+#include "pcd_common.cuh"
+
+namespace pcd {
+
+constexpr int kKnnWarps = 8;
+constexpr int kKnnThreads = kKnnWarps * 32;
+constexpr int kKnnRQ = 4;          // query rows per warp
+constexpr int kKnnTile = 512;      // xyz candidates per TMA stage (16 B each)
+constexpr unsigned long long kEmptyKey = ~0ull;
+
+static inline size_t align_up_k(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ------------------------------------------------------------------ warp-level key sorting
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m) {
+    return __shfl_xor_sync(0xffffffffu, v, m);
+}
+__device__ __forceinline__ unsigned long long shfl_u64(unsigned long long v, int src) {
+    return __shfl_sync(0xffffffffu, v, src);
+}
+__device__ __forceinline__ unsigned long long umin64(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
+__device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsigned long long b) { return a < b ? b : a; }
+
+// full bitonic sort of one key per lane, ascending in lane order
+__device__ __forceinline__ unsigned long long warp_sort32(unsigned long long key, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const unsigned long long o = shfl_xor_u64(key, j);
+            const bool up = (lane & k) == 0 || k == 32;
+            const bool lower = (lane & j) == 0;
+            key = (lower == up) ? umin64(key, o) : umax64(key, o);
+        }
+    }
+    return key;
+}
+// sort a bitonic sequence (one key per lane) ascending
+__device__ __forceinline__ unsigned long long warp_bitonic_merge32(unsigned long long key, int lane) {
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) {
+        const unsigned long long o = shfl_xor_u64(key, j);
+        key = ((lane & j) == 0) ? umin64(key, o) : umax64(key, o);
+    }
+    return key;
+}
+
+// Merge an ascending run `s` (one key per lane) into the NL sorted lists of a row.
+template <int NL>
+__device__ __forceinline__ void merge_run(unsigned long long (&L)[NL], unsigned long long s, int lane) {
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        const unsigned long long rev = shfl_u64(s, 31 - lane);
+        const unsigned long long lo = umin64(L[l], rev);
+        const unsigned long long hi = umax64(L[l], rev);
+        L[l] = warp_bitonic_merge32(lo, lane);
+        if (l + 1 < NL) s = warp_bitonic_merge32(hi, lane);
+    }
+}
+
+__device__ __forceinline__ float key_threshold(unsigned long long kth) {
+    return kth == kEmptyKey ? __int_as_float(0x7f800000) : ordered_to_f32((uint32_t)(kth >> 32));
+}
+
+// Per-row select state shared by the xyz and the feature kernels.
+template <int NL>
+struct RowSelect {
+    unsigned long long L[NL];
+    float thr;
+    int cnt;
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int l = 0; l < NL; ++l) L[l] = kEmptyKey;
+        thr = __int_as_float(0x7f800000);
+        cnt = 0;
+    }
+    // stage the passing lanes of one 32-candidate step; merge when 32 are staged
+    __device__ __forceinline__ void offer(float d, int j, unsigned long long *buf, int lane, int K) {
+        const bool pass = d < thr;
+        const unsigned mask = __ballot_sync(0xffffffffu, pass);
+        if (mask == 0) return;
+        if (pass) buf[cnt + __popc(mask & ((1u << lane) - 1u))] = make_key(d, (uint32_t)j);
+        cnt += __popc(mask);
+        if (cnt >= 32) {
+            __syncwarp();
+            const unsigned long long run = warp_sort32(buf[lane], lane);
+            merge_run<NL>(L, run, lane);
+            const int rem = cnt - 32;
+            const unsigned long long carry = (lane < rem) ? buf[32 + lane] : kEmptyKey;
+            __syncwarp();
+            if (lane < rem) buf[lane] = carry;
+            cnt = rem;
+            unsigned long long kl = L[0];
+#pragma unroll
+            for (int l = 1; l < NL; ++l)
+                if (((K - 1) >> 5) == l) kl = L[l];
+            thr = key_threshold(shfl_u64(kl, (K - 1) & 31));
+            __syncwarp();
+        }
+    }
+    __device__ __forceinline__ void finish(unsigned long long *buf, int lane) {
+        __syncwarp();
+        if (cnt > 0) {
+            const unsigned long long run = warp_sort32(lane < cnt ? buf[lane] : kEmptyKey, lane);
+            merge_run<NL>(L, run, lane);
+            cnt = 0;
+        }
+        __syncwarp();
+    }
+    __device__ __forceinline__ void store(float *dists, int32_t *idx, size_t base, int lane, int K) const {
+#pragma unroll
+        for (int l = 0; l < NL; ++l) {
+            const int k = l * 32 + lane;
+            if (k < K) {
+                if (dists) dists[base + k] = ordered_to_f32((uint32_t)(L[l] >> 32));
+                idx[base + k] = (int32_t)(uint32_t)L[l];
+            }
+        }
+    }
+};
+
+// -------------------------------------------------------------------------- prep (xyz clouds)
+// rowq[b][i] = (-2x,-2y,-2z,nrow)   colq[b][j] = (x,y,z,ncol)   padded points inert (n = +inf)
+__global__ void knn3_prep_kernel(const float *__restrict__ rows, int64_t r_sb, int64_t r_sp, int64_t r_sc,
+                                 const float *__restrict__ cols, int64_t c_sb, int64_t c_sp, int64_t c_sc,
+                                 int B, int N, int M, int Npad, int Mpad, int norm_kind, int swap_norms,
+                                 float4 *__restrict__ rowq, float4 *__restrict__ colq) {
+    const long long per_b = (long long)Npad + Mpad;
+    const long long total = per_b * B;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(t / per_b);
+        const int p = (int)(t - (long long)b * per_b);
+        const bool is_row = p < Npad;
+        const int i = is_row ? p : p - Npad;
+        const int n_own = is_row ? N : M;
+        float x = 0.f, y = 0.f, z = 0.f, n = __int_as_float(0x7f800000);
+        if (i < n_own) {
+            const float *s = is_row ? rows + b * r_sb + i * r_sp : cols + b * c_sb + i * c_sp;
+            const int64_t sc = is_row ? r_sc : c_sc;
+            x = s[0]; y = s[sc]; z = s[2 * sc];
+            if (swap_norms) {
+                const float *o = is_row ? cols + b * c_sb + i * c_sp : rows + b * r_sb + i * r_sp;
+                const int64_t oc = is_row ? c_sc : r_sc;
+                n = sq_norm3(norm_kind, o[0], o[oc], o[2 * oc]);
+            } else {
+                n = sq_norm3(norm_kind, x, y, z);
+            }
+        }
+        if (is_row) rowq[(size_t)b * Npad + i] = make_float4(-2.f * x, -2.f * y, -2.f * z, n);
+        else colq[(size_t)b * Mpad + i] = make_float4(x, y, z, n);
+    }
+}
+
+// ------------------------------------------------------------------------- xyz k-NN kernel
+struct Knn3Smem {
+    float4 tile[2][kKnnTile];                              // 2 x 8 KB candidate tiles (TMA)
+    unsigned long long stage[kKnnWarps][kKnnRQ][64];       // 16 KB staging buffers
+    uint64_t full[2];
+};
+
+template <int FORM, int NL>
+__global__ void __launch_bounds__(kKnnThreads)
+knn3_kernel(const float4 *__restrict__ rowq, const float4 *__restrict__ colq, int N, int M, int Npad, int Mpad,
+            int K, float *__restrict__ dists, int32_t *__restrict__ idx) {
+    __shared__ __align__(128) Knn3Smem sm;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y;
+    const int row0 = (blockIdx.x * kKnnWarps + warp) * kKnnRQ;
+    const int ntiles = (M + kKnnTile - 1) / kKnnTile;
+    const float4 *src = colq + (size_t)b * Mpad;
+    const uint32_t tile_bytes = kKnnTile * 16u;
+
+    if (tid == 0) {
+        mbar_init(&sm.full[0], 1);
+        mbar_init(&sm.full[1], 1);
+        fence_mbar_init();
+        fence_proxy_async();
+        mbar_expect_tx(&sm.full[0], tile_bytes);
+        tma_load_1d(sm.tile[0], src, tile_bytes, &sm.full[0]);
+        if (ntiles > 1) {
+            mbar_expect_tx(&sm.full[1], tile_bytes);
+            tma_load_1d(sm.tile[1], src + kKnnTile, tile_bytes, &sm.full[1]);
+        }
+    }
+    __syncthreads();
+
+    float4 q[kKnnRQ];
+    RowSelect<NL> sel[kKnnRQ];
+#pragma unroll
+    for (int r = 0; r < kKnnRQ; ++r) {
+        q[r] = __ldg(&rowq[(size_t)b * Npad + row0 + r]);   // rows are padded to a multiple of 32 per CTA
+        sel[r].init();
+    }
+
+    for (int t = 0; t < ntiles; ++t) {
+        const int buf = t & 1;
+        mbar_wait(&sm.full[buf], (t >> 1) & 1);
+        const float4 *tile = sm.tile[buf];
+        const int jbase = t * kKnnTile;
+#pragma unroll 2
+        for (int s = 0; s < kKnnTile / 32; ++s) {
+            const float4 c = tile[s * 32 + lane];
+            const int j = jbase + s * 32 + lane;
+#pragma unroll
+            for (int r = 0; r < kKnnRQ; ++r) {
+                const float d = pair_dist_scalar<FORM>(q[r].x, q[r].y, q[r].z, q[r].w, c.x, c.y, c.z, c.w);
+                sel[r].offer(d, j, sm.stage[warp][r], lane, K);
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && t + 2 < ntiles) {
+            mbar_expect_tx(&sm.full[buf], tile_bytes);
+            tma_load_1d(sm.tile[buf], src + (size_t)(t + 2) * kKnnTile, tile_bytes, &sm.full[buf]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < kKnnRQ; ++r) {
+        sel[r].finish(sm.stage[warp][r], lane);
+        const int i = row0 + r;
+        if (i < N) sel[r].store(dists, idx, ((size_t)b * N + i) * K, lane, K);
+    }
+}
+
+// ------------------------------------------------------------- C-channel (feature) k-NN
+// Workspace: rowf[b][Npad][C] (= -2 * feature), rown[b][Npad], colT[b][C][Mpad] (channel-major so
+// that a lane reads consecutive candidates), coln[b][Mpad].
+__global__ void knnc_prep_kernel(const float *__restrict__ rows, int64_t r_sb, int64_t r_sp, int64_t r_sc,
+                                 const float *__restrict__ cols, int64_t c_sb, int64_t c_sp, int64_t c_sc,
+                                 int B, int N, int M, int C, int Npad, int Mpad, int norm_kind, int swap_norms,
+                                 float *__restrict__ rowf, float *__restrict__ rown,
+                                 float *__restrict__ colT, float *__restrict__ coln) {
+    const long long per_b = (long long)Npad + Mpad;
+    const long long total = per_b * B;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(t / per_b);
+        const int p = (int)(t - (long long)b * per_b);
+        const bool is_row = p < Npad;
+        const int i = is_row ? p : p - Npad;
+        const int n_own = is_row ? N : M;
+        const bool live = i < n_own;
+        const float *own = is_row ? rows + b * r_sb + i * r_sp : cols + b * c_sb + i * c_sp;
+        const int64_t osc = is_row ? r_sc : c_sc;
+        const float *nsrc = own;
+        int64_t nsc = osc;
+        if (swap_norms) {
+            nsrc = is_row ? cols + b * c_sb + i * c_sp : rows + b * r_sb + i * r_sp;
+            nsc = is_row ? c_sc : r_sc;
+        }
+        float n = __int_as_float(0x7f800000);
+        if (live) {
+            const float v0 = nsrc[0];
+            n = __fmul_rn(v0, v0);
+            for (int k = 1; k < C; ++k) {
+                const float v = nsrc[k * nsc];
+                n = (norm_kind == PCD_NORM_FMA) ? __fmaf_rn(v, v, n) : __fadd_rn(n, __fmul_rn(v, v));
+            }
+        }
+        if (is_row) {
+            for (int k = 0; k < C; ++k) rowf[((size_t)b * Npad + i) * C + k] = live ? -2.f * own[k * osc] : 0.f;
+            rown[(size_t)b * Npad + i] = n;
+        } else {
+            for (int k = 0; k < C; ++k) colT[((size_t)b * C + k) * Mpad + i] = live ? own[k * osc] : 0.f;
+            coln[(size_t)b * Mpad + i] = n;
+        }
+    }
+}
+
+constexpr int kKncTile = 64;   // candidates per step (2 per lane)
+
+template <int NL>
+__global__ void __launch_bounds__(kKnnThreads)
+knnc_kernel(const float *__restrict__ rowf, const float *__restrict__ rown, const float *__restrict__ colT,
+            const float *__restrict__ coln, int N, int M, int C, int Npad, int Mpad, int K, int form,
+            float *__restrict__ dists, int32_t *__restrict__ idx) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // layout: qs[warps][C][RQ] | ct[C][64] | cn[64] | stage[warps][RQ][64] u64
+    float *qs = reinterpret_cast<float *>(smem_raw);
+    float *ct = qs + kKnnWarps * C * kKnnRQ;
+    float *cn = ct + C * kKncTile;
+    unsigned long long *stage = reinterpret_cast<unsigned long long *>(cn + kKncTile);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y;
+    const int row0 = (blockIdx.x * kKnnWarps + warp) * kKnnRQ;
+
+    float *myq = qs + warp * C * kKnnRQ;
+    for (int e = lane; e < C * kKnnRQ; e += 32) {
+        const int k = e / kKnnRQ, r = e - k * kKnnRQ;
+        myq[e] = rowf[((size_t)b * Npad + row0 + r) * C + k];
+    }
+    float qn[kKnnRQ];
+    RowSelect<NL> sel[kKnnRQ];
+#pragma unroll
+    for (int r = 0; r < kKnnRQ; ++r) {
+        qn[r] = rown[(size_t)b * Npad + row0 + r];
+        sel[r].init();
+    }
+    unsigned long long *mystage = stage + (size_t)warp * kKnnRQ * 64;
+
+    const float *cbase = colT + (size_t)b * C * Mpad;
+    for (int j0 = 0; j0 < M; j0 += kKncTile) {
+        __syncthreads();
+        for (int e = tid; e < C * kKncTile; e += kKnnThreads) {
+            const int k = e / kKncTile, jj = e - k * kKncTile;
+            ct[e] = cbase[(size_t)k * Mpad + j0 + jj];
+        }
+        if (tid < kKncTile) cn[tid] = coln[(size_t)b * Mpad + j0 + tid];
+        __syncthreads();
+
+        float acc0[kKnnRQ], acc1[kKnnRQ];
+        {
+            const float4 q4 = *reinterpret_cast<const float4 *>(myq);
+            const float c0 = ct[lane], c1 = ct[32 + lane];
+            acc0[0] = __fmul_rn(q4.x, c0); acc0[1] = __fmul_rn(q4.y, c0); acc0[2] = __fmul_rn(q4.z, c0); acc0[3] = __fmul_rn(q4.w, c0);
+            acc1[0] = __fmul_rn(q4.x, c1); acc1[1] = __fmul_rn(q4.y, c1); acc1[2] = __fmul_rn(q4.z, c1); acc1[3] = __fmul_rn(q4.w, c1);
+        }
+#pragma unroll 4
+        for (int k = 1; k < C; ++k) {
+            const float4 q4 = *reinterpret_cast<const float4 *>(myq + k * kKnnRQ);
+            const float c0 = ct[k * kKncTile + lane], c1 = ct[k * kKncTile + 32 + lane];
+            acc0[0] = __fmaf_rn(q4.x, c0, acc0[0]); acc0[1] = __fmaf_rn(q4.y, c0, acc0[1]);
+            acc0[2] = __fmaf_rn(q4.z, c0, acc0[2]); acc0[3] = __fmaf_rn(q4.w, c0, acc0[3]);
+            acc1[0] = __fmaf_rn(q4.x, c1, acc1[0]); acc1[1] = __fmaf_rn(q4.y, c1, acc1[1]);
+            acc1[2] = __fmaf_rn(q4.z, c1, acc1[2]); acc1[3] = __fmaf_rn(q4.w, c1, acc1[3]);
+        }
+        const float n0 = cn[lane], n1 = cn[32 + lane];
+#pragma unroll
+        for (int r = 0; r < kKnnRQ; ++r) {
+            float d0, d1;
+            if (form == PCD_FORM_ROW_COL) {
+                d0 = __fadd_rn(__fadd_rn(acc0[r], qn[r]), n0); d1 = __fadd_rn(__fadd_rn(acc1[r], qn[r]), n1);
+            } else if (form == PCD_FORM_COL_ROW) {
+                d0 = __fadd_rn(__fadd_rn(acc0[r], n0), qn[r]); d1 = __fadd_rn(__fadd_rn(acc1[r], n1), qn[r]);
+            } else {
+                d0 = __fadd_rn(__fadd_rn(qn[r], n0), acc0[r]); d1 = __fadd_rn(__fadd_rn(qn[r], n1), acc1[r]);
+            }
+            sel[r].offer(d0, j0 + lane, mystage + r * 64, lane, K);
+            sel[r].offer(d1, j0 + 32 + lane, mystage + r * 64, lane, K);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < kKnnRQ; ++r) {
+        sel[r].finish(mystage + r * 64, lane);
+        const int i = row0 + r;
+        if (i < N) sel[r].store(dists, idx, ((size_t)b * N + i) * K, lane, K);
+    }
+}
+
+// ------------------------------------------------------------------------ k-NN backward
+// dists[b,i,k] = d(i, j=idx[b,i,k]) ; own-index terms with plain stores, partner terms with
+// atomics (same two-pass scheme as the NN-1 backward).
+struct KnnBwdArgs {
+    const float *rows; int64_t r_sb, r_sp, r_sc;
+    const float *cols; int64_t c_sb, c_sp, c_sc;
+    int B, N, M, K, swap_norms;
+    const int32_t *idx; const float *g;
+    float *grad_rows; int64_t gr_sb, gr_sp, gr_sc;
+    float *grad_cols; int64_t gc_sb, gc_sp, gc_sc;
+};
+
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) knn_bwd_kernel(KnnBwdArgs a) {
+    const long long total = (long long)a.B * (a.N + a.M);
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(t / (a.N + a.M));
+        const int p = (int)(t - (long long)b * (a.N + a.M));
+        const float *rb = a.rows + b * a.r_sb, *cb = a.cols + b * a.c_sb;
+        if (p < a.N) {
+            const int i = p;
+            const float rx = rb[i * a.r_sp], ry = rb[i * a.r_sp + a.r_sc], rz = rb[i * a.r_sp + 2 * a.r_sc];
+            float ox = 0.f, oy = 0.f, oz = 0.f, gsum = 0.f;
+            for (int k = 0; k < a.K; ++k) {
+                const size_t e = ((size_t)b * a.N + i) * a.K + k;
+                const float g2 = 2.f * a.g[e];
+                const int j = a.idx[e];
+                const float cx = cb[j * a.c_sp], cy = cb[j * a.c_sp + a.c_sc], cz = cb[j * a.c_sp + 2 * a.c_sc];
+                gsum += g2;
+                if (!SCATTER) {
+                    if (a.swap_norms) { ox -= g2 * cx; oy -= g2 * cy; oz -= g2 * cz; }
+                    else { ox += g2 * (rx - cx); oy += g2 * (ry - cy); oz += g2 * (rz - cz); }
+                } else if (g2 != 0.f) {
+                    if (a.grad_cols) {
+                        float *gp = a.grad_cols + b * a.gc_sb + j * a.gc_sp;
+                        if (a.swap_norms) {
+                            atomicAdd(gp, -g2 * rx); atomicAdd(gp + a.gc_sc, -g2 * ry); atomicAdd(gp + 2 * a.gc_sc, -g2 * rz);
+                        } else {
+                            atomicAdd(gp, -g2 * (rx - cx)); atomicAdd(gp + a.gc_sc, -g2 * (ry - cy));
+                            atomicAdd(gp + 2 * a.gc_sc, -g2 * (rz - cz));
+                        }
+                    }
+                    if (a.swap_norms && a.grad_rows) {   // |rows_j|^2 term
+                        const float jx = rb[j * a.r_sp], jy = rb[j * a.r_sp + a.r_sc], jz = rb[j * a.r_sp + 2 * a.r_sc];
+                        float *gp = a.grad_rows + b * a.gr_sb + j * a.gr_sp;
+                        atomicAdd(gp, g2 * jx); atomicAdd(gp + a.gr_sc, g2 * jy); atomicAdd(gp + 2 * a.gr_sc, g2 * jz);
+                    }
+                }
+            }
+            if (!SCATTER && a.grad_rows) {
+                float *gp = a.grad_rows + b * a.gr_sb + i * a.gr_sp;
+                gp[0] = ox; gp[a.gr_sc] = oy; gp[2 * a.gr_sc] = oz;
+            }
+        } else if (!SCATTER && a.grad_cols) {
+            // own-index term of a column point: only the swapped-norm |cols_i|^2 term (N == M)
+            const int j = p - a.N;
+            float ox = 0.f, oy = 0.f, oz = 0.f;
+            if (a.swap_norms) {
+                float gsum = 0.f;
+                for (int k = 0; k < a.K; ++k) gsum += 2.f * a.g[((size_t)b * a.N + j) * a.K + k];
+                ox = gsum * cb[j * a.c_sp]; oy = gsum * cb[j * a.c_sp + a.c_sc]; oz = gsum * cb[j * a.c_sp + 2 * a.c_sc];
+            }
+            float *gp = a.grad_cols + b * a.gc_sb + j * a.gc_sp;
+            gp[0] = ox; gp[a.gc_sc] = oy; gp[2 * a.gc_sc] = oz;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ ball query
+// One warp per query row; lanes sweep 32 columns per step in ascending index order and
+// ballot-compact the hits, so the output is already ordered and the sweep stops as soon as
+// nsample hits are found (the reference sorts all N indices per row instead).
+__global__ void __launch_bounds__(256)
+ball_query_kernel(const float *__restrict__ xyz, int64_t x_sb, int64_t x_sp, int64_t x_sc,
+                  const float *__restrict__ qry, int64_t q_sb, int64_t q_sp, int64_t q_sc,
+                  int B, int N, int S, float r2, int nsample, int32_t *__restrict__ idx) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < (long long)B * S; w += warps) {
+        const int b = (int)(w / S), i = (int)(w - (long long)b * S);
+        const float *qp = qry + b * q_sb + i * q_sp;
+        const float qx = qp[0], qy = qp[q_sc], qz = qp[2 * q_sc];
+        const float qn = sq_norm3(PCD_NORM_MULSUM, qx, qy, qz);
+        const float mx = -2.f * qx, my = -2.f * qy, mz = -2.f * qz;
+        int32_t *out = idx + ((size_t)b * S + i) * nsample;
+        int cnt = 0, first = N;
+        for (int j0 = 0; j0 < N && cnt < nsample; j0 += 32) {
+            const int j = j0 + lane;
+            bool hit = false;
+            if (j < N) {
+                const float *cp = xyz + b * x_sb + j * x_sp;
+                const float cx = cp[0], cy = cp[x_sc], cz = cp[2 * x_sc];
+                const float d = pair_dist_scalar<PCD_FORM_ROW_COL>(mx, my, mz, qn, cx, cy, cz,
+                                                                   sq_norm3(PCD_NORM_MULSUM, cx, cy, cz));
+                hit = !(d > r2);
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, hit);
+            if (mask) {
+                if (cnt == 0) first = j0 + __ffs(mask) - 1;
+                const int pos = cnt + __popc(mask & ((1u << lane) - 1u));
+                if (hit && pos < nsample) out[pos] = j;
+                cnt += __popc(mask);
+            }
+        }
+        for (int s = (cnt < nsample ? cnt : nsample) + lane; s < nsample; s += 32) out[s] = first;
+    }
+}
+
+struct KnnLayout {
+    int Npad, Mpad;
+    size_t a, b, c, d, total;   // xyz: a=rowq, b=colq ; features: a=rowf b=rown c=colT d=coln
+};
+static KnnLayout knn_layout(int B, int N, int M, int C) {
+    KnnLayout L;
+    L.Npad = (int)align_up_k((size_t)N, kKnnWarps * kKnnRQ);
+    size_t off = 0;
+    if (C == 3) {
+        L.Mpad = (int)align_up_k((size_t)M, kKnnTile);
+        L.a = off; off = align_up_k(off + (size_t)B * L.Npad * 16, 256);
+        L.b = off; off = align_up_k(off + (size_t)B * L.Mpad * 16, 256);
+        L.c = L.d = off;
+    } else {
+        L.Mpad = (int)align_up_k((size_t)M, kKncTile);
+        L.a = off; off = align_up_k(off + (size_t)B * L.Npad * C * 4, 256);
+        L.b = off; off = align_up_k(off + (size_t)B * L.Npad * 4, 256);
+        L.c = off; off = align_up_k(off + (size_t)B * L.Mpad * C * 4, 256);
+        L.d = off; off = align_up_k(off + (size_t)B * L.Mpad * 4, 256);
+    }
+    L.total = off;
+    return L;
+}
+
+}  // namespace pcd
+
+using namespace pcd;
+
+extern "C" size_t pcd_knn_workspace_bytes(int B, int N, int M, int C, int K) {
+    (void)K;
+    if (B <= 0 || N <= 0 || M <= 0 || C <= 0) return 0;
+    return knn_layout(B, N, M, C).total;
+}
+
+extern "C" int pcd_knn_forward(const float *rows, int64_t r_sb, int64_t r_sp, int64_t r_sc,
+                               const float *cols, int64_t c_sb, int64_t c_sp, int64_t c_sc,
+                               int B, int N, int M, int C, int K, int form, int norm_kind, int swap_norms,
+                               float *dists, int32_t *idx, void *workspace, size_t workspace_bytes, void *stream) {
+    if (!rows || !cols || !idx || !workspace) {
+        set_error("pcd_knn_forward: NULL pointer argument");
+        return PCD_ERR_ARG;
+    }
+    if (B <= 0 || N <= 0 || M <= 0 || form < 0 || form > 2 || norm_kind < 0 || norm_kind > 1 || B > 65535) {
+        set_error("pcd_knn_forward: bad argument B=%d N=%d M=%d form=%d norm=%d", B, N, M, form, norm_kind);
+        return PCD_ERR_ARG;
+    }
+    if (K < 1 || K > M || K > PCD_KNN_MAX_K || C < 1 || C > PCD_KNN_MAX_C) {
+        set_error("pcd_knn_forward: unsupported K=%d (1..min(M,%d)) or C=%d (1..%d)", K, PCD_KNN_MAX_K, C, PCD_KNN_MAX_C);
+        return PCD_ERR_UNSUPPORTED;
+    }
+    if (swap_norms && N != M) {
+        set_error("pcd_knn_forward: swap_norms requires N == M");
+        return PCD_ERR_ARG;
+    }
+    const KnnLayout L = knn_layout(B, N, M, C);
+    if (workspace_bytes < L.total) {
+        set_error("pcd_knn_forward: workspace %zu < required %zu bytes", workspace_bytes, L.total);
+        return PCD_ERR_WORKSPACE;
+    }
+    int dev = 0, sms = 0;
+    PCD_CUDA_CHECK(cudaGetDevice(&dev));
+    PCD_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    cudaStream_t st = (cudaStream_t)stream;
+    char *ws = (char *)workspace;
+    const long long total = (long long)B * (L.Npad + L.Mpad);
+    const int pgrid = (int)((total + 255) / 256 < (long long)sms * 8 ? (total + 255) / 256 : (long long)sms * 8);
+    const dim3 grid(L.Npad / (kKnnWarps * kKnnRQ), B);
+    const int NL = (K + 31) / 32;
+    if (C == 3) {
+        float4 *rowq = (float4 *)(ws + L.a), *colq = (float4 *)(ws + L.b);
+        knn3_prep_kernel<<<pgrid, 256, 0, st>>>(rows, r_sb, r_sp, r_sc, cols, c_sb, c_sp, c_sc, B, N, M, L.Npad, L.Mpad,
+                                                norm_kind, swap_norms, rowq, colq);
+        PCD_CUDA_CHECK(cudaGetLastError());
+#define PCD_LAUNCH_KNN3(F)                                                                                        \
+    do {                                                                                                          \
+        if (NL == 1) knn3_kernel<F, 1><<<grid, kKnnThreads, 0, st>>>(rowq, colq, N, M, L.Npad, L.Mpad, K, dists, idx); \
+        else knn3_kernel<F, 2><<<grid, kKnnThreads, 0, st>>>(rowq, colq, N, M, L.Npad, L.Mpad, K, dists, idx);    \
+    } while (0)
+        if (form == PCD_FORM_ROW_COL) PCD_LAUNCH_KNN3(PCD_FORM_ROW_COL);
+        else if (form == PCD_FORM_COL_ROW) PCD_LAUNCH_KNN3(PCD_FORM_COL_ROW);
+        else PCD_LAUNCH_KNN3(PCD_FORM_SUM_FIRST);
+#undef PCD_LAUNCH_KNN3
+        PCD_CUDA_CHECK(cudaGetLastError());
+    } else {
+        float *rowf = (float *)(ws + L.a), *rown = (float *)(ws + L.b);
+        float *colT = (float *)(ws + L.c), *coln = (float *)(ws + L.d);
+        knnc_prep_kernel<<<pgrid, 256, 0, st>>>(rows, r_sb, r_sp, r_sc, cols, c_sb, c_sp, c_sc, B, N, M, C, L.Npad,
+                                                L.Mpad, norm_kind, swap_norms, rowf, rown, colT, coln);
+        PCD_CUDA_CHECK(cudaGetLastError());
+        const size_t smem = (size_t)kKnnWarps * C * kKnnRQ * 4 + (size_t)C * kKncTile * 4 + kKncTile * 4 +
+                            (size_t)kKnnWarps * kKnnRQ * 64 * 8;
+        if (NL == 1) {
+            PCD_CUDA_CHECK(cudaFuncSetAttribute(knnc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            knnc_kernel<1><<<grid, kKnnThreads, smem, st>>>(rowf, rown, colT, coln, N, M, C, L.Npad, L.Mpad, K, form, dists, idx);
+        } else {
+            PCD_CUDA_CHECK(cudaFuncSetAttribute(knnc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            knnc_kernel<2><<<grid, kKnnThreads, smem, st>>>(rowf, rown, colT, coln, N, M, C, L.Npad, L.Mpad, K, form, dists, idx);
+        }
+        PCD_CUDA_CHECK(cudaGetLastError());
+    }
+    return PCD_OK;
+}
+
+extern "C" int pcd_knn_backward(const float *rows, int64_t r_sb, int64_t r_sp, int64_t r_sc,
+                                const float *cols, int64_t c_sb, int64_t c_sp, int64_t c_sc,
+                                int B, int N, int M, int K, int swap_norms, const int32_t *idx, const float *g_dists,
+                                float *grad_rows, int64_t gr_sb, int64_t gr_sp, int64_t gr_sc,
+                                float *grad_cols, int64_t gc_sb, int64_t gc_sp, int64_t gc_sc, void *stream) {
+    if (!rows || !cols || !idx || !g_dists || B <= 0 || N <= 0 || M <= 0 || K <= 0) {
+        set_error("pcd_knn_backward: bad argument");
+        return PCD_ERR_ARG;
+    }
+    if (swap_norms && N != M) {
+        set_error("pcd_knn_backward: swap_norms requires N == M");
+        return PCD_ERR_ARG;
+    }
+    if (!grad_rows && !grad_cols) return PCD_OK;
+    int dev = 0, sms = 0;
+    PCD_CUDA_CHECK(cudaGetDevice(&dev));
+    PCD_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    KnnBwdArgs a{rows, r_sb, r_sp, r_sc, cols, c_sb, c_sp, c_sc, B, N, M, K, swap_norms, idx, g_dists,
+                 grad_rows, gr_sb, gr_sp, gr_sc, grad_cols, gc_sb, gc_sp, gc_sc};
+    const long long total = (long long)B * (N + M);
+    const long long want = (total + 255) / 256;
+    const int grid = (int)(want < (long long)sms * 16 ? want : (long long)sms * 16);
+    cudaStream_t st = (cudaStream_t)stream;
+    knn_bwd_kernel<false><<<grid, 256, 0, st>>>(a);
+    PCD_CUDA_CHECK(cudaGetLastError());
+    knn_bwd_kernel<true><<<grid, 256, 0, st>>>(a);
+    PCD_CUDA_CHECK(cudaGetLastError());
+    return PCD_OK;
+}
+
+extern "C" int pcd_ball_query(const float *xyz, int64_t x_sb, int64_t x_sp, int64_t x_sc,
+                              const float *new_xyz, int64_t q_sb, int64_t q_sp, int64_t q_sc,
+                              int B, int N, int S, float radius2, int nsample, int32_t *idx, void *stream) {
+    if (!xyz || !new_xyz || !idx || B <= 0 || N <= 0 || S <= 0 || nsample <= 0) {
+        set_error("pcd_ball_query: bad argument");
+        return PCD_ERR_ARG;
+    }
+    int dev = 0, sms = 0;
+    PCD_CUDA_CHECK(cudaGetDevice(&dev));
+    PCD_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const long long rows = (long long)B * S;
+    const long long want = (rows + 7) / 8;
+    const int grid = (int)(want < (long long)sms * 8 ? want : (long long)sms * 8);
+    ball_query_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(xyz, x_sb, x_sp, x_sc, new_xyz, q_sb, q_sp, q_sc, B, N, S,
+                                                             radius2, nsample, idx);
+    PCD_CUDA_CHECK(cudaGetLastError());
+    return PCD_OK;
+}

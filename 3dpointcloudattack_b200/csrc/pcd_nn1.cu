@@ -1,0 +1,675 @@
+// pcd_nn1.cu -- NN-1 sweep (Chamfer / Hausdorff / knn_points K=1) for sm_100a.
+//
+// Pipeline of pcd_nn1_forward (4 launches on the caller's stream, no host sync):
+//   1. nn1_prep    pack both clouds into the sweep layout, compute |p|^2 in the reference's
+//                  rounding order, reset the (value,tag) keys.
+//   2. nn1_sweep   THE hot kernel: every (row i, col j) distance exactly once; row minima and
+//                  column minima are both taken from the same tile sweep.  Packed fp32x2
+//                  math (FMUL2/FFMA2/FADD2), FMNMX3 running minima, CREDUX warp minima,
+//                  column tiles streamed by 1-D TMA bulk copies behind an mbarrier, stream-K
+//                  partition of (sample, row tile, col tile) units over a persistent grid.
+//                  Emits per point a 64-bit key = (ordered min value, tag of the 32-wide /
+//                  32R-wide chunk that produced it) with atomicMin.
+//   3. nn1_fixup   one warp per point re-evaluates its winning chunk (bit-identical
+//                  arithmetic) and ballots for the lowest index with d == min.
+//   4. nn1_reduce  per-sample sum / max / first-argmax of both minima arrays (fixed order).
+//
+// Reference semantics served: utils/dis_utils_torch.py:8-28, attack/CW/CW_utils/distance.py:15-70,
+// attack/GeoA3/knn_utils.py:10-55 (K=1); see include/pcdist.h.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "pcd_common.cuh"
+
+namespace pcd {
+
+// ------------------------------------------------------------------------------ error state
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char *what) {
+    set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    return PCD_ERR_CUDA;
+}
+
+// ---------------------------------------------------------------------------------- layout
+constexpr int kSweepWarps = 4;
+constexpr int kSweepThreads = kSweepWarps * 32;
+constexpr int kColChunk = 32;     // columns per row-direction tag
+constexpr int kMaxColTile = 256;  // columns per TMA stage (16 B each)
+constexpr int kRowPadUnit = 1024; // rows are padded to a multiple of 128*R, R <= 8
+
+struct Nn1Layout {
+    int Npad, Mpad;
+    size_t rowpk, colpk, rowkey, colkey, total;
+};
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static Nn1Layout nn1_layout(int B, int N, int M) {
+    Nn1Layout L;
+    L.Npad = (int)align_up((size_t)N, kRowPadUnit);
+    L.Mpad = (int)align_up((size_t)M, kMaxColTile);
+    size_t off = 0;
+    L.rowpk = off; off = align_up(off + (size_t)B * L.Npad * 16, 256);
+    L.colpk = off; off = align_up(off + (size_t)B * L.Mpad * 16, 256);
+    L.rowkey = off; off = align_up(off + (size_t)B * L.Npad * 8, 256);
+    L.colkey = off; off = align_up(off + (size_t)B * L.Mpad * 8, 256);
+    L.total = off;
+    return L;
+}
+
+// ------------------------------------------------------------------------------------ prep
+// rowpk[b][i] = float4(-2x, -2y, -2z, nrow)           (AoS, one LDG.128 per query)
+// colpk[b][j/2] = {x0,x1,y0,y1,z0,z1,n0,n1}           (pair records: two LDS.128 feed 2 columns
+//                                                      as ready-made fp32x2 operands)
+// Padded points are inert: coordinates 0, norm +inf  => every distance through them is +inf.
+__global__ void nn1_prep_kernel(const float *__restrict__ rows, int64_t r_sb, int64_t r_sp, int64_t r_sc,
+                                const float *__restrict__ cols, int64_t c_sb, int64_t c_sp, int64_t c_sc,
+                                int B, int N, int M, int Npad, int Mpad, int norm_kind, int swap_norms,
+                                float4 *__restrict__ rowpk, float *__restrict__ colpk,
+                                unsigned long long *__restrict__ rowkey, unsigned long long *__restrict__ colkey) {
+    const long long per_b = (long long)Npad + Mpad;
+    const long long total = per_b * B;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(t / per_b);
+        const int p = (int)(t - (long long)b * per_b);
+        if (p < Npad) {
+            const int i = p;
+            float x = 0.f, y = 0.f, z = 0.f, n = __int_as_float(0x7f800000);
+            if (i < N) {
+                const float *s = rows + b * r_sb + i * r_sp;
+                x = s[0]; y = s[r_sc]; z = s[2 * r_sc];
+                if (swap_norms) {
+                    const float *o = cols + b * c_sb + i * c_sp;
+                    n = sq_norm3(norm_kind, o[0], o[c_sc], o[2 * c_sc]);
+                } else {
+                    n = sq_norm3(norm_kind, x, y, z);
+                }
+            }
+            rowpk[(size_t)b * Npad + i] = make_float4(-2.f * x, -2.f * y, -2.f * z, n);
+            rowkey[(size_t)b * Npad + i] = ~0ull;
+        } else {
+            const int j = p - Npad;
+            float x = 0.f, y = 0.f, z = 0.f, n = __int_as_float(0x7f800000);
+            if (j < M) {
+                const float *s = cols + b * c_sb + j * c_sp;
+                x = s[0]; y = s[c_sc]; z = s[2 * c_sc];
+                if (swap_norms) {
+                    const float *o = rows + b * r_sb + j * r_sp;
+                    n = sq_norm3(norm_kind, o[0], o[r_sc], o[2 * r_sc]);
+                } else {
+                    n = sq_norm3(norm_kind, x, y, z);
+                }
+            }
+            float *rec = colpk + ((size_t)b * Mpad + (j & ~1)) * 4 + (j & 1);
+            rec[0] = x; rec[2] = y; rec[4] = z; rec[6] = n;
+            colkey[(size_t)b * Mpad + j] = ~0ull;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------- sweep
+struct SweepSmem {
+    float4 tile[2][kMaxColTile];                 // 2 x 4 KB   column pair-records (TMA destination)
+    float colpart[2][kSweepWarps][kMaxColTile];  // 2 x 4 KB   per-warp column minima
+    uint64_t full[2];                            // mbarriers: tile[s] has landed
+};
+
+template <int FORM, int R>
+__global__ void __launch_bounds__(kSweepThreads, (R >= 8) ? 3 : ((R >= 4) ? 4 : 6))
+nn1_sweep_kernel(const float4 *__restrict__ rowpk, const float4 *__restrict__ colpk,
+                 unsigned long long *__restrict__ rowkey, unsigned long long *__restrict__ colkey,
+                 int Npad, int Mpad, int mt, int nqt, int nct, long long units) {
+    constexpr int QW = 32 * R;            // queries per warp (= column-direction tag granularity)
+    constexpr int QT = kSweepWarps * QW;  // queries per CTA tile
+    __shared__ __align__(128) SweepSmem sm;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long u0 = units * blockIdx.x / gridDim.x;
+    const long long u1 = units * (blockIdx.x + 1) / gridDim.x;
+    if (u0 >= u1) return;
+
+    const uint32_t tile_bytes = (uint32_t)mt * 16u;
+    auto tile_src = [&](long long u) -> const float4 * {
+        const long long bq = u / nct;
+        const int ct = (int)(u - bq * nct);
+        const int b = (int)(bq / nqt);
+        return colpk + (size_t)b * Mpad + (size_t)ct * mt;
+    };
+    if (tid == 0) {
+        mbar_init(&sm.full[0], 1);
+        mbar_init(&sm.full[1], 1);
+        fence_mbar_init();
+        fence_proxy_async();
+        mbar_expect_tx(&sm.full[0], tile_bytes);
+        tma_load_1d(sm.tile[0], tile_src(u0), tile_bytes, &sm.full[0]);
+        if (u0 + 1 < u1) {
+            mbar_expect_tx(&sm.full[1], tile_bytes);
+            tma_load_1d(sm.tile[1], tile_src(u0 + 1), tile_bytes, &sm.full[1]);
+        }
+    }
+    __syncthreads();
+
+    float qx[R], qy[R], qz[R], qn[R], best[R];
+    uint32_t btag[R];
+    long long cur_bq = -1;
+    size_t row_base = 0;
+
+    for (long long u = u0; u < u1; ++u) {
+        const int it = (int)(u - u0);
+        const int buf = it & 1;
+        const uint32_t parity = (it >> 1) & 1;
+        const long long bq = u / nct;
+        const int ct = (int)(u - bq * nct);
+        const int b = (int)(bq / nqt);
+        const int qt = (int)(bq - (long long)b * nqt);
+
+        if (bq != cur_bq) {
+            if (cur_bq >= 0) {
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    atomicMin(&rowkey[row_base + r * 32 + lane], make_key(best[r], btag[r]));
+            }
+            cur_bq = bq;
+            row_base = (size_t)b * Npad + (size_t)qt * QT + warp * QW;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float4 q = __ldg(&rowpk[row_base + r * 32 + lane]);
+                qx[r] = q.x; qy[r] = q.y; qz[r] = q.z; qn[r] = q.w;
+                best[r] = __int_as_float(0x7f800000);
+                btag[r] = 0;
+            }
+        }
+
+        mbar_wait(&sm.full[buf], parity);
+
+        const float4 *t4 = sm.tile[buf];
+        float *cp = sm.colpart[buf][warp];
+        const int nchunk = mt / kColChunk;
+        const uint32_t tag0 = (uint32_t)(ct * mt) / kColChunk;
+        for (int c = 0; c < nchunk; ++c) {
+            float m[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) m[r] = __int_as_float(0x7f800000);
+#pragma unroll 4
+            for (int s = 0; s < kColChunk / 2; ++s) {
+                const float4 A = t4[(c * (kColChunk / 2) + s) * 2];
+                const float4 Bv = t4[(c * (kColChunk / 2) + s) * 2 + 1];
+                const f32x2 X = pack2(A.x, A.y), Y = pack2(A.z, A.w);
+                const f32x2 Z = pack2(Bv.x, Bv.y), Nn = pack2(Bv.z, Bv.w);
+                float lo[R], hi[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const f32x2 d = pair_dist_x2<FORM>(qx[r], qy[r], qz[r], qn[r], X, Y, Z, Nn);
+                    unpack2(d, lo[r], hi[r]);
+                    m[r] = min3(m[r], lo[r], hi[r]);
+                }
+                float clo = lo[0], chi = hi[0];
+#pragma unroll
+                for (int r = 1; r + 1 < R; r += 2) {
+                    clo = min3(clo, lo[r], lo[r + 1]);
+                    chi = min3(chi, hi[r], hi[r + 1]);
+                }
+                if ((R & 1) == 0) {
+                    clo = fminf(clo, lo[R - 1]);
+                    chi = fminf(chi, hi[R - 1]);
+                }
+                clo = warp_min_f32(clo);
+                chi = warp_min_f32(chi);
+                *reinterpret_cast<float2 *>(&cp[c * kColChunk + 2 * s]) = make_float2(clo, chi);
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (m[r] < best[r]) {
+                    best[r] = m[r];
+                    btag[r] = tag0 + c;
+                }
+            }
+        }
+        __syncthreads();  // tile[buf] fully read, colpart[buf] fully written
+
+        if (tid == 0 && u + 2 < u1) {
+            mbar_expect_tx(&sm.full[buf], tile_bytes);
+            tma_load_1d(sm.tile[buf], tile_src(u + 2), tile_bytes, &sm.full[buf]);
+        }
+        // column flush: min over the CTA's warps, lowest warp on ties, one atomic per column
+        for (int col = tid; col < mt; col += kSweepThreads) {
+            float v = sm.colpart[buf][0][col];
+            uint32_t w = 0;
+#pragma unroll
+            for (int k = 1; k < kSweepWarps; ++k) {
+                const float o = sm.colpart[buf][k][col];
+                if (o < v) { v = o; w = k; }
+            }
+            if (v < __int_as_float(0x7f800000))
+                atomicMin(&colkey[(size_t)b * Mpad + (size_t)ct * mt + col],
+                          make_key(v, (uint32_t)qt * kSweepWarps + w));
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) atomicMin(&rowkey[row_base + r * 32 + lane], make_key(best[r], btag[r]));
+}
+
+// ----------------------------------------------------------------------------------- fixup
+__device__ __forceinline__ float apply_transform(int transform, float v) {
+    return transform == PCD_VALUE_SQRT_CLAMP ? sqrtf(fmaxf(v, 0.0f)) : v;
+}
+
+template <int FORM>
+__global__ void __launch_bounds__(256)
+nn1_fixup_kernel(const float4 *__restrict__ rowpk, const float *__restrict__ colpk,
+                 const unsigned long long *__restrict__ rowkey, const unsigned long long *__restrict__ colkey,
+                 int B, int N, int M, int Npad, int Mpad, int qchunk, int transform,
+                 float *__restrict__ row_min, int32_t *__restrict__ row_arg,
+                 float *__restrict__ col_min, int32_t *__restrict__ col_arg) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long items = (long long)B * (N + M);
+    for (long long it = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; it < items; it += warps) {
+        const int b = (int)(it / (N + M));
+        const int p = (int)(it - (long long)b * (N + M));
+        if (p < N) {
+            const int i = p;
+            const unsigned long long key = rowkey[(size_t)b * Npad + i];
+            const float v = ordered_to_f32((uint32_t)(key >> 32));
+            const uint32_t c = (uint32_t)key;
+            const float4 q = __ldg(&rowpk[(size_t)b * Npad + i]);
+            const int j = (int)c * kColChunk + lane;
+            const float *rec = colpk + ((size_t)b * Mpad + (j & ~1)) * 4 + (j & 1);
+            const float d = pair_dist_scalar<FORM>(q.x, q.y, q.z, q.w, rec[0], rec[2], rec[4], rec[6]);
+            const unsigned mask = __ballot_sync(0xffffffffu, d == v);
+            if (lane == 0) {
+                row_min[(size_t)b * N + i] = apply_transform(transform, v);
+                row_arg[(size_t)b * N + i] = (int)c * kColChunk + (mask ? __ffs(mask) - 1 : 0);
+            }
+        } else {
+            const int j = p - N;
+            const unsigned long long key = colkey[(size_t)b * Mpad + j];
+            const float v = ordered_to_f32((uint32_t)(key >> 32));
+            const uint32_t c = (uint32_t)key;
+            const float *rec = colpk + ((size_t)b * Mpad + (j & ~1)) * 4 + (j & 1);
+            const float cx = rec[0], cy = rec[2], cz = rec[4], cn = rec[6];
+            int found = (int)c * qchunk;
+            for (int s = 0; s < qchunk; s += 32) {
+                const int i = (int)c * qchunk + s + lane;
+                const float4 q = __ldg(&rowpk[(size_t)b * Npad + i]);
+                const float d = pair_dist_scalar<FORM>(q.x, q.y, q.z, q.w, cx, cy, cz, cn);
+                const unsigned mask = __ballot_sync(0xffffffffu, d == v);
+                if (mask) {
+                    found = (int)c * qchunk + s + __ffs(mask) - 1;
+                    break;
+                }
+            }
+            if (lane == 0) {
+                col_min[(size_t)b * M + j] = apply_transform(transform, v);
+                col_arg[(size_t)b * M + j] = found;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------- reduce
+// grid (B, 2): y = 0 rows, y = 1 cols.  Fixed summation order -> run-to-run deterministic.
+__global__ void __launch_bounds__(256)
+nn1_reduce_kernel(const float *__restrict__ row_min, const float *__restrict__ col_min, int N, int M,
+                  float *__restrict__ stats_f, int32_t *__restrict__ stats_i) {
+    const int b = blockIdx.x, side = blockIdx.y;
+    const int n = side ? M : N;
+    const float *v = (side ? col_min : row_min) + (size_t)b * n;
+    float s = 0.f, mx = -__int_as_float(0x7f800000);
+    int am = 0x7fffffff;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float x = v[i];
+        s += x;
+        if (x > mx) { mx = x; am = i; }
+    }
+    __shared__ float ss[256], smx[256];
+    __shared__ int sam[256];
+    ss[threadIdx.x] = s; smx[threadIdx.x] = mx; sam[threadIdx.x] = am;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            ss[threadIdx.x] += ss[threadIdx.x + o];
+            const float om = smx[threadIdx.x + o];
+            const int oa = sam[threadIdx.x + o];
+            if (om > smx[threadIdx.x] || (om == smx[threadIdx.x] && oa < sam[threadIdx.x])) {
+                smx[threadIdx.x] = om; sam[threadIdx.x] = oa;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        stats_f[b * 4 + side * 2 + 0] = ss[0];
+        stats_f[b * 4 + side * 2 + 1] = smx[0];
+        stats_i[b * 2 + side] = sam[0] == 0x7fffffff ? 0 : sam[0];
+    }
+}
+
+// -------------------------------------------------------------------------------- backward
+struct BwdArgs {
+    const float *rows; int64_t r_sb, r_sp, r_sc;
+    const float *cols; int64_t c_sb, c_sp, c_sc;
+    int B, N, M, swap_norms, transform;
+    const int32_t *row_arg, *col_arg;
+    const float *row_min, *col_min;
+    const float *g_row, *g_col;
+    const float *w_row_all, *w_row_max; const int32_t *row_argmax;
+    const float *w_col_all, *w_col_max; const int32_t *col_argmax;
+    float *grad_rows; int64_t gr_sb, gr_sp, gr_sc;
+    float *grad_cols; int64_t gc_sb, gc_sp, gc_sc;
+};
+
+__device__ __forceinline__ float3 ld3(const float *base, int64_t sc) {
+    return make_float3(base[0], base[sc], base[2 * sc]);
+}
+// upstream gradient of minimum (b,p) on one side
+__device__ __forceinline__ float upstream(const float *g, const float *w_all, const float *w_max,
+                                          const int32_t *argmax, int b, int p, int n) {
+    float r = 0.f;
+    if (g) r += g[(size_t)b * n + p];
+    if (w_all) r += w_all[b];
+    if (w_max && argmax[b] == p) r += w_max[b];
+    return r;
+}
+// d(value)/d(d2) factor: squared -> 2 * g (applied to (p - q)); sqrt -> g / v, 0 at v == 0
+__device__ __forceinline__ float chain_factor(int transform, float g, const float *vals, size_t off) {
+    if (transform == PCD_VALUE_SQRT_CLAMP) {
+        const float v = vals[off];
+        return v > 0.f ? g / v : 0.f;
+    }
+    return 2.f * g;
+}
+
+// Pass 1 (plain stores, writes every gradient element): the terms indexed by the thread's own
+// point.  Pass 2 (atomics): the terms that land on the argmin partner.
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) nn1_bwd_kernel(BwdArgs a) {
+    const long long total = (long long)a.B * (a.N + a.M);
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(t / (a.N + a.M));
+        const int p = (int)(t - (long long)b * (a.N + a.M));
+        const float *rb = a.rows + b * a.r_sb, *cb = a.cols + b * a.c_sb;
+        if (p < a.N) {
+            const int i = p;
+            const float g = upstream(a.g_row, a.w_row_all, a.w_row_max, a.row_argmax, b, i, a.N);
+            const int j = a.row_arg[(size_t)b * a.N + i];
+            const float3 r = ld3(rb + i * a.r_sp, a.r_sc), c = ld3(cb + j * a.c_sp, a.c_sc);
+            const float f = chain_factor(a.transform, g, a.row_min, (size_t)b * a.N + i);
+            if (!SCATTER) {
+                if (a.grad_rows) {
+                    float3 o;
+                    if (a.swap_norms) {
+                        // entry (i,j): -2 g c_j ; column-direction entry (i*, j=i): +2 g' r_i
+                        const float g2 = upstream(a.g_col, a.w_col_all, a.w_col_max, a.col_argmax, b, i, a.M);
+                        o = make_float3(-f * c.x + 2.f * g2 * r.x, -f * c.y + 2.f * g2 * r.y, -f * c.z + 2.f * g2 * r.z);
+                    } else {
+                        o = make_float3(f * (r.x - c.x), f * (r.y - c.y), f * (r.z - c.z));
+                    }
+                    float *gp = a.grad_rows + b * a.gr_sb + i * a.gr_sp;
+                    gp[0] = o.x; gp[a.gr_sc] = o.y; gp[2 * a.gr_sc] = o.z;
+                }
+            } else if (g != 0.f) {
+                if (a.grad_cols) {
+                    float *gp = a.grad_cols + b * a.gc_sb + j * a.gc_sp;
+                    if (a.swap_norms) {
+                        atomicAdd(gp, -f * r.x); atomicAdd(gp + a.gc_sc, -f * r.y); atomicAdd(gp + 2 * a.gc_sc, -f * r.z);
+                    } else {
+                        atomicAdd(gp, -f * (r.x - c.x)); atomicAdd(gp + a.gc_sc, -f * (r.y - c.y));
+                        atomicAdd(gp + 2 * a.gc_sc, -f * (r.z - c.z));
+                    }
+                }
+                if (a.swap_norms && a.grad_rows) {   // |rows_j|^2 term of entry (i,j)
+                    const float3 rj = ld3(rb + j * a.r_sp, a.r_sc);
+                    float *gp = a.grad_rows + b * a.gr_sb + j * a.gr_sp;
+                    atomicAdd(gp, f * rj.x); atomicAdd(gp + a.gr_sc, f * rj.y); atomicAdd(gp + 2 * a.gr_sc, f * rj.z);
+                }
+            }
+        } else {
+            const int j = p - a.N;
+            const float g = upstream(a.g_col, a.w_col_all, a.w_col_max, a.col_argmax, b, j, a.M);
+            const int i = a.col_arg[(size_t)b * a.M + j];
+            const float3 r = ld3(rb + i * a.r_sp, a.r_sc), c = ld3(cb + j * a.c_sp, a.c_sc);
+            const float f = chain_factor(a.transform, g, a.col_min, (size_t)b * a.M + j);
+            if (!SCATTER) {
+                if (a.grad_cols) {
+                    float3 o;
+                    if (a.swap_norms) {
+                        // entry (i*,j): -2 g' r_i* ; row-direction entry (i=j, j*): +2 g c_j
+                        const float g1 = upstream(a.g_row, a.w_row_all, a.w_row_max, a.row_argmax, b, j, a.N);
+                        o = make_float3(-f * r.x + 2.f * g1 * c.x, -f * r.y + 2.f * g1 * c.y, -f * r.z + 2.f * g1 * c.z);
+                    } else {
+                        o = make_float3(f * (c.x - r.x), f * (c.y - r.y), f * (c.z - r.z));
+                    }
+                    float *gp = a.grad_cols + b * a.gc_sb + j * a.gc_sp;
+                    gp[0] = o.x; gp[a.gc_sc] = o.y; gp[2 * a.gc_sc] = o.z;
+                }
+            } else if (g != 0.f) {
+                if (a.grad_rows) {
+                    float *gp = a.grad_rows + b * a.gr_sb + i * a.gr_sp;
+                    if (a.swap_norms) {
+                        atomicAdd(gp, -f * c.x); atomicAdd(gp + a.gr_sc, -f * c.y); atomicAdd(gp + 2 * a.gr_sc, -f * c.z);
+                    } else {
+                        atomicAdd(gp, -f * (c.x - r.x)); atomicAdd(gp + a.gr_sc, -f * (c.y - r.y));
+                        atomicAdd(gp + 2 * a.gr_sc, -f * (c.z - r.z));
+                    }
+                }
+                if (a.swap_norms && a.grad_cols) {   // |cols_i*|^2 term of entry (i*,j)
+                    const float3 ci = ld3(cb + i * a.c_sp, a.c_sc);
+                    float *gp = a.grad_cols + b * a.gc_sb + i * a.gc_sp;
+                    atomicAdd(gp, f * ci.x); atomicAdd(gp + a.gc_sc, f * ci.y); atomicAdd(gp + 2 * a.gc_sc, f * ci.z);
+                }
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------- host helpers
+static int g_num_sms = 0;
+static int num_sms() {
+    if (g_num_sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+        if (cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) g_num_sms = 0;
+    }
+    return g_num_sms;
+}
+
+template <int FORM, int R>
+static cudaError_t launch_sweep(const float4 *rowpk, const float4 *colpk, unsigned long long *rowkey,
+                                unsigned long long *colkey, int B, int N, int M, int Npad, int Mpad, int mt,
+                                int sms, cudaStream_t st) {
+    const int QT = kSweepWarps * 32 * R;
+    const int nqt = (N + QT - 1) / QT, nct = (M + mt - 1) / mt;   // fully inert tiles are skipped
+    const long long units = (long long)B * nqt * nct;
+    int occ = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nn1_sweep_kernel<FORM, R>, kSweepThreads, 0);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) occ = 1;
+    long long grid = (long long)sms * occ;
+    if (grid > units) grid = units;
+    nn1_sweep_kernel<FORM, R><<<(unsigned)grid, kSweepThreads, 0, st>>>(rowpk, colpk, rowkey, colkey, Npad, Mpad, mt,
+                                                                         nqt, nct, units);
+    return cudaGetLastError();
+}
+
+template <int FORM>
+static cudaError_t launch_sweep_r(int R, const float4 *rowpk, const float4 *colpk, unsigned long long *rowkey,
+                                  unsigned long long *colkey, int B, int N, int M, int Npad, int Mpad, int mt,
+                                  int sms, cudaStream_t st) {
+    switch (R) {
+    case 8: return launch_sweep<FORM, 8>(rowpk, colpk, rowkey, colkey, B, N, M, Npad, Mpad, mt, sms, st);
+    case 4: return launch_sweep<FORM, 4>(rowpk, colpk, rowkey, colkey, B, N, M, Npad, Mpad, mt, sms, st);
+    default: return launch_sweep<FORM, 2>(rowpk, colpk, rowkey, colkey, B, N, M, Npad, Mpad, mt, sms, st);
+    }
+}
+
+// Tile-shape heuristic.  R queries per lane (register blocking: more = fewer LDS / CREDUX per
+// pair) and mt columns per stage; small problems trade blocking for enough units to fill the
+// 148 SMs.  PCD_SWEEP_R / PCD_SWEEP_MT override for tuning.
+static void choose_tiling(int B, int N, int M, int sms, int *R_out, int *mt_out) {
+    int R = 8;
+    while (R > 2) {
+        const long long qtiles = (long long)B * ((N + 128 * R - 1) / (128 * R));
+        const long long padded = qtiles * 128 * R;
+        const bool waste = padded > (long long)B * N * 5 / 4;        // > 25 % inert rows
+        const bool starved = qtiles * ((M + 255) / 256) < 2LL * sms * 4;
+        if (!waste && !starved) break;
+        R >>= 1;
+    }
+    int mt = kMaxColTile;
+    const long long qtiles = (long long)B * ((N + 128 * R - 1) / (128 * R));
+    while (mt > kColChunk && qtiles * ((M + mt - 1) / mt) < 2LL * sms * 5) mt >>= 1;
+    if (const char *e = getenv("PCD_SWEEP_R")) { int v = atoi(e); if (v == 2 || v == 4 || v == 8) R = v; }
+    if (const char *e = getenv("PCD_SWEEP_MT")) { int v = atoi(e); if (v >= 32 && v <= 256 && (v & (v - 1)) == 0) mt = v; }
+    *R_out = R; *mt_out = mt;
+}
+
+}  // namespace pcd
+
+// =================================================================================== C ABI
+using namespace pcd;
+
+extern "C" int pcd_version(void) { return PCD_VERSION; }
+extern "C" const char *pcd_last_error(void) { return g_err; }
+
+// optional profiling hook: events recorded around the sweep launch of the next forward calls
+static thread_local cudaEvent_t g_sweep_ev0 = nullptr, g_sweep_ev1 = nullptr;
+extern "C" int pcd_nn1_set_sweep_events(void *start_event, void *stop_event) {
+    g_sweep_ev0 = (cudaEvent_t)start_event;
+    g_sweep_ev1 = (cudaEvent_t)stop_event;
+    return PCD_OK;
+}
+
+extern "C" size_t pcd_nn1_workspace_bytes(int B, int N, int M) {
+    if (B <= 0 || N <= 0 || M <= 0) return 0;
+    return nn1_layout(B, N, M).total;
+}
+
+extern "C" int pcd_nn1_forward(const float *rows, int64_t r_sb, int64_t r_sp, int64_t r_sc,
+                               const float *cols, int64_t c_sb, int64_t c_sp, int64_t c_sc,
+                               int B, int N, int M, int form, int norm_kind, int swap_norms, int transform,
+                               float *row_min, int32_t *row_arg, float *col_min, int32_t *col_arg,
+                               float *stats_f, int32_t *stats_i,
+                               void *workspace, size_t workspace_bytes, void *stream) {
+    if (!rows || !cols || !row_min || !row_arg || !col_min || !col_arg || !stats_f || !stats_i || !workspace) {
+        set_error("pcd_nn1_forward: NULL pointer argument");
+        return PCD_ERR_ARG;
+    }
+    if (B <= 0 || N <= 0 || M <= 0 || form < 0 || form > 2 || norm_kind < 0 || norm_kind > 1 || transform < 0 ||
+        transform > 1) {
+        set_error("pcd_nn1_forward: bad argument B=%d N=%d M=%d form=%d norm=%d transform=%d", B, N, M, form,
+                  norm_kind, transform);
+        return PCD_ERR_ARG;
+    }
+    if (swap_norms && N != M) {
+        set_error("pcd_nn1_forward: swap_norms requires N == M (got %d, %d), as the reference's broadcast does", N, M);
+        return PCD_ERR_ARG;
+    }
+    const Nn1Layout L = nn1_layout(B, N, M);
+    if (workspace_bytes < L.total) {
+        set_error("pcd_nn1_forward: workspace %zu < required %zu bytes", workspace_bytes, L.total);
+        return PCD_ERR_WORKSPACE;
+    }
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) {
+        set_error("pcd_nn1_forward: workspace must be 256-byte aligned");
+        return PCD_ERR_ARG;
+    }
+    const int sms = num_sms();
+    if (sms <= 0) return cuda_fail(cudaGetLastError(), "no CUDA device");
+    cudaStream_t st = (cudaStream_t)stream;
+    char *ws = (char *)workspace;
+    float4 *rowpk = (float4 *)(ws + L.rowpk);
+    float *colpk = (float *)(ws + L.colpk);
+    unsigned long long *rowkey = (unsigned long long *)(ws + L.rowkey);
+    unsigned long long *colkey = (unsigned long long *)(ws + L.colkey);
+
+    int R, mt;
+    choose_tiling(B, N, M, sms, &R, &mt);
+
+    {
+        const long long total = (long long)B * (L.Npad + L.Mpad);
+        const int grid = (int)((total + 255) / 256 < (long long)sms * 8 ? (total + 255) / 256 : (long long)sms * 8);
+        nn1_prep_kernel<<<grid, 256, 0, st>>>(rows, r_sb, r_sp, r_sc, cols, c_sb, c_sp, c_sc, B, N, M, L.Npad,
+                                              L.Mpad, norm_kind, swap_norms, rowpk, colpk, rowkey, colkey);
+        PCD_CUDA_CHECK(cudaGetLastError());
+    }
+    {
+        cudaError_t e;
+        if (g_sweep_ev0) PCD_CUDA_CHECK(cudaEventRecord(g_sweep_ev0, st));
+        if (form == PCD_FORM_ROW_COL)
+            e = launch_sweep_r<PCD_FORM_ROW_COL>(R, rowpk, (const float4 *)colpk, rowkey, colkey, B, N, M, L.Npad, L.Mpad, mt, sms, st);
+        else if (form == PCD_FORM_COL_ROW)
+            e = launch_sweep_r<PCD_FORM_COL_ROW>(R, rowpk, (const float4 *)colpk, rowkey, colkey, B, N, M, L.Npad, L.Mpad, mt, sms, st);
+        else
+            e = launch_sweep_r<PCD_FORM_SUM_FIRST>(R, rowpk, (const float4 *)colpk, rowkey, colkey, B, N, M, L.Npad, L.Mpad, mt, sms, st);
+        PCD_CUDA_CHECK(e);
+        if (g_sweep_ev1) PCD_CUDA_CHECK(cudaEventRecord(g_sweep_ev1, st));
+    }
+    {
+        const long long items = (long long)B * (N + M);
+        const long long want = (items + 7) / 8;
+        const int grid = (int)(want < (long long)sms * 8 ? want : (long long)sms * 8);
+        const int qchunk = 32 * R;
+        if (form == PCD_FORM_ROW_COL)
+            nn1_fixup_kernel<PCD_FORM_ROW_COL><<<grid, 256, 0, st>>>(rowpk, colpk, rowkey, colkey, B, N, M, L.Npad, L.Mpad, qchunk, transform, row_min, row_arg, col_min, col_arg);
+        else if (form == PCD_FORM_COL_ROW)
+            nn1_fixup_kernel<PCD_FORM_COL_ROW><<<grid, 256, 0, st>>>(rowpk, colpk, rowkey, colkey, B, N, M, L.Npad, L.Mpad, qchunk, transform, row_min, row_arg, col_min, col_arg);
+        else
+            nn1_fixup_kernel<PCD_FORM_SUM_FIRST><<<grid, 256, 0, st>>>(rowpk, colpk, rowkey, colkey, B, N, M, L.Npad, L.Mpad, qchunk, transform, row_min, row_arg, col_min, col_arg);
+        PCD_CUDA_CHECK(cudaGetLastError());
+    }
+    nn1_reduce_kernel<<<dim3(B, 2), 256, 0, st>>>(row_min, col_min, N, M, stats_f, stats_i);
+    PCD_CUDA_CHECK(cudaGetLastError());
+    return PCD_OK;
+}
+
+extern "C" int pcd_nn1_backward(const float *rows, int64_t r_sb, int64_t r_sp, int64_t r_sc,
+                                const float *cols, int64_t c_sb, int64_t c_sp, int64_t c_sc,
+                                int B, int N, int M, int swap_norms, int transform,
+                                const int32_t *row_arg, const int32_t *col_arg,
+                                const float *row_min, const float *col_min,
+                                const float *g_row, const float *g_col,
+                                const float *w_row_all, const float *w_row_max, const int32_t *row_argmax,
+                                const float *w_col_all, const float *w_col_max, const int32_t *col_argmax,
+                                float *grad_rows, int64_t gr_sb, int64_t gr_sp, int64_t gr_sc,
+                                float *grad_cols, int64_t gc_sb, int64_t gc_sp, int64_t gc_sc, void *stream) {
+    if (!rows || !cols || !row_arg || !col_arg || B <= 0 || N <= 0 || M <= 0) {
+        set_error("pcd_nn1_backward: bad argument");
+        return PCD_ERR_ARG;
+    }
+    if ((w_row_max && !row_argmax) || (w_col_max && !col_argmax)) {
+        set_error("pcd_nn1_backward: w_*_max given without *_argmax");
+        return PCD_ERR_ARG;
+    }
+    if (transform == PCD_VALUE_SQRT_CLAMP && (!row_min || !col_min)) {
+        set_error("pcd_nn1_backward: SQRT_CLAMP needs the stored minima");
+        return PCD_ERR_ARG;
+    }
+    if (swap_norms && N != M) {
+        set_error("pcd_nn1_backward: swap_norms requires N == M");
+        return PCD_ERR_ARG;
+    }
+    if (!grad_rows && !grad_cols) return PCD_OK;
+    const int sms = num_sms();
+    if (sms <= 0) return cuda_fail(cudaGetLastError(), "no CUDA device");
+    BwdArgs a{rows, r_sb, r_sp, r_sc, cols, c_sb, c_sp, c_sc, B, N, M, swap_norms, transform,
+              row_arg, col_arg, row_min, col_min, g_row, g_col,
+              w_row_all, w_row_max, row_argmax, w_col_all, w_col_max, col_argmax,
+              grad_rows, gr_sb, gr_sp, gr_sc, grad_cols, gc_sb, gc_sp, gc_sc};
+    const long long total = (long long)B * (N + M);
+    const long long want = (total + 255) / 256;
+    const int grid = (int)(want < (long long)sms * 16 ? want : (long long)sms * 16);
+    cudaStream_t st = (cudaStream_t)stream;
+    nn1_bwd_kernel<false><<<grid, 256, 0, st>>>(a);
+    PCD_CUDA_CHECK(cudaGetLastError());
+    nn1_bwd_kernel<true><<<grid, 256, 0, st>>>(a);
+    PCD_CUDA_CHECK(cudaGetLastError());
+    return PCD_OK;
+}

@@ -1,0 +1,63 @@
+"""Drop-in for attack/CW/CW_utils/distance.py (identical copy: attack/Gen3DAdv/utils/distance.py).
+
+`ChamferDistance()(preds[B,N1,3], gts[B,N2,3]) -> (loss1[B], loss2[B])`, `HausdorffDistance`
+likewise, module singletons `chamfer` and `hausdorff`.  Arithmetic = the reference's
+P = rx^T + ry - 2*zz with bmm-diagonal norms (distance.py:15-32), evaluated by the NN-1
+sweep; both classes share one sweep when called on the same tensors.
+"""
+import torch
+import torch.nn as nn
+
+from . import functional as F
+
+
+def _sweep(preds, gts):
+    # P = batch_pairwise_dist(gts, preds): rows = gts, cols = preds  (distance.py:45, :63)
+    return F.nn1(gts, preds, F.FORM_SUM_FIRST, F.NORM_FMA)
+
+
+class _Distance(nn.Module):
+
+    def __init__(self):
+        super(_Distance, self).__init__()
+        self.use_cuda = torch.cuda.is_available()
+
+    def forward(self, preds, gts):
+        pass
+
+    def batch_pairwise_dist(self, x, y):
+        """distance.py:15-32 -- materialising compatibility API ([B,Nx,Ny], plain torch)."""
+        xx = torch.bmm(x, x.transpose(2, 1))
+        yy = torch.bmm(y, y.transpose(2, 1))
+        zz = torch.bmm(x, y.transpose(2, 1))
+        rx = torch.diagonal(xx, dim1=1, dim2=2).unsqueeze(1).expand_as(zz.transpose(2, 1))
+        ry = torch.diagonal(yy, dim1=1, dim2=2).unsqueeze(1).expand_as(zz)
+        return rx.transpose(2, 1) + ry - 2 * zz
+
+
+class ChamferDistance(_Distance):
+
+    def forward(self, preds, gts):
+        """preds: [B, N1, 3], gts: [B, N2, 3] -> (mean_j min_i P, mean_i min_j P)  (distance.py:40-50)"""
+        r = _sweep(preds, gts)
+        loss1 = r.stats[2] / preds.shape[1]
+        loss2 = r.stats[0] / gts.shape[1]
+        return loss1, loss2
+
+
+class HausdorffDistance(_Distance):
+
+    def forward(self, preds, gts):
+        """(max_j min_i P, max_i min_j P)  (distance.py:58-70); ties -> first index like torch.max(dim)."""
+        r = _sweep(preds, gts)
+        return r.stats[3], r.stats[1]
+
+
+chamfer = ChamferDistance()
+hausdorff = HausdorffDistance()
+
+
+def chamfer_hausdorff(preds, gts):
+    """Fused convenience: (chamfer_loss1, chamfer_loss2, hausdorff_loss1, hausdorff_loss2), one sweep."""
+    r = _sweep(preds, gts)
+    return r.stats[2] / preds.shape[1], r.stats[0] / gts.shape[1], r.stats[3], r.stats[1]

@@ -1,0 +1,265 @@
+"""PyTorch autograd Functions over the C ABI of libpcdist.so (include/pcdist.h).
+
+PyTorch is plumbing here: it owns device memory, the current stream and autograd; every
+arithmetic step of the path runs in the hand-written sm_100a kernels.  Nothing in this
+module computes a distance with torch ops and nothing falls back to CPU.
+"""
+from __future__ import annotations
+
+from collections import namedtuple
+
+import torch
+
+from . import _lib
+from ._lib import (FORM_COL_ROW, FORM_ROW_COL, FORM_SUM_FIRST, NORM_FMA, NORM_MULSUM,
+                   VALUE_SQRT_CLAMP, VALUE_SQUARED)
+
+__all__ = ["nn1", "NN1Result", "knn", "ball_query", "fp32_peak_flops",
+           "FORM_ROW_COL", "FORM_COL_ROW", "FORM_SUM_FIRST", "NORM_MULSUM", "NORM_FMA",
+           "VALUE_SQUARED", "VALUE_SQRT_CLAMP"]
+
+_launch_count = 0   # number of C-ABI compute calls issued (bench.py reports launches)
+
+
+def launches():
+    return _launch_count
+
+
+def _check_cloud(t, name, C=3):
+    if not isinstance(t, torch.Tensor) or t.dim() != 3:
+        raise ValueError(f"{name} must be a 3-D tensor [B, N, {C}] (a transposed view is fine)")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} is on {t.device}: this path runs on CUDA only (no CPU fallback)")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    if C is not None and t.shape[2] != C:
+        raise ValueError(f"{name} must have {C} channels in its last logical dim, got {tuple(t.shape)}")
+
+
+def _cloud_args(t):
+    return [t.data_ptr(), t.stride(0), t.stride(1), t.stride(2)]
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+# ----------------------------------------------------------------------------------- NN-1
+NN1Result = namedtuple("NN1Result", "row_min row_arg col_min col_arg stats stats_arg")
+# stats: [4, B] = (sum_i row_min, max_i row_min, sum_j col_min, max_j col_min)
+# stats_arg: [2, B] int32 = (first argmax_i row_min, first argmax_j col_min)
+
+
+class _NN1(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rows, cols, form, norm, swap_norms, transform):
+        global _launch_count
+        lib = _lib.load()
+        B, N, _ = rows.shape
+        M = cols.shape[1]
+        dev = rows.device
+        with torch.cuda.device(dev):
+            row_min = torch.empty((B, N), dtype=torch.float32, device=dev)
+            col_min = torch.empty((B, M), dtype=torch.float32, device=dev)
+            row_arg = torch.empty((B, N), dtype=torch.int32, device=dev)
+            col_arg = torch.empty((B, M), dtype=torch.int32, device=dev)
+            stats_bt = torch.empty((B, 4), dtype=torch.float32, device=dev)
+            stats_i_bt = torch.empty((B, 2), dtype=torch.int32, device=dev)
+            ws_bytes = lib.pcd_nn1_workspace_bytes(B, N, M)
+            ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+            st = lib.pcd_nn1_forward(*_cloud_args(rows), *_cloud_args(cols), B, N, M,
+                                     form, norm, int(swap_norms), transform,
+                                     row_min.data_ptr(), row_arg.data_ptr(), col_min.data_ptr(), col_arg.data_ptr(),
+                                     stats_bt.data_ptr(), stats_i_bt.data_ptr(),
+                                     ws.data_ptr(), ws_bytes, _stream())
+            _lib.check(st, "pcd_nn1_forward")
+        _launch_count += 4
+        ctx.save_for_backward(rows, cols, row_arg, col_arg, row_min, col_min, stats_i_bt)
+        ctx.cfg = (int(swap_norms), transform)
+        ctx.mark_non_differentiable(row_arg, col_arg, stats_i_bt)
+        return row_min, row_arg, col_min, col_arg, stats_bt, stats_i_bt
+
+    @staticmethod
+    def backward(ctx, g_row_min, _ga, g_col_min, _gb, g_stats, _gc):
+        global _launch_count
+        rows, cols, row_arg, col_arg, row_min, col_min, stats_i = ctx.saved_tensors
+        swap_norms, transform = ctx.cfg
+        lib = _lib.load()
+        B, N, _ = rows.shape
+        M = cols.shape[1]
+        need_r, need_c = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if not (need_r or need_c):
+            return (None,) * 6
+        dev = rows.device
+        with torch.cuda.device(dev):
+            g_row = None if g_row_min is None else g_row_min.contiguous()
+            g_col = None if g_col_min is None else g_col_min.contiguous()
+            w = [None] * 4
+            argmax = [None, None]
+            if g_stats is not None:
+                gs = g_stats.t().contiguous()                     # [4, B]
+                am = stats_i.t().contiguous()                     # [2, B]
+                w = [gs[0], gs[1], gs[2], gs[3]]
+                argmax = [am[0], am[1]]
+            grad_rows = torch.empty((B, N, 3), dtype=torch.float32, device=dev) if need_r else None
+            grad_cols = torch.empty((B, M, 3), dtype=torch.float32, device=dev) if need_c else None
+            gr = _cloud_args(grad_rows) if need_r else [None, 0, 0, 0]
+            gc = _cloud_args(grad_cols) if need_c else [None, 0, 0, 0]
+            st = lib.pcd_nn1_backward(*_cloud_args(rows), *_cloud_args(cols), B, N, M, swap_norms, transform,
+                                      row_arg.data_ptr(), col_arg.data_ptr(), row_min.data_ptr(), col_min.data_ptr(),
+                                      _ptr(g_row), _ptr(g_col),
+                                      _ptr(w[0]), _ptr(w[1]), _ptr(argmax[0]),
+                                      _ptr(w[2]), _ptr(w[3]), _ptr(argmax[1]),
+                                      *gr, *gc, _stream())
+            _lib.check(st, "pcd_nn1_backward")
+        _launch_count += 2
+        return grad_rows, grad_cols, None, None, None, None
+
+
+_nn1_cache = {"key": None, "val": None, "refs": None}
+
+
+def _tensor_key(t):
+    # identity of the autograd root (the base of a view), storage, version counter and geometry:
+    # two `x.permute(0, 2, 1)` views of the same unmodified x hit the same entry.
+    root = t._base if t._is_view() else t
+    return (id(root), t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()), t.requires_grad)
+
+
+def nn1(rows, cols, form, norm, swap_norms=False, transform=VALUE_SQUARED, cache=True) -> NN1Result:
+    """One NN-1 sweep of every sample: row/column minima of d(i,j), lowest-index argmins and
+    per-sample sum / max (see pcd_nn1_forward in include/pcdist.h).
+
+    rows [B,N,3], cols [B,M,3]: fp32 CUDA tensors, any strides (pass `x.transpose(1, 2)` for a
+    channel-first [B,3,N] cloud).  A one-entry cache returns the previous result when called
+    again with the very same tensors (same storage, same version counter) and mode -- the
+    reference's losses recompute the same adv->ori nearest neighbours up to six times per
+    iteration (attack/GeoA3/GeoA3_attack.py:134-166, Chamfer then Hausdorff in CW).
+    """
+    _check_cloud(rows, "rows"); _check_cloud(cols, "cols")
+    if rows.shape[0] != cols.shape[0]:
+        raise ValueError("rows and cols must have the same batch dimension.")
+    if rows.device != cols.device:
+        raise ValueError("rows and cols must be on the same device")
+    if rows.shape[1] == 0 or cols.shape[1] == 0 or rows.shape[0] == 0:
+        raise ValueError("empty clouds are not supported (the reference's min() raises as well)")
+    key = None
+    if cache:
+        key = (_tensor_key(rows), _tensor_key(cols), form, norm, bool(swap_norms), transform,
+               torch.is_grad_enabled())
+        if _nn1_cache["key"] == key:
+            return _nn1_cache["val"]
+    out = _NN1.apply(rows, cols, form, norm, bool(swap_norms), transform)
+    res = NN1Result(out[0], out[1], out[2], out[3], out[4].t(), out[5].t())
+    if cache:
+        _nn1_cache["key"] = key
+        _nn1_cache["val"] = res
+        _nn1_cache["refs"] = (rows, cols)      # keeps the ids in the key from being recycled
+    return res
+
+
+def clear_cache():
+    _nn1_cache["key"] = None
+    _nn1_cache["val"] = None
+    _nn1_cache["refs"] = None
+
+
+# -------------------------------------------------------------------------------- k-NN
+class _KNN(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rows, cols, K, form, norm, swap_norms, want_dists):
+        global _launch_count
+        lib = _lib.load()
+        B, N, C = rows.shape
+        M = cols.shape[1]
+        dev = rows.device
+        with torch.cuda.device(dev):
+            dists = torch.empty((B, N, K), dtype=torch.float32, device=dev)
+            idx = torch.empty((B, N, K), dtype=torch.int32, device=dev)
+            ws_bytes = lib.pcd_knn_workspace_bytes(B, N, M, C, K)
+            ws = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=dev)
+            st = lib.pcd_knn_forward(*_cloud_args(rows), *_cloud_args(cols), B, N, M, C, K,
+                                     form, norm, int(swap_norms), dists.data_ptr(), idx.data_ptr(),
+                                     ws.data_ptr(), ws_bytes, _stream())
+            _lib.check(st, "pcd_knn_forward")
+        _launch_count += 2
+        ctx.save_for_backward(rows, cols, idx)
+        ctx.cfg = (int(swap_norms), K)
+        ctx.mark_non_differentiable(idx)
+        return dists, idx
+
+    @staticmethod
+    def backward(ctx, g_dists, _gi):
+        global _launch_count
+        rows, cols, idx = ctx.saved_tensors
+        swap_norms, K = ctx.cfg
+        need_r, need_c = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if g_dists is None or not (need_r or need_c):
+            return (None,) * 7
+        B, N, C = rows.shape
+        M = cols.shape[1]
+        if C != 3:
+            raise NotImplementedError("gradients of k-NN distances are provided for 3-channel clouds only "
+                                      "(the reference differentiates kNN distances on xyz only)")
+        lib = _lib.load()
+        dev = rows.device
+        with torch.cuda.device(dev):
+            g = g_dists.contiguous()
+            grad_rows = torch.empty((B, N, 3), dtype=torch.float32, device=dev) if need_r else None
+            grad_cols = torch.empty((B, M, 3), dtype=torch.float32, device=dev) if need_c else None
+            gr = _cloud_args(grad_rows) if need_r else [None, 0, 0, 0]
+            gc = _cloud_args(grad_cols) if need_c else [None, 0, 0, 0]
+            st = lib.pcd_knn_backward(*_cloud_args(rows), *_cloud_args(cols), B, N, M, K, swap_norms,
+                                      idx.data_ptr(), g.data_ptr(), *gr, *gc, _stream())
+            _lib.check(st, "pcd_knn_backward")
+        _launch_count += 2
+        return grad_rows, grad_cols, None, None, None, None, None
+
+
+def knn(rows, cols, K, form=FORM_COL_ROW, norm=NORM_MULSUM, swap_norms=False):
+    """K smallest d(i,j) per row, ascending by (distance, index): (dists[B,N,K] fp32,
+    idx[B,N,K] int32).  rows [B,N,C], cols [B,M,C] with 1 <= C <= 128 (any strides)."""
+    _check_cloud(rows, "rows", C=None); _check_cloud(cols, "cols", C=None)
+    if rows.shape[0] != cols.shape[0]:
+        raise ValueError("rows and cols must have the same batch dimension.")
+    if rows.shape[2] != cols.shape[2]:
+        raise ValueError("rows and cols must have the same point dimension.")
+    K = int(K)
+    if not 1 <= K <= min(cols.shape[1], _lib.KNN_MAX_K):
+        raise ValueError(f"K={K} out of range: need 1 <= K <= min(M={cols.shape[1]}, {_lib.KNN_MAX_K})")
+    if not 1 <= rows.shape[2] <= _lib.KNN_MAX_C:
+        raise ValueError(f"C={rows.shape[2]} out of range 1..{_lib.KNN_MAX_C}")
+    return _KNN.apply(rows, cols, K, form, norm, bool(swap_norms), True)
+
+
+# --------------------------------------------------------------------------- ball query
+def ball_query(radius, nsample, xyz, new_xyz):
+    """model/pointnet2_utils.py:84-104 semantics -> idx [B,S,nsample] int32."""
+    global _launch_count
+    _check_cloud(xyz, "xyz"); _check_cloud(new_xyz, "new_xyz")
+    lib = _lib.load()
+    B, N, _ = xyz.shape
+    S = new_xyz.shape[1]
+    dev = xyz.device
+    with torch.cuda.device(dev):
+        idx = torch.empty((B, S, int(nsample)), dtype=torch.int32, device=dev)
+        r2 = torch.tensor(float(radius) ** 2, dtype=torch.float32).item()   # fp32(radius**2), as the reference compares
+        st = lib.pcd_ball_query(*_cloud_args(xyz.detach()), *_cloud_args(new_xyz.detach()), B, N, S, r2,
+                                int(nsample), idx.data_ptr(), _stream())
+        _lib.check(st, "pcd_ball_query")
+    _launch_count += 1
+    return idx
+
+
+def fp32_peak_flops(iters=2048):
+    """Measured fp32 FMA peak of the current device (FLOP/s) -- roofline denominator."""
+    import ctypes
+    lib = _lib.load()
+    out = ctypes.c_double(0.0)
+    st = lib.pcd_measure_fp32_peak(int(iters), ctypes.byref(out), _stream())
+    _lib.check(st, "pcd_measure_fp32_peak")
+    return out.value

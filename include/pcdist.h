@@ -1,0 +1,185 @@
+/*
+ * pcdist.h -- C ABI of libpcdist.so, the B200 (sm_100a) point-set distance library.
+ *
+ * Drop-in boundary for the point-set distance hot path of LI-Yiquan/3DPointCloudAttack.
+ * The reference has no FFI for this path -- it is stock PyTorch (ATen) called from Python --
+ * so each entry point below names the reference Python symbols (file:line, relative to the
+ * reference root) whose arithmetic it replaces.  Bindings: ctypes (see INTEGRATION.md and
+ * 3dpointcloudattack_b200/_lib.py).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer on the current CUDA
+ *     device unless stated otherwise; `stream` is a cudaStream_t passed as void*.
+ *   - stream-ordered, re-entrant, allocation-free: the caller owns every input, output and
+ *     workspace buffer and keeps it alive until the stream work has completed.
+ *   - return value: 0 on success, otherwise a PCD_ERR_* code; pcd_last_error() gives a
+ *     thread-local message.  Nothing throws or exits across the ABI.
+ *   - there is NO CPU fallback.  Without a CUDA device every compute entry point returns
+ *     PCD_ERR_CUDA.
+ *   - clouds are fp32 with explicit element strides (batch, point, channel), so both the
+ *     [B,N,3] point-major and the [B,3,N] channel-first layouts of the reference are
+ *     accepted without a copy.  Indices are int32 on this side (N <= 2^31-1); the Python
+ *     shim widens to int64 where the reference returns LongTensors.
+ *
+ * Arithmetic contract (bit-faithful to the reference's expansion-form evaluation):
+ *     t(i,j) = -2 * fma(r_z,c_z, fma(r_y,c_y, r_x*c_x))           (GEMM, k ascending)
+ *     PCD_FORM_ROW_COL    d = (t + nrow[i]) + ncol[j]
+ *     PCD_FORM_COL_ROW    d = (t + ncol[j]) + nrow[i]
+ *     PCD_FORM_SUM_FIRST  d = (nrow[i] + ncol[j]) + t
+ * with every operation rounded to fp32 (no contraction beyond the stated FMAs).
+ * Ties: the lowest index wins (torch.min(dim) semantics).
+ */
+#ifndef PCDIST_H_
+#define PCDIST_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCD_VERSION 100
+
+enum pcd_status {
+    PCD_OK = 0,
+    PCD_ERR_ARG = 1,        /* bad shape / stride / enum / NULL pointer            */
+    PCD_ERR_WORKSPACE = 2,  /* workspace smaller than pcd_*_workspace_bytes()      */
+    PCD_ERR_CUDA = 3,       /* CUDA runtime error (launch, no device, ...)         */
+    PCD_ERR_UNSUPPORTED = 4 /* e.g. K > PCD_KNN_MAX_K, C > PCD_KNN_MAX_C           */
+};
+
+enum pcd_form { PCD_FORM_ROW_COL = 0, PCD_FORM_COL_ROW = 1, PCD_FORM_SUM_FIRST = 2 };
+
+/* How |p|^2 is rounded. MULSUM: ((x*x + y*y) + z*z) as torch.sum(p**2, dim);
+ * FMA: fma(z,z, fma(y,y, x*x)) as the diagonal of torch.bmm(p, p^T). */
+enum pcd_norm { PCD_NORM_MULSUM = 0, PCD_NORM_FMA = 1 };
+
+/* Value transform applied to the minima before they are stored / reduced.
+ * SQRT_CLAMP = sqrt(max(d, 0)): torch.cdist's clamp_min_(0).sqrt_(). */
+enum pcd_transform { PCD_VALUE_SQUARED = 0, PCD_VALUE_SQRT_CLAMP = 1 };
+
+#define PCD_KNN_MAX_K 64
+#define PCD_KNN_MAX_C 128
+
+int pcd_version(void);
+const char *pcd_last_error(void);
+
+/* ------------------------------------------------------------------------------------
+ * NN-1 sweep: one pass over the N x M pair matrix of every sample that yields the row
+ * minima (over j) AND the column minima (over i) with their lowest-index argmins, plus the
+ * per-sample sum / max / first-argmax of both -- everything Chamfer and Hausdorff need.
+ * The [B,N,M] matrix is never materialised.
+ *
+ * Replaces (forward):
+ *   utils/dis_utils_torch.py:8-28            pairwise_distances+chamfer/sgd_/bid_hausdorff_dis
+ *       form ROW_COL, norm MULSUM, transform SQRT_CLAMP, rows = a^T, cols = b^T
+ *   attack/CW/CW_utils/distance.py:15-70     batch_pairwise_dist + Chamfer/HausdorffDistance
+ *       form SUM_FIRST, norm FMA, rows = gts, cols = preds   (also Gen3DAdv, SIadv copies)
+ *   attack/GeoA3/knn_utils.py:10-55 (K = 1)  knn_points / apply_knn
+ *       form COL_ROW, norm MULSUM, swap_norms = 1, rows = p1, cols = p2
+ *
+ * rows  : [B,N,3] via strides (r_sb, r_sp, r_sc) in elements; cols likewise [B,M,3].
+ * swap_norms != 0 (requires N == M): nrow[i] = |cols_i|^2 and ncol[j] = |rows_j|^2 -- the
+ *   broadcast of attack/GeoA3/knn_utils.py:13-15.
+ * Outputs (any of the four per-point arrays may NOT be NULL):
+ *   row_min[B,N] row_arg[B,N] col_min[B,M] col_arg[B,M]   (values after `transform`)
+ *   stats_f[B,4] = {sum_i row_min, max_i row_min, sum_j col_min, max_j col_min}
+ *   stats_i[B,2] = {first argmax_i row_min, first argmax_j col_min}
+ * ---------------------------------------------------------------------------------- */
+size_t pcd_nn1_workspace_bytes(int B, int N, int M);
+
+int pcd_nn1_forward(const float *rows, int64_t r_sb, int64_t r_sp, int64_t r_sc,
+                    const float *cols, int64_t c_sb, int64_t c_sp, int64_t c_sc,
+                    int B, int N, int M,
+                    int form, int norm_kind, int swap_norms, int transform,
+                    float *row_min, int32_t *row_arg, float *col_min, int32_t *col_arg,
+                    float *stats_f, int32_t *stats_i,
+                    void *workspace, size_t workspace_bytes, void *stream);
+
+/* Profiling hook (bench.py): when both are non-NULL cudaEvent_t handles, every following
+ * pcd_nn1_forward on this host thread records them immediately before / after the sweep kernel
+ * launch on the caller's stream, so the dominant kernel can be timed live with CUDA events
+ * without a profiler.  Pass NULL, NULL to switch it off. */
+int pcd_nn1_set_sweep_events(void *start_event, void *stop_event);
+
+/* Backward of everything derived from the NN-1 minima, through the saved argmins
+ * (autograd of torch.min(dim) / torch.max / mean / cdist in the reference).
+ * The upstream gradient of row minimum (b,i) is
+ *     g_row[b,i] + w_row_all[b] + (i == row_argmax[b] ? w_row_max[b] : 0)
+ * (each term optional: NULL = 0), the same for columns.  So Chamfer (mean of minima:
+ * w_*_all = g/N), Hausdorff (max of minima: w_*_max) and knn_points(K=1).dists (g_row) are
+ * all one call.  For PCD_VALUE_SQRT_CLAMP row_min/col_min (the stored post-sqrt values) must
+ * be given: d/dp sqrt(d2) = (p - q)/sqrt(d2), 0 where it is 0 (cdist backward).
+ * grad_rows / grad_cols are written in full (no need to zero them) with the caller's strides;
+ * either may be NULL when that cloud needs no gradient.
+ * swap_norms: gradients of the swapped-norm surrogate exactly as autograd produces them
+ * (norm terms land on the *other* index, attack/GeoA3/knn_utils.py:13-15).
+ * ---------------------------------------------------------------------------------- */
+int pcd_nn1_backward(const float *rows, int64_t r_sb, int64_t r_sp, int64_t r_sc,
+                     const float *cols, int64_t c_sb, int64_t c_sp, int64_t c_sc,
+                     int B, int N, int M, int swap_norms, int transform,
+                     const int32_t *row_arg, const int32_t *col_arg,
+                     const float *row_min, const float *col_min,
+                     const float *g_row, const float *g_col,
+                     const float *w_row_all, const float *w_row_max, const int32_t *row_argmax,
+                     const float *w_col_all, const float *w_col_max, const int32_t *col_argmax,
+                     float *grad_rows, int64_t gr_sb, int64_t gr_sp, int64_t gr_sc,
+                     float *grad_cols, int64_t gc_sb, int64_t gc_sp, int64_t gc_sc,
+                     void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * k-NN select sweep: the K smallest d(i,j) of every row, ascending by (distance, index).
+ *
+ * Replaces:
+ *   attack/GeoA3/knn_utils.py:10-55 (K > 1)             form COL_ROW, swap_norms = 1
+ *   attack/CW/CW_utils/dist_utils.py:133-143 (KNNDist)  form COL_ROW, rows = cols = pc
+ *   model/dgcnn.py:194-200, model/curvenet_util.py:10-26, attack/AOF/TAOF_attack.py:13-28
+ *       form COL_ROW on C-channel features (the reference's negated matrix + topk largest)
+ *   model/pointnet2_utils.py:293-300 (3-NN of feature propagation)  form ROW_COL
+ *
+ * rows [B,N,C], cols [B,M,C] via strides; 1 <= C <= PCD_KNN_MAX_C, 1 <= K <= min(M,
+ * PCD_KNN_MAX_K).  dists[B,N,K] fp32 (may be NULL), idx[B,N,K] int32.
+ * ---------------------------------------------------------------------------------- */
+size_t pcd_knn_workspace_bytes(int B, int N, int M, int C, int K);
+
+int pcd_knn_forward(const float *rows, int64_t r_sb, int64_t r_sp, int64_t r_sc,
+                    const float *cols, int64_t c_sb, int64_t c_sp, int64_t c_sc,
+                    int B, int N, int M, int C, int K,
+                    int form, int norm_kind, int swap_norms,
+                    float *dists, int32_t *idx,
+                    void *workspace, size_t workspace_bytes, void *stream);
+
+/* Backward of dists[B,N,K] w.r.t. both clouds through idx (3-channel clouds).
+ * g_dists[B,N,K] upstream.  grad_* are written in full. */
+int pcd_knn_backward(const float *rows, int64_t r_sb, int64_t r_sp, int64_t r_sc,
+                     const float *cols, int64_t c_sb, int64_t c_sp, int64_t c_sc,
+                     int B, int N, int M, int K, int swap_norms,
+                     const int32_t *idx, const float *g_dists,
+                     float *grad_rows, int64_t gr_sb, int64_t gr_sp, int64_t gr_sc,
+                     float *grad_cols, int64_t gc_sb, int64_t gc_sp, int64_t gc_sc,
+                     void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * Ordered ball query.  Replaces model/pointnet2_utils.py:84-104 (query_ball_point; copies in
+ * pointnet/pointnet2_utils.py, model/curvenet_util.py:38-113, DUP_Net/pu_utils.py):
+ * the first `nsample` indices j (ascending) with NOT(d(i,j) > radius2), d in form ROW_COL
+ * with MULSUM norms (square_distance, :35-37), padded with the first hit; a row without any
+ * hit is filled with N.  new_xyz [B,S,3] are the rows, xyz [B,N,3] the columns.
+ * ---------------------------------------------------------------------------------- */
+int pcd_ball_query(const float *xyz, int64_t x_sb, int64_t x_sp, int64_t x_sc,
+                   const float *new_xyz, int64_t q_sb, int64_t q_sp, int64_t q_sc,
+                   int B, int N, int S, float radius2, int nsample,
+                   int32_t *idx, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * Measurement helper (bench.py): runs an FFMA-only micro-kernel and returns the achieved
+ * fp32 FLOP/s in *flops_per_s (host pointer).  This is the measured roofline denominator for
+ * the sweep kernels (the FP32 FMA peak is not in MEASURED_PEAKS.json).
+ * ---------------------------------------------------------------------------------- */
+int pcd_measure_fp32_peak(int iters, double *flops_per_s, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCDIST_H_ */

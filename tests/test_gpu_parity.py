@@ -1,0 +1,375 @@
+"""GPU parity: the sm_100a kernels (through the ctypes C ABI and the drop-in Python surface)
+against the CPU oracle and against the golden vectors produced by the unmodified reference.
+
+Bar (BASELINE.json north_star): argmin / kNN indices bit-exact under the lowest-index tie-break,
+distances and gradients within 1e-5 relative (fp32).  Where the arithmetic is op-order
+faithful we assert the stronger property: bit-identical fp32 values.
+"""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_inf
+from oracle import pcd_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+pcd = importlib.import_module("3dpointcloudattack_b200")
+F = pcd.functional
+
+RTOL = 1e-5
+
+
+def cu(a, grad=False):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return t.requires_grad_(grad)
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+FORMS = {
+    "row_col_mulsum": (F.FORM_ROW_COL, F.NORM_MULSUM, O.FORM_ROW_COL, O.NORM_MULSUM),
+    "col_row_mulsum": (F.FORM_COL_ROW, F.NORM_MULSUM, O.FORM_COL_ROW, O.NORM_MULSUM),
+    "sum_first_fma": (F.FORM_SUM_FIRST, F.NORM_FMA, O.FORM_SUM_FIRST, O.NORM_FMA),
+}
+
+
+def oracle_nn1(rows, cols, oform, onorm, swap=False):
+    nr, nc = O.norms(onorm, rows), O.norms(onorm, cols)
+    if swap:
+        nr, nc = O.norms(onorm, cols), O.norms(onorm, rows)
+    return O.nn1(oform, rows, cols, nr, nc)
+
+
+def check_nn1(rows, cols, form_key, swap=False):
+    form, norm, oform, onorm = FORMS[form_key]
+    r = F.nn1(cu(rows), cu(cols), form, norm, swap_norms=swap, cache=False)
+    o = oracle_nn1(rows, cols, oform, onorm, swap)
+    assert np.array_equal(npy(r.row_min), o.row_min)
+    assert np.array_equal(npy(r.col_min), o.col_min)
+    assert np.array_equal(npy(r.row_arg), o.row_arg)
+    assert np.array_equal(npy(r.col_arg), o.col_arg)
+    st = npy(r.stats)
+    np.testing.assert_allclose(st[0], o.row_min.sum(1, dtype=np.float64), rtol=2e-6)
+    np.testing.assert_allclose(st[2], o.col_min.sum(1, dtype=np.float64), rtol=2e-6)
+    assert np.array_equal(st[1], o.row_min.max(1)) and np.array_equal(st[3], o.col_min.max(1))
+    sa = npy(r.stats_arg)
+    assert np.array_equal(sa[0], o.row_min.argmax(1)) and np.array_equal(sa[1], o.col_min.argmax(1))
+
+
+# ------------------------------------------------------------------ NN-1 sweep vs the oracle
+@pytest.mark.parametrize("form_key", list(FORMS))
+@pytest.mark.parametrize("shape", [(1, 1, 1), (2, 33, 257), (3, 700, 1000), (1, 1025, 31), (2, 1024, 1024),
+                                   (5, 300, 300), (1, 4096, 4096), (4, 2048, 513)])
+def test_nn1_bit_exact_random(form_key, shape):
+    B, N, M = shape
+    rs = np.random.RandomState(B * 7919 + N * 31 + M)
+    cols = (rs.rand(B, M, 3) - 0.5).astype(np.float32)
+    rows = (rs.rand(B, N, 3) - 0.5).astype(np.float32)
+    k = min(N, M)
+    rows[:, :k] = cols[:, :k] + 0.01 * rs.randn(B, k, 3).astype(np.float32)
+    check_nn1(rows, cols, form_key)
+
+
+@pytest.mark.parametrize("form_key", list(FORMS))
+def test_nn1_swapped_norms(form_key):
+    g = load_golden("a3_knn_utils")
+    check_nn1(g["adv"], g["ori"], form_key, swap=True)
+
+
+@pytest.mark.parametrize("form_key", list(FORMS))
+def test_nn1_ties_and_duplicates(form_key):
+    g = load_golden("a2_distance_ties")
+    check_nn1(g["gts"], g["preds"], form_key)
+    # all points identical: every distance equal -> every argmin must be index 0
+    same = np.full((2, 300, 3), 0.25, np.float32)
+    form, norm, _, _ = FORMS[form_key]
+    r = F.nn1(cu(same), cu(same[:, :77]), form, norm, cache=False)
+    assert int(r.row_arg.abs().max()) == 0 and int(r.col_arg.abs().max()) == 0
+    # integer grid: exact ties everywhere
+    gx = np.stack(np.meshgrid(np.arange(8), np.arange(8), np.arange(8), indexing="ij"), -1).reshape(1, -1, 3)
+    check_nn1(gx.astype(np.float32), (gx[:, ::3] + 0.5).astype(np.float32), form_key)
+
+
+@pytest.mark.parametrize("layout", ["channel_first", "strided"])
+def test_nn1_layouts(layout):
+    rs = np.random.RandomState(5)
+    rows = rs.randn(2, 500, 3).astype(np.float32); cols = rs.randn(2, 400, 3).astype(np.float32)
+    if layout == "channel_first":
+        tr = cu(np.ascontiguousarray(rows.transpose(0, 2, 1))).transpose(1, 2)
+        tc = cu(np.ascontiguousarray(cols.transpose(0, 2, 1))).transpose(1, 2)
+    else:
+        big_r = torch.zeros(2, 500, 7, device="cuda"); big_r[:, :, 2:5] = cu(rows); tr = big_r[:, :, 2:5]
+        big_c = torch.zeros(3, 400, 3, device="cuda"); big_c[1:] = cu(cols); tc = big_c[1:]
+    r = F.nn1(tr, tc, F.FORM_SUM_FIRST, F.NORM_FMA, cache=False)
+    o = oracle_nn1(rows, cols, O.FORM_SUM_FIRST, O.NORM_FMA)
+    assert np.array_equal(npy(r.row_min), o.row_min) and np.array_equal(npy(r.col_arg), o.col_arg)
+
+
+@pytest.mark.parametrize("env", [("2", "32"), ("4", "64"), ("8", "256"), ("8", "128")])
+def test_nn1_every_tiling(env, monkeypatch):
+    monkeypatch.setenv("PCD_SWEEP_R", env[0]); monkeypatch.setenv("PCD_SWEEP_MT", env[1])
+    g = load_golden("a2_distance_ragged")
+    check_nn1(g["gts"], g["preds"], "sum_first_fma")
+    rs = np.random.RandomState(1)
+    check_nn1(rs.randn(3, 1500, 3).astype(np.float32), rs.randn(3, 2100, 3).astype(np.float32), "row_col_mulsum")
+
+
+def test_nn1_full_size_c2_against_oracle():
+    """BASELINE config 2 (B=32, N=M=4096, sigma=0.01): every index and value against the C oracle."""
+    synth = importlib.import_module("3dpointcloudattack_b200.synth")
+    ori = synth.face_clouds(32, 4096, seed=1234)
+    adv = synth.perturb(ori, 0.01, seed=99)
+    check_nn1(ori.numpy(), adv.numpy(), "sum_first_fma")
+
+
+def test_nn1_large_properties():
+    """Size-independent properties at a size the oracle is not asked to do: role swap symmetry
+    (rows<->cols gives transposed answers bit-for-bit for the symmetric form) and idempotence."""
+    synth = importlib.import_module("3dpointcloudattack_b200.synth")
+    ori = synth.face_clouds(8, 16384, seed=7).cuda(); adv = synth.perturb(ori.cpu(), 0.01, seed=8).cuda()
+    a = F.nn1(ori, adv, F.FORM_SUM_FIRST, F.NORM_FMA, cache=False)
+    b = F.nn1(adv, ori, F.FORM_SUM_FIRST, F.NORM_FMA, cache=False)
+    assert torch.equal(a.row_min, b.col_min) and torch.equal(a.col_min, b.row_min)
+    assert torch.equal(a.row_arg, b.col_arg) and torch.equal(a.col_arg, b.row_arg)
+    c = F.nn1(ori, adv, F.FORM_SUM_FIRST, F.NORM_FMA, cache=False)
+    assert torch.equal(a.row_min, c.row_min) and torch.equal(a.col_arg, c.col_arg)
+    # a cloud against itself: every point's nearest neighbour is itself at (rounded) zero
+    s = F.nn1(ori, ori, F.FORM_SUM_FIRST, F.NORM_FMA, cache=False)
+    ar = torch.arange(16384, device="cuda", dtype=torch.int32).expand(8, -1)
+    assert torch.equal(s.row_arg, ar) and torch.equal(s.col_arg, ar)
+
+
+# ------------------------------------------------- a2: distance.py against the reference
+@pytest.mark.parametrize("tag", ["face", "iter0", "ragged"])
+def test_a2_distance_vs_reference(tag):
+    g = load_golden("a2_distance_" + tag)
+    for name, mod in (("chamfer", pcd.distance.chamfer), ("hausdorff", pcd.distance.hausdorff)):
+        p, t = cu(g["preds"], True), cu(g["gts"], True)
+        l1, l2 = mod(p, t)
+        ((l1 * cu(g["g1"])).sum() + (l2 * cu(g["g2"])).sum()).backward()
+        np.testing.assert_allclose(npy(l1), g[name + "_l1"], rtol=RTOL, atol=1e-12)
+        np.testing.assert_allclose(npy(l2), g[name + "_l2"], rtol=RTOL, atol=1e-12)
+        if tag != "iter0":      # |adv-ori| ~ 1e-7: the reference's own fp32 gradient is rounding noise
+            assert rel_inf(npy(p.grad), g[name + "_gp"]) < RTOL
+            assert rel_inf(npy(t.grad), g[name + "_gg"]) < RTOL
+        gp, gg = (O.chamfer_distance_grads if name == "chamfer" else O.hausdorff_distance_grads)(
+            g["preds"], g["gts"], g["g1"], g["g2"])
+        assert rel_inf(npy(p.grad), gp) < RTOL and rel_inf(npy(t.grad), gg) < RTOL
+    r = F.nn1(cu(g["gts"]), cu(g["preds"]), F.FORM_SUM_FIRST, F.NORM_FMA, cache=False)
+    assert np.array_equal(npy(r.row_min), g["row_min"]) and np.array_equal(npy(r.col_min), g["col_min"])
+    assert np.array_equal(npy(r.row_arg), g["row_arg"]) and np.array_equal(npy(r.col_arg), g["col_arg"])
+
+
+def test_a2_set_distance_variant():
+    g = load_golden("a2_set_distance")
+    np.testing.assert_allclose(npy(pcd.set_distance.chamfer(cu(g["preds"]), cu(g["gts"]))), g["chamfer"], rtol=RTOL)
+    np.testing.assert_allclose(npy(pcd.set_distance.hausdorff(cu(g["preds"]), cu(g["gts"]))), g["hausdorff"], rtol=RTOL)
+
+
+def test_fused_chamfer_hausdorff_shares_one_sweep():
+    g = load_golden("a2_distance_face")
+    p, t = cu(g["preds"], True), cu(g["gts"])
+    n0 = F.launches()
+    c1, c2 = pcd.distance.chamfer(p, t)
+    h1, h2 = pcd.distance.hausdorff(p, t)
+    assert F.launches() - n0 == 4          # second call is served by the one-entry cache
+    (c1.sum() + c2.sum() + h1.sum() + h2.sum()).backward()
+    with torch.no_grad():
+        p.add_(0.001)                        # in-place update bumps the version -> no stale hit
+    c1b, _ = pcd.distance.chamfer(p, t)
+    assert F.launches() - n0 == 4 + 2 + 4
+    assert not torch.equal(c1, c1b)
+
+
+# ------------------------------------------------- a1: dis_utils_torch.py against the reference
+def test_a1_dis_utils_torch_vs_reference():
+    g = load_golden("a1_dis_utils_torch")
+    D = pcd.dis_utils_torch
+    for fn in ("chamfer", "sgd_hausdorff_dis", "bid_hausdorff_dis"):
+        a, b = cu(g["a"], True), cu(g["b"], True)
+        v = getattr(D, fn)(a, b)
+        assert v.dim() == 0
+        v.backward()
+        np.testing.assert_allclose(npy(v), g[fn], rtol=RTOL)
+        assert rel_inf(npy(a.grad), g[fn + "_ga"]) < RTOL, fn
+        assert rel_inf(npy(b.grad), g[fn + "_gb"]) < RTOL, fn
+    np.testing.assert_allclose(npy(D.chamfer(cu(g["ka"]), cu(g["kb"]))), g["k_chamfer"], rtol=RTOL)
+    np.testing.assert_allclose(npy(D.sgd_hausdorff_dis(cu(g["ka"]), cu(g["kb"]))), g["k_sgd"], rtol=RTOL)
+    np.testing.assert_allclose(npy(D.bid_hausdorff_dis(cu(g["ka"]), cu(g["kb"]))), g["k_bid"], rtol=RTOL)
+    # oracle (correctly rounded sqrt) agrees bit for bit on the reductions that do not sum
+    assert npy(D.sgd_hausdorff_dis(cu(g["a"]), cu(g["b"]))) == O.dis_sgd_hausdorff(g["a"], g["b"])
+    assert npy(D.bid_hausdorff_dis(cu(g["a"]), cu(g["b"]))) == O.dis_bid_hausdorff(g["a"], g["b"])
+
+
+# ------------------------------------------------- L3 wrappers against the reference
+def test_l3_dist_utils_vs_reference():
+    g = load_golden("l3_dist_utils")
+    DU = pcd.dist_utils
+    w = torch.from_numpy(g["weights"])          # CPU weights, like the reference's callers pass
+    for method in ("adv2ori", "ori2adv", "avg"):
+        for cls in ("ChamferDist", "HausdorffDist"):
+            a = cu(g["adv"], True)
+            v = getattr(DU, cls)(method=method)(a, cu(g["ori"]), weights=w, batch_avg=False)
+            (v * cu(g["gB"])).sum().backward()
+            np.testing.assert_allclose(npy(v), g[f"{cls}_{method}"], rtol=RTOL)
+            assert rel_inf(npy(a.grad), g[f"{cls}_{method}_g"]) < RTOL
+    a = cu(g["adv"], True)
+    v = DU.ChamferDist()(a, cu(g["ori"])); v.backward()
+    np.testing.assert_allclose(npy(v), g["ChamferDist_default_mean"], rtol=RTOL)
+    assert rel_inf(npy(a.grad), g["ChamferDist_default_mean_g"]) < RTOL
+    for k in (5, 16):
+        a = cu(g["adv"], True)
+        v = DU.KNNDist(k=k, alpha=1.05)(a, weights=w, batch_avg=False)
+        (v * cu(g["gB"])).sum().backward()
+        np.testing.assert_allclose(npy(v), g[f"KNNDist_k{k}"], rtol=RTOL)
+        assert rel_inf(npy(a.grad), g[f"KNNDist_k{k}_g"]) < RTOL
+    a = cu(g["adv"], True)
+    v = DU.ChamferkNNDist(knn_k=16)(a, cu(g["ori"]), weights=w, batch_avg=True); v.backward()
+    np.testing.assert_allclose(npy(v), g["ChamferkNNDist_k16"], rtol=RTOL)
+    assert rel_inf(npy(a.grad), g["ChamferkNNDist_k16_g"]) < RTOL
+
+
+# ------------------------------------------------- a3: knn_utils.py against the reference
+def assert_knn_idx(idx, ref_idx, dists, matrix):
+    """Same contract as tests/test_oracle_golden.py: bit-identical distances at every rank;
+    where indices differ it is an exact tie and ours are the lowest tied indices."""
+    ref_d = np.take_along_axis(matrix, ref_idx.astype(np.int64), axis=2)
+    assert np.array_equal(ref_d, dists)
+    diff = idx != ref_idx
+    assert diff.mean() < 0.01
+    for b, r, c in np.argwhere(diff):
+        tied = dists[b, r] == dists[b, r, c]
+        lo = np.flatnonzero(matrix[b, r] == dists[b, r, c])
+        assert sorted(idx[b, r][tied]) == sorted(lo[:tied.sum()])
+
+
+def test_a3_knn_points_vs_reference():
+    g = load_golden("a3_knn_utils")
+    KU = pcd.knn_utils
+    for tag, p1, p2, K in (("cross1", g["adv"], g["ori"], 1), ("self17", g["adv"], g["adv"], 17),
+                           ("cross4", g["ori"], g["adv"], 4)):
+        same = p1 is p2
+        a = cu(p1, True); b = a if same else cu(p2, True)
+        r = KU.knn_points(a, b, K=K, return_nn=True)
+        assert r.idx.dtype == torch.int64 and tuple(r.dists.shape) == g[tag + "_dists"].shape
+        (r.dists * cu(g[tag + "_gw"])).sum().backward()
+        assert np.array_equal(npy(r.dists), g[tag + "_dists"]), tag
+        od, oi = O.knn_points(p1, p2, K)
+        assert np.array_equal(npy(r.idx), oi), tag                      # lowest-index contract
+        assert_knn_idx(npy(r.idx), g[tag + "_idx"], npy(r.dists), O.knn_points_matrix(p1, p2))
+        assert np.array_equal(npy(r.knn), O.knn_gather(p2, oi))
+        assert rel_inf(npy(a.grad), g[tag + "_g1"]) < RTOL, tag
+        if not same:
+            assert rel_inf(npy(b.grad), g[tag + "_g2"]) < RTOL, tag
+    out = KU.knn_gather(cu(g["gather_x"]), torch.from_numpy(g["self17_idx"]).cuda())
+    assert np.array_equal(npy(out), g["gather_out"])
+    with pytest.raises(RuntimeError):
+        KU.knn_points(cu(g["adv"][:, :100]), cu(g["ori"][:, :90]), K=1)
+    with pytest.raises(ValueError):
+        KU.knn_points(cu(g["adv"][:1]), cu(g["ori"]), K=1)
+
+
+@pytest.mark.parametrize("K", [1, 2, 5, 17, 21, 32, 33, 64])
+@pytest.mark.parametrize("form_key", ["col_row_mulsum", "row_col_mulsum"])
+def test_knn_bit_exact_random(K, form_key):
+    form, norm, oform, onorm = FORMS[form_key]
+    rs = np.random.RandomState(K)
+    rows = rs.randn(2, 333, 3).astype(np.float32); cols = rs.randn(2, 1100, 3).astype(np.float32)
+    cols[:, 500:600] = cols[:, :100]            # duplicated candidates: exact ties
+    d, i = F.knn(cu(rows), cu(cols), K, form=form, norm=norm)
+    od, oi = O.knn(oform, rows, cols, O.norms(onorm, rows), O.norms(onorm, cols), K)
+    assert np.array_equal(npy(d), od) and np.array_equal(npy(i), oi)
+
+
+@pytest.mark.parametrize("C", [1, 2, 5, 64, 128])
+def test_knn_feature_channels(C):
+    rs = np.random.RandomState(C)
+    x = rs.randn(2, 300, C).astype(np.float32)
+    d, i = F.knn(cu(x), cu(x), 20)
+    nrm = O.norms(O.NORM_MULSUM, x)
+    od, oi = O.knn(O.FORM_COL_ROW, x, x, nrm, nrm, 20)
+    assert np.array_equal(npy(d), od) and np.array_equal(npy(i), oi)
+
+
+# ------------------------------------------------- a4: GeoA3 losses against the reference
+def test_a4_geoa3_losses_vs_reference():
+    g = load_golden("a4_geoa3_losses")
+    LU = pcd.loss_utils
+    for fn in ("chamfer_loss", "pseudo_chamfer_loss", "hausdorff_loss"):
+        a = cu(g["adv"], True)
+        v = getattr(LU, fn)(a, cu(g["ori"])); (v * cu(g["gB"])).sum().backward()
+        np.testing.assert_allclose(npy(v), g[fn], rtol=RTOL)
+        assert rel_inf(npy(a.grad), g[fn + "_g"]) < RTOL, fn
+    a = cu(g["adv"], True)
+    v = LU.kNN_smoothing_loss(a, 16); (v * cu(g["gB"])).sum().backward()
+    np.testing.assert_allclose(npy(v), g["kNN_smoothing_loss"], rtol=RTOL)
+    assert rel_inf(npy(a.grad), g["kNN_smoothing_loss_g"]) < 2e-5
+    ori_kappa = LU._get_kappa_ori(cu(g["ori"]), cu(g["normal"]), 16)
+    np.testing.assert_allclose(npy(ori_kappa), g["ori_kappa"], rtol=1e-4, atol=1e-6)
+    a = cu(g["adv"], True)
+    adv_kappa, normal_curr = LU._get_kappa_adv(a, cu(g["ori"]), cu(g["normal"]), 16)
+    assert np.array_equal(npy(normal_curr), g["normal_curr"])
+    np.testing.assert_allclose(npy(adv_kappa), g["adv_kappa"], rtol=1e-4, atol=1e-6)
+    v = LU.curvature_loss(a, cu(g["ori"]), adv_kappa, ori_kappa); (v * cu(g["gB"])).sum().backward()
+    np.testing.assert_allclose(npy(v), g["curvature_loss"], rtol=1e-4)
+    assert rel_inf(npy(a.grad), g["curvature_loss_g"]) < 1e-4
+
+
+# ------------------------------------------------- a6 / a7 against the reference
+def test_a6_knn_graph_vs_reference():
+    g = load_golden("a6_knn_graph")
+    x3 = cu(g["x3"])
+    pm = O._cf_to_pm(g["x3"]); nrm = O.norms(O.NORM_MULSUM, pm)
+    mat = -O.dgcnn_neg_matrix(g["x3"])
+    d20, i20 = O.knn(O.FORM_COL_ROW, pm, pm, nrm, nrm, 20)
+    d21, i21 = O.knn(O.FORM_COL_ROW, pm, pm, nrm, nrm, 21)
+    ours = pcd.dgcnn.knn(x3, 20)
+    assert ours.dtype == torch.int64 and np.array_equal(npy(ours), i20)
+    assert_knn_idx(npy(ours), g["dgcnn_k20"], d20, mat)
+    assert np.array_equal(npy(pcd.curvenet_util.knn(x3, 20)), i21)
+    assert_knn_idx(npy(pcd.curvenet_util.knn(x3, 20)), g["curvenet_k20"], d21, mat)
+    assert np.array_equal(npy(pcd.curvenet_util.normal_knn(x3, 20)), i20)
+    f64 = cu(g["f64"])
+    assert np.array_equal(npy(pcd.dgcnn.knn(f64, 20)), O.dgcnn_knn(g["f64"], 20))
+    assert (npy(pcd.dgcnn.knn(f64, 20)) == g["dgcnn_f64_k20"]).mean() > 0.999
+    # get_graph_feature: gather + concat, compared with a direct numpy restatement
+    feat = npy(pcd.dgcnn.get_graph_feature(x3, k=20))
+    xt = g["x3"].transpose(0, 2, 1)
+    nb = xt[np.arange(2)[:, None, None], i20]
+    ref = np.concatenate([nb - xt[:, :, None, :], np.broadcast_to(xt[:, :, None, :], nb.shape)], -1).transpose(0, 3, 1, 2)
+    assert np.array_equal(feat, ref)
+
+
+def test_a7_pointnet2_utils_vs_reference():
+    g = load_golden("a7_pointnet2_utils")
+    P2 = pcd.pointnet2_utils
+    xyz, new_xyz = cu(g["xyz"]), cu(g["new_xyz"])
+    q = P2.query_ball_point(0.2, 32, xyz, new_xyz)
+    assert q.dtype == torch.int64 and np.array_equal(npy(q), g["ball_r02_n32"])
+    assert np.array_equal(npy(P2.query_ball_point(0.4, 64, xyz[:, :512], new_xyz[:, :128])), g["ball_r04_n64"])
+    assert np.array_equal(npy(P2.query_ball_point(0.02, 8, xyz, new_xyz[:, :64])), g["ball_r002_n8"])
+    # radius so small that rows without any hit exist -> filled with N
+    far = new_xyz[:, :16] + 10.0
+    assert np.array_equal(npy(P2.query_ball_point(0.01, 4, xyz, far)), O.query_ball_point(0.01, 4, g["xyz"], npy(far)))
+    np.testing.assert_allclose(npy(P2.square_distance(new_xyz[:, :64], xyz[:, :96])), g["sqdist_block"], atol=1e-6)
+
+
+# ------------------------------------------------- error behaviour
+def test_errors_are_loud():
+    with pytest.raises(RuntimeError):
+        F.nn1(torch.zeros(1, 4, 3), torch.zeros(1, 4, 3), F.FORM_SUM_FIRST, F.NORM_FMA)     # CPU tensors
+    with pytest.raises(ValueError):
+        F.nn1(torch.zeros(1, 4, 3, device="cuda"), torch.zeros(2, 4, 3, device="cuda"), 0, 0)
+    with pytest.raises(TypeError):
+        F.nn1(torch.zeros(1, 4, 3, device="cuda", dtype=torch.float64), torch.zeros(1, 4, 3, device="cuda"), 0, 0)
+    with pytest.raises(ValueError):
+        F.knn(torch.zeros(1, 4, 3, device="cuda"), torch.zeros(1, 4, 3, device="cuda"), 5)       # K > M
+    lib = pcd._lib.load()
+    assert lib.pcd_nn1_forward(None, 0, 0, 0, None, 0, 0, 0, 1, 1, 1, 0, 0, 0, 0,
+                               None, None, None, None, None, None, None, 0, None) == 1
+    assert b"NULL" in lib.pcd_last_error()

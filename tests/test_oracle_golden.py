@@ -134,3 +134,17 @@ def test_topk_tie_rule_is_lowest_index():
     d, i = O.knn(O.FORM_COL_ROW, pc, pc, O.norms(0, pc), O.norms(0, pc), 3)
     assert i[0, 0].tolist() == [0, 1, 2]
     assert i[0, 1].tolist() == [1, 2, 3]
+
+
+def test_ref_torch_port_matches_golden():
+    """bench.py's CPU baseline is a torch restatement of the reference path; pin it too."""
+    import torch
+    from oracle import ref_torch_port as RP
+    g = load_golden("a2_distance_face")
+    p, t = torch.from_numpy(g["preds"]), torch.from_numpy(g["gts"])
+    c1, c2 = RP.chamfer_distance(p, t)
+    h1, h2 = RP.hausdorff_distance(p, t)
+    np.testing.assert_allclose(c1.numpy(), g["chamfer_l1"], rtol=1e-6)
+    np.testing.assert_allclose(c2.numpy(), g["chamfer_l2"], rtol=1e-6)
+    assert np.array_equal(h1.numpy(), g["hausdorff_l1"]) and np.array_equal(h2.numpy(), g["hausdorff_l2"])
+    assert np.array_equal(RP.batch_pairwise_dist(t, p)[:, :64, :48].numpy(), g["P_block"])
