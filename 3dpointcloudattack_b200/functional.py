@@ -54,9 +54,17 @@ NN1Result = namedtuple("NN1Result", "row_min row_arg col_min col_arg stats stats
 # stats_arg: [2, B] int32 = (first argmax_i row_min, first argmax_j col_min)
 
 
+class _Token:
+    """Marks a cached NN-1 result whose autograd graph has been consumed by backward()."""
+    __slots__ = ("consumed",)
+
+    def __init__(self):
+        self.consumed = False
+
+
 class _NN1(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, rows, cols, form, norm, swap_norms, transform):
+    def forward(ctx, rows, cols, form, norm, swap_norms, transform, token):
         global _launch_count
         lib = _lib.load()
         B, N, _ = rows.shape
@@ -80,6 +88,7 @@ class _NN1(torch.autograd.Function):
         _launch_count += 4
         ctx.save_for_backward(rows, cols, row_arg, col_arg, row_min, col_min, stats_i_bt)
         ctx.cfg = (int(swap_norms), transform)
+        ctx.token = token
         ctx.mark_non_differentiable(row_arg, col_arg, stats_i_bt)
         return row_min, row_arg, col_min, col_arg, stats_bt, stats_i_bt
 
@@ -88,12 +97,13 @@ class _NN1(torch.autograd.Function):
         global _launch_count
         rows, cols, row_arg, col_arg, row_min, col_min, stats_i = ctx.saved_tensors
         swap_norms, transform = ctx.cfg
+        ctx.token.consumed = True          # the graph is (normally) freed after this: never serve it again
         lib = _lib.load()
         B, N, _ = rows.shape
         M = cols.shape[1]
         need_r, need_c = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if not (need_r or need_c):
-            return (None,) * 6
+            return (None,) * 7
         dev = rows.device
         with torch.cuda.device(dev):
             g_row = None if g_row_min is None else g_row_min.contiguous()
@@ -117,10 +127,10 @@ class _NN1(torch.autograd.Function):
                                       *gr, *gc, _stream())
             _lib.check(st, "pcd_nn1_backward")
         _launch_count += 2
-        return grad_rows, grad_cols, None, None, None, None
+        return grad_rows, grad_cols, None, None, None, None, None
 
 
-_nn1_cache = {"key": None, "val": None, "refs": None}
+_nn1_cache = {"key": None, "val": None, "refs": None, "token": None}
 
 
 def _tensor_key(t):
@@ -151,14 +161,16 @@ def nn1(rows, cols, form, norm, swap_norms=False, transform=VALUE_SQUARED, cache
     if cache:
         key = (_tensor_key(rows), _tensor_key(cols), form, norm, bool(swap_norms), transform,
                torch.is_grad_enabled())
-        if _nn1_cache["key"] == key:
+        if _nn1_cache["key"] == key and not _nn1_cache["token"].consumed:
             return _nn1_cache["val"]
-    out = _NN1.apply(rows, cols, form, norm, bool(swap_norms), transform)
+    token = _Token()
+    out = _NN1.apply(rows, cols, form, norm, bool(swap_norms), transform, token)
     res = NN1Result(out[0], out[1], out[2], out[3], out[4].t(), out[5].t())
     if cache:
         _nn1_cache["key"] = key
         _nn1_cache["val"] = res
         _nn1_cache["refs"] = (rows, cols)      # keeps the ids in the key from being recycled
+        _nn1_cache["token"] = token
     return res
 
 
@@ -166,6 +178,7 @@ def clear_cache():
     _nn1_cache["key"] = None
     _nn1_cache["val"] = None
     _nn1_cache["refs"] = None
+    _nn1_cache["token"] = None
 
 
 # -------------------------------------------------------------------------------- k-NN

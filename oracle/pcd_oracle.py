@@ -151,6 +151,31 @@ def dis_bid_hausdorff(a, b):
     return np.maximum(dis_sgd_hausdorff(a, b), dis_sgd_hausdorff(b, a))
 
 
+def dis_grads(a, b, w_col_sum=0.0, w_row_sum=0.0, w_row_max=0.0, w_col_max=0.0):
+    """float64 closed-form gradient (through the fp32 argmins) of
+         w_col_sum * sum_j min_i M + w_row_sum * sum_i min_j M + w_row_max * max_i min_j M
+         + w_col_max * max_j min_i M            for sample 0 of utils/dis_utils_torch.py's M,
+    i.e. chamfer = (1/3, 1/3, 0, 0), sgd_hausdorff = (0, 0, 1, 0).  d sqrt(d2)/dp = (p - q)/M,
+    0 where M == 0 (cdist backward).  Returns (grad_a, grad_b) shaped like the inputs."""
+    A, Bm = _cf_to_pm(a)[:1], _cf_to_pm(b)[:1]
+    r = nn1(FORM_ROW_COL, A, Bm, norms(NORM_MULSUM, A), norms(NORM_MULSUM, Bm))
+    A64, B64 = A[0].astype(np.float64), Bm[0].astype(np.float64)
+    ga = np.zeros_like(A64); gb = np.zeros_like(B64)
+    rowv = np.sqrt(np.maximum(r.row_min[0], 0)).astype(np.float64)
+    colv = np.sqrt(np.maximum(r.col_min[0], 0)).astype(np.float64)
+    gr = np.full(A64.shape[0], float(w_row_sum)); gr[int(np.argmax(rowv))] += float(w_row_max)
+    gc = np.full(B64.shape[0], float(w_col_sum)); gc[int(np.argmax(colv))] += float(w_col_max)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        fr = np.where(rowv > 0, gr / rowv, 0.0); fc = np.where(colv > 0, gc / colv, 0.0)
+    diff = A64 - B64[r.row_arg[0]]
+    ga += fr[:, None] * diff; np.add.at(gb, r.row_arg[0], -fr[:, None] * diff)
+    diff = B64 - A64[r.col_arg[0]]
+    gb += fc[:, None] * diff; np.add.at(ga, r.col_arg[0], -fc[:, None] * diff)
+    out_a = np.zeros(np.asarray(a).shape, np.float64); out_b = np.zeros(np.asarray(b).shape, np.float64)
+    out_a[0] = ga.T; out_b[0] = gb.T
+    return out_a, out_b
+
+
 # ------------------------------------------------------- a2: attack/CW/CW_utils/distance.py
 def batch_pairwise_dist(x, y):
     """attack/CW/CW_utils/distance.py:15-32: P = rx^T + ry - 2*zz, norms = diag of bmm."""
@@ -227,6 +252,23 @@ def knn_points(p1, p2, K=1):
     nrow = norms(NORM_MULSUM, p2)    # indexed by i
     d, i = knn(FORM_COL_ROW, p1, p2, nrow, ncol, K)
     return d, i.astype(np.int64)
+
+
+def knn_points_grads(p1, p2, idx, gw):
+    """float64 closed-form gradient of sum(dists * gw) for attack/GeoA3/knn_utils.py's
+    dist[i,j] = |p1_j|^2 - 2 p1_i.p2_j + |p2_i|^2 through GIVEN indices idx[B,P,K]:
+    d/dp1_i = -2g p2_j ; d/dp2_j = -2g p1_i ; d/dp1_j = 2g p1_j ; d/dp2_i = 2g p2_i."""
+    a, b = np.asarray(p1, np.float64), np.asarray(p2, np.float64)
+    g1, g2 = np.zeros_like(a), np.zeros_like(b)
+    B, P, K = idx.shape
+    for bb in range(B):
+        for k in range(K):
+            j = idx[bb, :, k]; g = np.asarray(gw, np.float64)[bb, :, k][:, None]
+            g1[bb] += -2 * g * b[bb][j]
+            np.add.at(g2[bb], j, -2 * g * a[bb])
+            np.add.at(g1[bb], j, 2 * g * a[bb][j])
+            g2[bb] += 2 * g * b[bb]
+    return g1, g2
 
 
 def knn_points_matrix(p1, p2):

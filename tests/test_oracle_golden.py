@@ -31,6 +31,14 @@ def test_a1_dis_utils_torch():
     np.testing.assert_allclose(O.dis_bid_hausdorff(a, b), g["bid_hausdorff_dis"], rtol=2e-7)
 
 
+def test_a1_gradients_closed_form_vs_reference_autograd():
+    g = load_golden("a1_dis_utils_torch")
+    ga, gb = O.dis_grads(g["a"], g["b"], w_col_sum=1 / 3, w_row_sum=1 / 3)
+    assert rel_inf(g["chamfer_ga"], ga) < 5e-5 and rel_inf(g["chamfer_gb"], gb) < 5e-5
+    ga, gb = O.dis_grads(g["a"], g["b"], w_row_max=1.0)
+    assert rel_inf(g["sgd_hausdorff_dis_ga"], ga) < 5e-5 and rel_inf(g["sgd_hausdorff_dis_gb"], gb) < 5e-5
+
+
 @pytest.mark.parametrize("tag", ["face", "iter0", "ragged", "ties"])
 def test_a2_nn1_bit_exact(tag):
     g = load_golden("a2_distance_" + tag)
@@ -148,3 +156,13 @@ def test_ref_torch_port_matches_golden():
     np.testing.assert_allclose(c2.numpy(), g["chamfer_l2"], rtol=1e-6)
     assert np.array_equal(h1.numpy(), g["hausdorff_l1"]) and np.array_equal(h2.numpy(), g["hausdorff_l2"])
     assert np.array_equal(RP.batch_pairwise_dist(t, p)[:, :64, :48].numpy(), g["P_block"])
+
+
+def test_a3_knn_gradients_closed_form_vs_reference_autograd():
+    g = load_golden("a3_knn_utils")
+    for tag, p1, p2 in (("cross1", g["adv"], g["ori"]), ("cross4", g["ori"], g["adv"]), ("self17", g["adv"], g["adv"])):
+        g1, g2 = O.knn_points_grads(p1, p2, g[tag + "_idx"], g[tag + "_gw"])
+        if tag == "self17":
+            assert rel_inf(g[tag + "_g1"], g1 + g2) < 1e-5
+        else:
+            assert rel_inf(g[tag + "_g1"], g1) < 1e-5 and rel_inf(g[tag + "_g2"], g2) < 1e-5
