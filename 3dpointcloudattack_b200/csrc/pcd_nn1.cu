@@ -1,6 +1,6 @@
 // pcd_nn1.cu -- NN-1 sweep (Chamfer / Hausdorff / knn_points K=1) for sm_100a.
 //
-// Pipeline of pcd_nn1_forward (4 launches on the caller's stream, no host sync):
+// Pipeline of pcd_nn1_forward (3 launches on the caller's stream, no host sync):
 //   1. nn1_prep    pack both clouds into the sweep layout, compute |p|^2 in the reference's
 //                  rounding order, reset the (value,tag) keys.
 //   2. nn1_sweep   THE hot kernel: every (row i, col j) distance exactly once; row minima and
@@ -10,9 +10,9 @@
 //                  partition of (sample, row tile, col tile) units over a persistent grid.
 //                  Emits per point a 64-bit key = (ordered min value, tag of the 32-wide /
 //                  32R-wide chunk that produced it) with atomicMin.
-//   3. nn1_fixup   one warp per point re-evaluates its winning chunk (bit-identical
-//                  arithmetic) and ballots for the lowest index with d == min.
-//   4. nn1_reduce  per-sample sum / max / first-argmax of both minima arrays (fixed order).
+//   3. nn1_fixup   one thread per point re-evaluates its winning chunk (bit-identical
+//                  arithmetic) for the lowest index with d == min, then the per-sample
+//                  sum / max / first-argmax of both minima arrays (fixed order, last block folds).
 //
 // Reference semantics served: utils/dis_utils_torch.py:8-28, attack/CW/CW_utils/distance.py:15-70,
 // attack/GeoA3/knn_utils.py:10-55 (K=1); see include/pcdist.h.
@@ -43,22 +43,28 @@ constexpr int kSweepWarps = 4;
 constexpr int kSweepThreads = kSweepWarps * 32;
 constexpr int kColChunk = 32;     // columns per row-direction tag
 constexpr int kMaxColTile = 256;  // columns per TMA stage (16 B each)
-constexpr int kRowPadUnit = 1024; // rows are padded to a multiple of 128*R, R <= 8
+constexpr int kRowPadUnit = 2048; // rows are padded to a multiple of 128*R, R <= 16
+constexpr int kFixThreads = 256;  // points per fix-up block
+constexpr int kMaxFixBlocks = 4096;
 
 struct Nn1Layout {
-    int Npad, Mpad;
-    size_t rowpk, colpk, rowkey, colkey, total;
+    int Npad, Mpad, nblk_r, nblk_c;
+    size_t rowpk, colpk, rowkey, colkey, partial, counter, total;
 };
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static Nn1Layout nn1_layout(int B, int N, int M) {
     Nn1Layout L;
     L.Npad = (int)align_up((size_t)N, kRowPadUnit);
     L.Mpad = (int)align_up((size_t)M, kMaxColTile);
+    L.nblk_r = (N + kFixThreads - 1) / kFixThreads;
+    L.nblk_c = (M + kFixThreads - 1) / kFixThreads;
     size_t off = 0;
     L.rowpk = off; off = align_up(off + (size_t)B * L.Npad * 16, 256);
-    L.colpk = off; off = align_up(off + (size_t)B * L.Mpad * 16, 256);
+    L.colpk = off; off = align_up(off + (size_t)B * L.Mpad * 16 + 64, 256);   // +64: the sweep prefetches one record past a tile
     L.rowkey = off; off = align_up(off + (size_t)B * L.Npad * 8, 256);
     L.colkey = off; off = align_up(off + (size_t)B * L.Mpad * 8, 256);
+    L.partial = off; off = align_up(off + (size_t)B * (L.nblk_r + L.nblk_c) * 16, 256);
+    L.counter = off; off = align_up(off + (size_t)B * 2 * 4, 256);
     L.total = off;
     return L;
 }
@@ -72,11 +78,13 @@ __global__ void nn1_prep_kernel(const float *__restrict__ rows, int64_t r_sb, in
                                 const float *__restrict__ cols, int64_t c_sb, int64_t c_sp, int64_t c_sc,
                                 int B, int N, int M, int Npad, int Mpad, int norm_kind, int swap_norms,
                                 float4 *__restrict__ rowpk, float *__restrict__ colpk,
-                                unsigned long long *__restrict__ rowkey, unsigned long long *__restrict__ colkey) {
+                                unsigned long long *__restrict__ rowkey, unsigned long long *__restrict__ colkey,
+                                unsigned int *__restrict__ counter) {
     const long long per_b = (long long)Npad + Mpad;
     const long long total = per_b * B;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
          t += (long long)gridDim.x * blockDim.x) {
+        if (t < 2 * B) counter[t] = 0u;
         const int b = (int)(t / per_b);
         const int p = (int)(t - (long long)b * per_b);
         if (p < Npad) {
@@ -115,72 +123,86 @@ __global__ void nn1_prep_kernel(const float *__restrict__ rows, int64_t r_sb, in
 }
 
 // ----------------------------------------------------------------------------------- sweep
+// Lane l of warp w of the CTA working on row tile qt owns the R consecutive rows
+//     i = qt*QT + w*32R + l*R + r,  r < R
+// Row direction: running minimum per row over 32-column chunks, tag = chunk index.
+// Column direction: per column the lane folds its R rows (FMNMX3), CREDUX gives the warp
+// minimum, FSETP+VOTE the ballot of the lanes that hold it; (value, ballot) goes to shared
+// memory and the per-tile flush turns the lowest set lane into the tag
+//     tag = (qt*4 + w)*32 + lane      ->  the R rows of that lane.
 struct SweepSmem {
-    float4 tile[2][kMaxColTile];                 // 2 x 4 KB   column pair-records (TMA destination)
-    float colpart[2][kSweepWarps][kMaxColTile];  // 2 x 4 KB   per-warp column minima
-    uint64_t full[2];                            // mbarriers: tile[s] has landed
+    float4 tile[2][kMaxColTile + 2];                 // column pair-records (TMA destination) + prefetch pad
+    uint2 colpart[2][kSweepWarps][kMaxColTile];      // per-warp (column minimum, lane ballot)
+    uint64_t full[2];                                // mbarriers: tile[s] has landed
 };
 
 template <int FORM, int R>
-__global__ void __launch_bounds__(kSweepThreads, (R >= 8) ? 3 : ((R >= 4) ? 4 : 6))
+__global__ void __launch_bounds__(kSweepThreads, (R >= 16) ? 2 : ((R >= 8) ? 4 : ((R >= 4) ? 5 : 6)))
 nn1_sweep_kernel(const float4 *__restrict__ rowpk, const float4 *__restrict__ colpk,
                  unsigned long long *__restrict__ rowkey, unsigned long long *__restrict__ colkey,
-                 int Npad, int Mpad, int mt, int nqt, int nct, long long units) {
-    constexpr int QW = 32 * R;            // queries per warp (= column-direction tag granularity)
-    constexpr int QT = kSweepWarps * QW;  // queries per CTA tile
+                 int Npad, int Mpad, int cpt /* 32-col chunks per TMA tile */, int nqt, int nch, int units) {
+    constexpr int QW = 32 * R;            // rows per warp
+    constexpr int QT = kSweepWarps * QW;  // rows per CTA tile
     __shared__ __align__(128) SweepSmem sm;
 
+    // Stream-K at chunk granularity: the (sample, row tile, 32-column chunk) space is cut into
+    // gridDim.x equal contiguous ranges, so every CTA sweeps the same number of pairs (+-1 chunk).
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long u0 = units * blockIdx.x / gridDim.x;
-    const long long u1 = units * (blockIdx.x + 1) / gridDim.x;
+    const int u0 = (int)((long long)units * blockIdx.x / gridDim.x);
+    const int u1 = (int)((long long)units * (blockIdx.x + 1) / gridDim.x);
     if (u0 >= u1) return;
 
-    const uint32_t tile_bytes = (uint32_t)mt * 16u;
-    auto tile_src = [&](long long u) -> const float4 * {
-        const long long bq = u / nct;
-        const int ct = (int)(u - bq * nct);
-        const int b = (int)(bq / nqt);
-        return colpk + (size_t)b * Mpad + (size_t)ct * mt;
+    // a segment = the chunks [u, u+n) that share one row tile and one cpt-aligned column tile
+    auto seg_len = [&](int u) -> int {
+        const int ch = u % nch;
+        int e = (ch / cpt + 1) * cpt;
+        if (e > nch) e = nch;
+        const int n = e - ch;
+        return n < u1 - u ? n : u1 - u;
+    };
+    int pu = u0;   // producer cursor (thread 0)
+    auto issue = [&](int buf) {
+        if (pu >= u1) return;
+        const int bq = pu / nch, ch = pu - bq * nch, b = bq / nqt;
+        const int n = seg_len(pu);
+        const uint32_t bytes = (uint32_t)n * kColChunk * 16u;
+        mbar_expect_tx(&sm.full[buf], bytes);
+        tma_load_1d(sm.tile[buf], colpk + (size_t)b * Mpad + (size_t)ch * kColChunk, bytes, &sm.full[buf]);
+        pu += n;
     };
     if (tid == 0) {
         mbar_init(&sm.full[0], 1);
         mbar_init(&sm.full[1], 1);
         fence_mbar_init();
         fence_proxy_async();
-        mbar_expect_tx(&sm.full[0], tile_bytes);
-        tma_load_1d(sm.tile[0], tile_src(u0), tile_bytes, &sm.full[0]);
-        if (u0 + 1 < u1) {
-            mbar_expect_tx(&sm.full[1], tile_bytes);
-            tma_load_1d(sm.tile[1], tile_src(u0 + 1), tile_bytes, &sm.full[1]);
-        }
+        issue(0);
+        issue(1);
     }
     __syncthreads();
 
     float qx[R], qy[R], qz[R], qn[R], best[R];
     uint32_t btag[R];
-    long long cur_bq = -1;
+    int cur_bq = -1;
     size_t row_base = 0;
 
-    for (long long u = u0; u < u1; ++u) {
-        const int it = (int)(u - u0);
+    int it = 0;
+    for (int u = u0; u < u1; ++it) {
         const int buf = it & 1;
         const uint32_t parity = (it >> 1) & 1;
-        const long long bq = u / nct;
-        const int ct = (int)(u - bq * nct);
-        const int b = (int)(bq / nqt);
-        const int qt = (int)(bq - (long long)b * nqt);
+        const int bq = u / nch, ch0 = u - bq * nch;
+        const int b = bq / nqt, qt = bq - b * nqt;
+        const int nseg = seg_len(u);
 
         if (bq != cur_bq) {
             if (cur_bq >= 0) {
 #pragma unroll
-                for (int r = 0; r < R; ++r)
-                    atomicMin(&rowkey[row_base + r * 32 + lane], make_key(best[r], btag[r]));
+                for (int r = 0; r < R; ++r) atomicMin(&rowkey[row_base + r], make_key(best[r], btag[r]));
             }
             cur_bq = bq;
-            row_base = (size_t)b * Npad + (size_t)qt * QT + warp * QW;
+            row_base = (size_t)b * Npad + (size_t)qt * QT + warp * QW + lane * R;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const float4 q = __ldg(&rowpk[row_base + r * 32 + lane]);
+                const float4 q = __ldg(&rowpk[row_base + r]);
                 qx[r] = q.x; qy[r] = q.y; qz[r] = q.z; qn[r] = q.w;
                 best[r] = __int_as_float(0x7f800000);
                 btag[r] = 0;
@@ -190,17 +212,18 @@ nn1_sweep_kernel(const float4 *__restrict__ rowpk, const float4 *__restrict__ co
         mbar_wait(&sm.full[buf], parity);
 
         const float4 *t4 = sm.tile[buf];
-        float *cp = sm.colpart[buf][warp];
-        const int nchunk = mt / kColChunk;
-        const uint32_t tag0 = (uint32_t)(ct * mt) / kColChunk;
-        for (int c = 0; c < nchunk; ++c) {
+        uint2 *cp = sm.colpart[buf][warp];
+        float4 A = t4[0], Bv = t4[1];                       // operands of the step about to run
+        uint2 pend_lo = make_uint2(0x7f800000u, 0u), pend_hi = pend_lo;   // column results of the previous step
+        int pend_at = -1;
+        for (int c = 0; c < nseg; ++c) {
             float m[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) m[r] = __int_as_float(0x7f800000);
-#pragma unroll 4
+#pragma unroll 2
             for (int s = 0; s < kColChunk / 2; ++s) {
-                const float4 A = t4[(c * (kColChunk / 2) + s) * 2];
-                const float4 Bv = t4[(c * (kColChunk / 2) + s) * 2 + 1];
+                const int step = c * (kColChunk / 2) + s;
+                const float4 An = t4[step * 2 + 2], Bn = t4[step * 2 + 3];   // prefetch (pad keeps it in bounds)
                 const f32x2 X = pack2(A.x, A.y), Y = pack2(A.z, A.w);
                 const f32x2 Z = pack2(Bv.x, Bv.y), Nn = pack2(Bv.z, Bv.w);
                 float lo[R], hi[R];
@@ -220,120 +243,129 @@ nn1_sweep_kernel(const float4 *__restrict__ rowpk, const float4 *__restrict__ co
                     clo = fminf(clo, lo[R - 1]);
                     chi = fminf(chi, hi[R - 1]);
                 }
-                clo = warp_min_f32(clo);
-                chi = warp_min_f32(chi);
-                *reinterpret_cast<float2 *>(&cp[c * kColChunk + 2 * s]) = make_float2(clo, chi);
+                // retire the previous step's column results (their CREDUX latency is long gone)
+                if (pend_at >= 0) *reinterpret_cast<uint4 *>(&cp[pend_at]) = make_uint4(pend_lo.x, pend_lo.y, pend_hi.x, pend_hi.y);
+                const float vlo = warp_min_f32(clo), vhi = warp_min_f32(chi);
+                pend_lo = make_uint2(__float_as_uint(vlo), __ballot_sync(0xffffffffu, clo == vlo));
+                pend_hi = make_uint2(__float_as_uint(vhi), __ballot_sync(0xffffffffu, chi == vhi));
+                pend_at = 2 * step;
+                A = An; Bv = Bn;
             }
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 if (m[r] < best[r]) {
                     best[r] = m[r];
-                    btag[r] = tag0 + c;
+                    btag[r] = (uint32_t)(ch0 + c);
                 }
             }
         }
+        *reinterpret_cast<uint4 *>(&cp[pend_at]) = make_uint4(pend_lo.x, pend_lo.y, pend_hi.x, pend_hi.y);
         __syncthreads();  // tile[buf] fully read, colpart[buf] fully written
 
-        if (tid == 0 && u + 2 < u1) {
-            mbar_expect_tx(&sm.full[buf], tile_bytes);
-            tma_load_1d(sm.tile[buf], tile_src(u + 2), tile_bytes, &sm.full[buf]);
-        }
-        // column flush: min over the CTA's warps, lowest warp on ties, one atomic per column
-        for (int col = tid; col < mt; col += kSweepThreads) {
-            float v = sm.colpart[buf][0][col];
-            uint32_t w = 0;
+        if (tid == 0) issue(buf);
+        // column flush: min over the CTA's warps (lowest warp on ties), lowest lane of its ballot
+        const int ncols = nseg * kColChunk;
+        for (int col = tid; col < ncols; col += kSweepThreads) {
+            uint2 e = sm.colpart[buf][0][col];
+            float v = __uint_as_float(e.x);
+            uint32_t w = 0, msk = e.y;
 #pragma unroll
             for (int k = 1; k < kSweepWarps; ++k) {
-                const float o = sm.colpart[buf][k][col];
-                if (o < v) { v = o; w = k; }
+                const uint2 o = sm.colpart[buf][k][col];
+                if (__uint_as_float(o.x) < v) { v = __uint_as_float(o.x); w = k; msk = o.y; }
             }
             if (v < __int_as_float(0x7f800000))
-                atomicMin(&colkey[(size_t)b * Mpad + (size_t)ct * mt + col],
-                          make_key(v, (uint32_t)qt * kSweepWarps + w));
+                atomicMin(&colkey[(size_t)b * Mpad + (size_t)ch0 * kColChunk + col],
+                          make_key(v, (((uint32_t)qt * kSweepWarps + w) << 5) + (uint32_t)(__ffs(msk) - 1)));
         }
+        u += nseg;
     }
 #pragma unroll
-    for (int r = 0; r < R; ++r) atomicMin(&rowkey[row_base + r * 32 + lane], make_key(best[r], btag[r]));
+    for (int r = 0; r < R; ++r) atomicMin(&rowkey[row_base + r], make_key(best[r], btag[r]));
 }
 
-// ----------------------------------------------------------------------------------- fixup
+// --------------------------------------------------------------------- fix-up + reduction
 __device__ __forceinline__ float apply_transform(int transform, float v) {
     return transform == PCD_VALUE_SQRT_CLAMP ? sqrtf(fmaxf(v, 0.0f)) : v;
 }
 
+// One thread per point.  A row point re-evaluates the 32 columns of its winning chunk, a column
+// point the R rows of its winning lane -- with the sweep's exact arithmetic -- and takes the
+// lowest index whose distance equals the minimum.  The block then reduces its 256 values
+// (sum, max, first argmax) in a fixed order; the last block of each (sample, side) folds the
+// block partials in index order, so the statistics are run-to-run deterministic.
 template <int FORM>
-__global__ void __launch_bounds__(256)
-nn1_fixup_kernel(const float4 *__restrict__ rowpk, const float *__restrict__ colpk,
+__global__ void __launch_bounds__(kFixThreads)
+nn1_fixup_kernel(const float4 *__restrict__ rowpk, const float4 *__restrict__ colpk,
                  const unsigned long long *__restrict__ rowkey, const unsigned long long *__restrict__ colkey,
-                 int B, int N, int M, int Npad, int Mpad, int qchunk, int transform,
+                 int N, int M, int Npad, int Mpad, int R, int transform, int nblk_r, int nblk_c,
+                 float row_scale, float col_scale,
                  float *__restrict__ row_min, int32_t *__restrict__ row_arg,
-                 float *__restrict__ col_min, int32_t *__restrict__ col_arg) {
-    const int lane = threadIdx.x & 31;
-    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const long long items = (long long)B * (N + M);
-    for (long long it = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; it < items; it += warps) {
-        const int b = (int)(it / (N + M));
-        const int p = (int)(it - (long long)b * (N + M));
-        if (p < N) {
-            const int i = p;
-            const unsigned long long key = rowkey[(size_t)b * Npad + i];
-            const float v = ordered_to_f32((uint32_t)(key >> 32));
-            const uint32_t c = (uint32_t)key;
-            const float4 q = __ldg(&rowpk[(size_t)b * Npad + i]);
-            const int j = (int)c * kColChunk + lane;
-            const float *rec = colpk + ((size_t)b * Mpad + (j & ~1)) * 4 + (j & 1);
-            const float d = pair_dist_scalar<FORM>(q.x, q.y, q.z, q.w, rec[0], rec[2], rec[4], rec[6]);
-            const unsigned mask = __ballot_sync(0xffffffffu, d == v);
-            if (lane == 0) {
-                row_min[(size_t)b * N + i] = apply_transform(transform, v);
-                row_arg[(size_t)b * N + i] = (int)c * kColChunk + (mask ? __ffs(mask) - 1 : 0);
-            }
-        } else {
-            const int j = p - N;
-            const unsigned long long key = colkey[(size_t)b * Mpad + j];
-            const float v = ordered_to_f32((uint32_t)(key >> 32));
-            const uint32_t c = (uint32_t)key;
-            const float *rec = colpk + ((size_t)b * Mpad + (j & ~1)) * 4 + (j & 1);
-            const float cx = rec[0], cy = rec[2], cz = rec[4], cn = rec[6];
-            int found = (int)c * qchunk;
-            for (int s = 0; s < qchunk; s += 32) {
-                const int i = (int)c * qchunk + s + lane;
-                const float4 q = __ldg(&rowpk[(size_t)b * Npad + i]);
-                const float d = pair_dist_scalar<FORM>(q.x, q.y, q.z, q.w, cx, cy, cz, cn);
-                const unsigned mask = __ballot_sync(0xffffffffu, d == v);
-                if (mask) {
-                    found = (int)c * qchunk + s + __ffs(mask) - 1;
-                    break;
+                 float *__restrict__ col_min, int32_t *__restrict__ col_arg,
+                 float4 *__restrict__ partial, unsigned int *__restrict__ counter,
+                 float *__restrict__ stats_f, int32_t *__restrict__ stats_i, int B) {
+    const int b = blockIdx.y;
+    const bool is_col = (int)blockIdx.x >= nblk_r;
+    const int blk = is_col ? blockIdx.x - nblk_r : blockIdx.x;
+    const int n = is_col ? M : N;
+    const int p = blk * kFixThreads + threadIdx.x;
+    float val = -__int_as_float(0x7f800000);   // neutral for max; contributes 0 to the sum
+    bool live = p < n;
+    if (live) {
+        int arg = 0;
+        float v;
+        if (!is_col) {
+            const unsigned long long key = rowkey[(size_t)b * Npad + p];
+            v = ordered_to_f32((uint32_t)(key >> 32));
+            const int j0 = (int)(uint32_t)key * kColChunk;
+            const float4 q = __ldg(&rowpk[(size_t)b * Npad + p]);
+            const float4 *rec = colpk + (size_t)b * Mpad + j0;
+            arg = j0;
+            bool found = false;
+#pragma unroll 1
+            for (int g = 0; g < kColChunk / 2 && !found; g += 4) {
+                float4 a[4], c[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { a[k] = __ldg(&rec[(g + k) * 2]); c[k] = __ldg(&rec[(g + k) * 2 + 1]); }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float d0 = pair_dist_scalar<FORM>(q.x, q.y, q.z, q.w, a[k].x, a[k].z, c[k].x, c[k].z);
+                    const float d1 = pair_dist_scalar<FORM>(q.x, q.y, q.z, q.w, a[k].y, a[k].w, c[k].y, c[k].w);
+                    if (!found && d0 == v) { found = true; arg = j0 + (g + k) * 2; }
+                    if (!found && d1 == v) { found = true; arg = j0 + (g + k) * 2 + 1; }
                 }
             }
-            if (lane == 0) {
-                col_min[(size_t)b * M + j] = apply_transform(transform, v);
-                col_arg[(size_t)b * M + j] = found;
+            val = apply_transform(transform, v);
+            row_min[(size_t)b * N + p] = val;
+            row_arg[(size_t)b * N + p] = arg;
+        } else {
+            const unsigned long long key = colkey[(size_t)b * Mpad + p];
+            v = ordered_to_f32((uint32_t)(key >> 32));
+            const uint32_t tag = (uint32_t)key;
+            const int i0 = (int)(tag >> 5) * (32 * R) + (int)(tag & 31u) * R;
+            const float *rec = reinterpret_cast<const float *>(colpk) + ((size_t)b * Mpad + (p & ~1)) * 4 + (p & 1);
+            const float cx = rec[0], cy = rec[2], cz = rec[4], cn = rec[6];
+            arg = i0;
+            bool found = false;
+            for (int r = 0; r < R; ++r) {
+                const float4 q = __ldg(&rowpk[(size_t)b * Npad + i0 + r]);
+                const float d = pair_dist_scalar<FORM>(q.x, q.y, q.z, q.w, cx, cy, cz, cn);
+                if (!found && d == v) { found = true; arg = i0 + r; }
             }
+            val = apply_transform(transform, v);
+            col_min[(size_t)b * M + p] = val;
+            col_arg[(size_t)b * M + p] = arg;
         }
     }
-}
-
-// ---------------------------------------------------------------------------------- reduce
-// grid (B, 2): y = 0 rows, y = 1 cols.  Fixed summation order -> run-to-run deterministic.
-__global__ void __launch_bounds__(256)
-nn1_reduce_kernel(const float *__restrict__ row_min, const float *__restrict__ col_min, int N, int M,
-                  float *__restrict__ stats_f, int32_t *__restrict__ stats_i) {
-    const int b = blockIdx.x, side = blockIdx.y;
-    const int n = side ? M : N;
-    const float *v = (side ? col_min : row_min) + (size_t)b * n;
-    float s = 0.f, mx = -__int_as_float(0x7f800000);
-    int am = 0x7fffffff;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const float x = v[i];
-        s += x;
-        if (x > mx) { mx = x; am = i; }
-    }
-    __shared__ float ss[256], smx[256];
-    __shared__ int sam[256];
-    ss[threadIdx.x] = s; smx[threadIdx.x] = mx; sam[threadIdx.x] = am;
+    // ---- block reduction (fixed order) ----
+    __shared__ float ss[kFixThreads], smx[kFixThreads];
+    __shared__ int sam[kFixThreads];
+    __shared__ bool is_last;
+    ss[threadIdx.x] = live ? val : 0.f;
+    smx[threadIdx.x] = val;
+    sam[threadIdx.x] = live ? p : 0x7fffffff;
     __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
+    for (int o = kFixThreads / 2; o > 0; o >>= 1) {
         if (threadIdx.x < o) {
             ss[threadIdx.x] += ss[threadIdx.x + o];
             const float om = smx[threadIdx.x + o];
@@ -344,10 +376,28 @@ nn1_reduce_kernel(const float *__restrict__ row_min, const float *__restrict__ c
         }
         __syncthreads();
     }
+    const int nblk = is_col ? nblk_c : nblk_r;
+    float4 *part = partial + (size_t)b * (nblk_r + nblk_c) + (is_col ? nblk_r : 0);
     if (threadIdx.x == 0) {
-        stats_f[b * 4 + side * 2 + 0] = ss[0];
-        stats_f[b * 4 + side * 2 + 1] = smx[0];
-        stats_i[b * 2 + side] = sam[0] == 0x7fffffff ? 0 : sam[0];
+        part[blk] = make_float4(ss[0], smx[0], __int_as_float(sam[0]), 0.f);
+        __threadfence();
+        const unsigned done = atomicAdd(&counter[b * 2 + (is_col ? 1 : 0)], 1u);
+        is_last = (done == (unsigned)nblk - 1u);
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+        __threadfence();
+        float s = 0.f, mx = -__int_as_float(0x7f800000);
+        int am = 0;
+        for (int k = 0; k < nblk; ++k) {
+            const float4 e = __ldcg(&part[k]);
+            s += e.x;
+            if (e.y > mx) { mx = e.y; am = __float_as_int(e.z); }
+        }
+        const int side = is_col ? 1 : 0;
+        stats_f[(side * 2 + 0) * B + b] = s * (is_col ? col_scale : row_scale);
+        stats_f[(side * 2 + 1) * B + b] = mx;
+        stats_i[side * B + b] = am;
     }
 }
 
@@ -361,6 +411,7 @@ struct BwdArgs {
     const float *g_row, *g_col;
     const float *w_row_all, *w_row_max; const int32_t *row_argmax;
     const float *w_col_all, *w_col_max; const int32_t *col_argmax;
+    float row_scale, col_scale;
     float *grad_rows; int64_t gr_sb, gr_sp, gr_sc;
     float *grad_cols; int64_t gc_sb, gc_sp, gc_sc;
 };
@@ -370,10 +421,10 @@ __device__ __forceinline__ float3 ld3(const float *base, int64_t sc) {
 }
 // upstream gradient of minimum (b,p) on one side
 __device__ __forceinline__ float upstream(const float *g, const float *w_all, const float *w_max,
-                                          const int32_t *argmax, int b, int p, int n) {
+                                          const int32_t *argmax, int b, int p, int n, float scale) {
     float r = 0.f;
     if (g) r += g[(size_t)b * n + p];
-    if (w_all) r += w_all[b];
+    if (w_all) r += w_all[b] * scale;
     if (w_max && argmax[b] == p) r += w_max[b];
     return r;
 }
@@ -398,7 +449,7 @@ __global__ void __launch_bounds__(256) nn1_bwd_kernel(BwdArgs a) {
         const float *rb = a.rows + b * a.r_sb, *cb = a.cols + b * a.c_sb;
         if (p < a.N) {
             const int i = p;
-            const float g = upstream(a.g_row, a.w_row_all, a.w_row_max, a.row_argmax, b, i, a.N);
+            const float g = upstream(a.g_row, a.w_row_all, a.w_row_max, a.row_argmax, b, i, a.N, a.row_scale);
             const int j = a.row_arg[(size_t)b * a.N + i];
             const float3 r = ld3(rb + i * a.r_sp, a.r_sc), c = ld3(cb + j * a.c_sp, a.c_sc);
             const float f = chain_factor(a.transform, g, a.row_min, (size_t)b * a.N + i);
@@ -407,7 +458,7 @@ __global__ void __launch_bounds__(256) nn1_bwd_kernel(BwdArgs a) {
                     float3 o;
                     if (a.swap_norms) {
                         // entry (i,j): -2 g c_j ; column-direction entry (i*, j=i): +2 g' r_i
-                        const float g2 = upstream(a.g_col, a.w_col_all, a.w_col_max, a.col_argmax, b, i, a.M);
+                        const float g2 = upstream(a.g_col, a.w_col_all, a.w_col_max, a.col_argmax, b, i, a.M, a.col_scale);
                         o = make_float3(-f * c.x + 2.f * g2 * r.x, -f * c.y + 2.f * g2 * r.y, -f * c.z + 2.f * g2 * r.z);
                     } else {
                         o = make_float3(f * (r.x - c.x), f * (r.y - c.y), f * (r.z - c.z));
@@ -433,7 +484,7 @@ __global__ void __launch_bounds__(256) nn1_bwd_kernel(BwdArgs a) {
             }
         } else {
             const int j = p - a.N;
-            const float g = upstream(a.g_col, a.w_col_all, a.w_col_max, a.col_argmax, b, j, a.M);
+            const float g = upstream(a.g_col, a.w_col_all, a.w_col_max, a.col_argmax, b, j, a.M, a.col_scale);
             const int i = a.col_arg[(size_t)b * a.M + j];
             const float3 r = ld3(rb + i * a.r_sp, a.r_sc), c = ld3(cb + j * a.c_sp, a.c_sc);
             const float f = chain_factor(a.transform, g, a.col_min, (size_t)b * a.M + j);
@@ -442,7 +493,7 @@ __global__ void __launch_bounds__(256) nn1_bwd_kernel(BwdArgs a) {
                     float3 o;
                     if (a.swap_norms) {
                         // entry (i*,j): -2 g' r_i* ; row-direction entry (i=j, j*): +2 g c_j
-                        const float g1 = upstream(a.g_row, a.w_row_all, a.w_row_max, a.row_argmax, b, j, a.N);
+                        const float g1 = upstream(a.g_row, a.w_row_all, a.w_row_max, a.row_argmax, b, j, a.N, a.row_scale);
                         o = make_float3(-f * r.x + 2.f * g1 * c.x, -f * r.y + 2.f * g1 * c.y, -f * r.z + 2.f * g1 * c.z);
                     } else {
                         o = make_float3(f * (c.x - r.x), f * (c.y - r.y), f * (c.z - r.z));
@@ -486,16 +537,18 @@ static cudaError_t launch_sweep(const float4 *rowpk, const float4 *colpk, unsign
                                 unsigned long long *colkey, int B, int N, int M, int Npad, int Mpad, int mt,
                                 int sms, cudaStream_t st) {
     const int QT = kSweepWarps * 32 * R;
-    const int nqt = (N + QT - 1) / QT, nct = (M + mt - 1) / mt;   // fully inert tiles are skipped
-    const long long units = (long long)B * nqt * nct;
+    const int nqt = (N + QT - 1) / QT;                       // fully inert row tiles are skipped
+    const int nch = (M + kColChunk - 1) / kColChunk;         // ... and fully inert column chunks
+    const long long units = (long long)B * nqt * nch;
+    if (units >= (1LL << 31)) return cudaErrorInvalidValue;
     int occ = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nn1_sweep_kernel<FORM, R>, kSweepThreads, 0);
     if (e != cudaSuccess) return e;
     if (occ < 1) occ = 1;
     long long grid = (long long)sms * occ;
     if (grid > units) grid = units;
-    nn1_sweep_kernel<FORM, R><<<(unsigned)grid, kSweepThreads, 0, st>>>(rowpk, colpk, rowkey, colkey, Npad, Mpad, mt,
-                                                                         nqt, nct, units);
+    nn1_sweep_kernel<FORM, R><<<(unsigned)grid, kSweepThreads, 0, st>>>(rowpk, colpk, rowkey, colkey, Npad, Mpad,
+                                                                         mt / kColChunk, nqt, nch, (int)units);
     return cudaGetLastError();
 }
 
@@ -504,29 +557,30 @@ static cudaError_t launch_sweep_r(int R, const float4 *rowpk, const float4 *colp
                                   unsigned long long *colkey, int B, int N, int M, int Npad, int Mpad, int mt,
                                   int sms, cudaStream_t st) {
     switch (R) {
+    case 16: return launch_sweep<FORM, 16>(rowpk, colpk, rowkey, colkey, B, N, M, Npad, Mpad, mt, sms, st);
     case 8: return launch_sweep<FORM, 8>(rowpk, colpk, rowkey, colkey, B, N, M, Npad, Mpad, mt, sms, st);
     case 4: return launch_sweep<FORM, 4>(rowpk, colpk, rowkey, colkey, B, N, M, Npad, Mpad, mt, sms, st);
     default: return launch_sweep<FORM, 2>(rowpk, colpk, rowkey, colkey, B, N, M, Npad, Mpad, mt, sms, st);
     }
 }
 
-// Tile-shape heuristic.  R queries per lane (register blocking: more = fewer LDS / CREDUX per
-// pair) and mt columns per stage; small problems trade blocking for enough units to fill the
-// 148 SMs.  PCD_SWEEP_R / PCD_SWEEP_MT override for tuning.
+// Tile-shape heuristic.  R rows per lane (register blocking: the per-step overhead -- operand
+// LDS, CREDUX, ballots, stores -- is amortised over 2R pairs) against padding waste and the
+// number of chunks each CTA of the persistent grid gets.  PCD_SWEEP_R / PCD_SWEEP_MT override.
 static void choose_tiling(int B, int N, int M, int sms, int *R_out, int *mt_out) {
-    int R = 8;
+    static const int occ_of[5] = {6, 5, 4, 2, 0};       // CTAs/SM for R = 2, 4, 8, 16
+    const long long nch = (M + kColChunk - 1) / kColChunk;
+    int R = 16, oi = 3;
     while (R > 2) {
         const long long qtiles = (long long)B * ((N + 128 * R - 1) / (128 * R));
         const long long padded = qtiles * 128 * R;
-        const bool waste = padded > (long long)B * N * 5 / 4;        // > 25 % inert rows
-        const bool starved = qtiles * ((M + 255) / 256) < 2LL * sms * 4;
+        const bool waste = padded * 8 > (long long)B * N * 9;                 // > 12.5 % inert rows
+        const bool starved = qtiles * nch < 6LL * sms * occ_of[oi];            // < 6 chunks per CTA
         if (!waste && !starved) break;
-        R >>= 1;
+        R >>= 1; --oi;
     }
     int mt = kMaxColTile;
-    const long long qtiles = (long long)B * ((N + 128 * R - 1) / (128 * R));
-    while (mt > kColChunk && qtiles * ((M + mt - 1) / mt) < 2LL * sms * 5) mt >>= 1;
-    if (const char *e = getenv("PCD_SWEEP_R")) { int v = atoi(e); if (v == 2 || v == 4 || v == 8) R = v; }
+    if (const char *e = getenv("PCD_SWEEP_R")) { int v = atoi(e); if (v == 2 || v == 4 || v == 8 || v == 16) R = v; }
     if (const char *e = getenv("PCD_SWEEP_MT")) { int v = atoi(e); if (v >= 32 && v <= 256 && (v & (v - 1)) == 0) mt = v; }
     *R_out = R; *mt_out = mt;
 }
@@ -555,6 +609,7 @@ extern "C" size_t pcd_nn1_workspace_bytes(int B, int N, int M) {
 extern "C" int pcd_nn1_forward(const float *rows, int64_t r_sb, int64_t r_sp, int64_t r_sc,
                                const float *cols, int64_t c_sb, int64_t c_sp, int64_t c_sc,
                                int B, int N, int M, int form, int norm_kind, int swap_norms, int transform,
+                               float row_sum_scale, float col_sum_scale,
                                float *row_min, int32_t *row_arg, float *col_min, int32_t *col_arg,
                                float *stats_f, int32_t *stats_i,
                                void *workspace, size_t workspace_bytes, void *stream) {
@@ -563,7 +618,7 @@ extern "C" int pcd_nn1_forward(const float *rows, int64_t r_sb, int64_t r_sp, in
         return PCD_ERR_ARG;
     }
     if (B <= 0 || N <= 0 || M <= 0 || form < 0 || form > 2 || norm_kind < 0 || norm_kind > 1 || transform < 0 ||
-        transform > 1) {
+        transform > 1 || B > 65535) {
         set_error("pcd_nn1_forward: bad argument B=%d N=%d M=%d form=%d norm=%d transform=%d", B, N, M, form,
                   norm_kind, transform);
         return PCD_ERR_ARG;
@@ -589,6 +644,8 @@ extern "C" int pcd_nn1_forward(const float *rows, int64_t r_sb, int64_t r_sp, in
     float *colpk = (float *)(ws + L.colpk);
     unsigned long long *rowkey = (unsigned long long *)(ws + L.rowkey);
     unsigned long long *colkey = (unsigned long long *)(ws + L.colkey);
+    float4 *partial = (float4 *)(ws + L.partial);
+    unsigned int *counter = (unsigned int *)(ws + L.counter);
 
     int R, mt;
     choose_tiling(B, N, M, sms, &R, &mt);
@@ -597,7 +654,7 @@ extern "C" int pcd_nn1_forward(const float *rows, int64_t r_sb, int64_t r_sp, in
         const long long total = (long long)B * (L.Npad + L.Mpad);
         const int grid = (int)((total + 255) / 256 < (long long)sms * 8 ? (total + 255) / 256 : (long long)sms * 8);
         nn1_prep_kernel<<<grid, 256, 0, st>>>(rows, r_sb, r_sp, r_sc, cols, c_sb, c_sp, c_sc, B, N, M, L.Npad,
-                                              L.Mpad, norm_kind, swap_norms, rowpk, colpk, rowkey, colkey);
+                                              L.Mpad, norm_kind, swap_norms, rowpk, colpk, rowkey, colkey, counter);
         PCD_CUDA_CHECK(cudaGetLastError());
     }
     {
@@ -613,20 +670,18 @@ extern "C" int pcd_nn1_forward(const float *rows, int64_t r_sb, int64_t r_sp, in
         if (g_sweep_ev1) PCD_CUDA_CHECK(cudaEventRecord(g_sweep_ev1, st));
     }
     {
-        const long long items = (long long)B * (N + M);
-        const long long want = (items + 7) / 8;
-        const int grid = (int)(want < (long long)sms * 8 ? want : (long long)sms * 8);
-        const int qchunk = 32 * R;
-        if (form == PCD_FORM_ROW_COL)
-            nn1_fixup_kernel<PCD_FORM_ROW_COL><<<grid, 256, 0, st>>>(rowpk, colpk, rowkey, colkey, B, N, M, L.Npad, L.Mpad, qchunk, transform, row_min, row_arg, col_min, col_arg);
-        else if (form == PCD_FORM_COL_ROW)
-            nn1_fixup_kernel<PCD_FORM_COL_ROW><<<grid, 256, 0, st>>>(rowpk, colpk, rowkey, colkey, B, N, M, L.Npad, L.Mpad, qchunk, transform, row_min, row_arg, col_min, col_arg);
-        else
-            nn1_fixup_kernel<PCD_FORM_SUM_FIRST><<<grid, 256, 0, st>>>(rowpk, colpk, rowkey, colkey, B, N, M, L.Npad, L.Mpad, qchunk, transform, row_min, row_arg, col_min, col_arg);
+        const dim3 grid(L.nblk_r + L.nblk_c, B);
+        const float4 *colpk4 = (const float4 *)colpk;
+#define PCD_LAUNCH_FIXUP(F)                                                                                     \
+    nn1_fixup_kernel<F><<<grid, kFixThreads, 0, st>>>(rowpk, colpk4, rowkey, colkey, N, M, L.Npad, L.Mpad, R, transform, \
+                                                      L.nblk_r, L.nblk_c, row_sum_scale, col_sum_scale, row_min, row_arg, \
+                                                      col_min, col_arg, partial, counter, stats_f, stats_i, B)
+        if (form == PCD_FORM_ROW_COL) PCD_LAUNCH_FIXUP(PCD_FORM_ROW_COL);
+        else if (form == PCD_FORM_COL_ROW) PCD_LAUNCH_FIXUP(PCD_FORM_COL_ROW);
+        else PCD_LAUNCH_FIXUP(PCD_FORM_SUM_FIRST);
+#undef PCD_LAUNCH_FIXUP
         PCD_CUDA_CHECK(cudaGetLastError());
     }
-    nn1_reduce_kernel<<<dim3(B, 2), 256, 0, st>>>(row_min, col_min, N, M, stats_f, stats_i);
-    PCD_CUDA_CHECK(cudaGetLastError());
     return PCD_OK;
 }
 
@@ -638,6 +693,7 @@ extern "C" int pcd_nn1_backward(const float *rows, int64_t r_sb, int64_t r_sp, i
                                 const float *g_row, const float *g_col,
                                 const float *w_row_all, const float *w_row_max, const int32_t *row_argmax,
                                 const float *w_col_all, const float *w_col_max, const int32_t *col_argmax,
+                                float row_sum_scale, float col_sum_scale,
                                 float *grad_rows, int64_t gr_sb, int64_t gr_sp, int64_t gr_sc,
                                 float *grad_cols, int64_t gc_sb, int64_t gc_sp, int64_t gc_sc, void *stream) {
     if (!rows || !cols || !row_arg || !col_arg || B <= 0 || N <= 0 || M <= 0) {
@@ -661,7 +717,7 @@ extern "C" int pcd_nn1_backward(const float *rows, int64_t r_sb, int64_t r_sp, i
     if (sms <= 0) return cuda_fail(cudaGetLastError(), "no CUDA device");
     BwdArgs a{rows, r_sb, r_sp, r_sc, cols, c_sb, c_sp, c_sc, B, N, M, swap_norms, transform,
               row_arg, col_arg, row_min, col_min, g_row, g_col,
-              w_row_all, w_row_max, row_argmax, w_col_all, w_col_max, col_argmax,
+              w_row_all, w_row_max, row_argmax, w_col_all, w_col_max, col_argmax, row_sum_scale, col_sum_scale,
               grad_rows, gr_sb, gr_sp, gr_sc, grad_cols, gc_sb, gc_sp, gc_sc};
     const long long total = (long long)B * (N + M);
     const long long want = (total + 255) / 256;

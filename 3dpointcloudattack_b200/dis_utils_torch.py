@@ -32,23 +32,23 @@ def pairwise_distances(a: torch.Tensor, b: torch.Tensor, p=2):
 def _sweep(a, b):
     # rows = points of a, cols = points of b; sample 0 is all the reference ever reads
     return F.nn1(a[:1].permute(0, 2, 1), b[:1].permute(0, 2, 1), F.FORM_ROW_COL, F.NORM_MULSUM,
-                 swap_norms=False, transform=F.VALUE_SQRT_CLAMP)
+                 swap_norms=False, transform=F.VALUE_SQRT_CLAMP,
+                 row_sum_scale=1.0 / b.shape[1], col_sum_scale=1.0 / a.shape[1])
 
 
 def chamfer(a, b):
     """utils/dis_utils_torch.py:14-16: (M.min(1)[0].sum(1))/a.shape[1] + (M.min(2)[0].sum(1))/b.shape[1], [0]."""
-    r = _sweep(a, b)
-    row_sum, col_sum = r.stats[0], r.stats[2]
-    return (col_sum / a.shape[1] + row_sum / b.shape[1])[0]
+    r = _sweep(a, b)          # the divisors a.shape[1], b.shape[1] are folded into the kernel's sums
+    return (r.col_sum + r.row_sum)[0]
 
 
 def sgd_hausdorff_dis(a, b):
     """utils/dis_utils_torch.py:19-22: max_i min_j M[0]."""
-    return _sweep(a, b).stats[1][0]
+    return _sweep(a, b).row_max[0]
 
 
 def bid_hausdorff_dis(a, b):
     """utils/dis_utils_torch.py:25-28: max(d_ab, d_ba); both directions come from ONE sweep
     (d_ba = max_j min_i M[0] is the column side)."""
     r = _sweep(a, b)
-    return torch.max(r.stats[1][0], r.stats[3][0])
+    return torch.max(r.row_max[0], r.col_max[0])

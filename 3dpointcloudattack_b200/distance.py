@@ -13,7 +13,9 @@ from . import functional as F
 
 def _sweep(preds, gts):
     # P = batch_pairwise_dist(gts, preds): rows = gts, cols = preds  (distance.py:45, :63)
-    return F.nn1(gts, preds, F.FORM_SUM_FIRST, F.NORM_FMA)
+    # the means' divisors are folded into the kernel: col side = preds (N1), row side = gts (N2)
+    return F.nn1(gts, preds, F.FORM_SUM_FIRST, F.NORM_FMA,
+                 row_sum_scale=1.0 / gts.shape[1], col_sum_scale=1.0 / preds.shape[1])
 
 
 class _Distance(nn.Module):
@@ -40,9 +42,7 @@ class ChamferDistance(_Distance):
     def forward(self, preds, gts):
         """preds: [B, N1, 3], gts: [B, N2, 3] -> (mean_j min_i P, mean_i min_j P)  (distance.py:40-50)"""
         r = _sweep(preds, gts)
-        loss1 = r.stats[2] / preds.shape[1]
-        loss2 = r.stats[0] / gts.shape[1]
-        return loss1, loss2
+        return r.col_sum, r.row_sum
 
 
 class HausdorffDistance(_Distance):
@@ -50,7 +50,7 @@ class HausdorffDistance(_Distance):
     def forward(self, preds, gts):
         """(max_j min_i P, max_i min_j P)  (distance.py:58-70); ties -> first index like torch.max(dim)."""
         r = _sweep(preds, gts)
-        return r.stats[3], r.stats[1]
+        return r.col_max, r.row_max
 
 
 chamfer = ChamferDistance()
@@ -60,4 +60,4 @@ hausdorff = HausdorffDistance()
 def chamfer_hausdorff(preds, gts):
     """Fused convenience: (chamfer_loss1, chamfer_loss2, hausdorff_loss1, hausdorff_loss2), one sweep."""
     r = _sweep(preds, gts)
-    return r.stats[2] / preds.shape[1], r.stats[0] / gts.shape[1], r.stats[3], r.stats[1]
+    return r.col_sum, r.row_sum, r.col_max, r.row_max

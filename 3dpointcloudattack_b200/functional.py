@@ -49,9 +49,10 @@ def _ptr(t):
 
 
 # ----------------------------------------------------------------------------------- NN-1
-NN1Result = namedtuple("NN1Result", "row_min row_arg col_min col_arg stats stats_arg")
-# stats: [4, B] = (sum_i row_min, max_i row_min, sum_j col_min, max_j col_min)
-# stats_arg: [2, B] int32 = (first argmax_i row_min, first argmax_j col_min)
+NN1Result = namedtuple("NN1Result", "row_min row_arg col_min col_arg row_sum row_max col_sum col_max "
+                                    "row_argmax col_argmax")
+# row_* : minima over the columns j for every row i (and their per-sample scaled sum / max / first argmax)
+# col_* : minima over the rows i for every column j
 
 
 class _Token:
@@ -64,7 +65,7 @@ class _Token:
 
 class _NN1(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, rows, cols, form, norm, swap_norms, transform, token):
+    def forward(ctx, rows, cols, form, norm, swap_norms, transform, row_scale, col_scale, token):
         global _launch_count
         lib = _lib.load()
         B, N, _ = rows.shape
@@ -75,46 +76,41 @@ class _NN1(torch.autograd.Function):
             col_min = torch.empty((B, M), dtype=torch.float32, device=dev)
             row_arg = torch.empty((B, N), dtype=torch.int32, device=dev)
             col_arg = torch.empty((B, M), dtype=torch.int32, device=dev)
-            stats_bt = torch.empty((B, 4), dtype=torch.float32, device=dev)
-            stats_i_bt = torch.empty((B, 2), dtype=torch.int32, device=dev)
+            stats = torch.empty((4, B), dtype=torch.float32, device=dev)
+            stats_i = torch.empty((2, B), dtype=torch.int32, device=dev)
             ws_bytes = lib.pcd_nn1_workspace_bytes(B, N, M)
             ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
             st = lib.pcd_nn1_forward(*_cloud_args(rows), *_cloud_args(cols), B, N, M,
-                                     form, norm, int(swap_norms), transform,
+                                     form, norm, int(swap_norms), transform, row_scale, col_scale,
                                      row_min.data_ptr(), row_arg.data_ptr(), col_min.data_ptr(), col_arg.data_ptr(),
-                                     stats_bt.data_ptr(), stats_i_bt.data_ptr(),
+                                     stats.data_ptr(), stats_i.data_ptr(),
                                      ws.data_ptr(), ws_bytes, _stream())
             _lib.check(st, "pcd_nn1_forward")
-        _launch_count += 4
-        ctx.save_for_backward(rows, cols, row_arg, col_arg, row_min, col_min, stats_i_bt)
-        ctx.cfg = (int(swap_norms), transform)
+        _launch_count += 3
+        ctx.save_for_backward(rows, cols, row_arg, col_arg, row_min, col_min, stats_i)
+        ctx.cfg = (int(swap_norms), transform, row_scale, col_scale)
         ctx.token = token
-        ctx.mark_non_differentiable(row_arg, col_arg, stats_i_bt)
-        return row_min, row_arg, col_min, col_arg, stats_bt, stats_i_bt
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(row_arg, col_arg, stats_i)
+        return row_min, row_arg, col_min, col_arg, stats[0], stats[1], stats[2], stats[3], stats_i
 
     @staticmethod
-    def backward(ctx, g_row_min, _ga, g_col_min, _gb, g_stats, _gc):
+    def backward(ctx, g_row_min, _ga, g_col_min, _gb, g_row_sum, g_row_max, g_col_sum, g_col_max, _gc):
         global _launch_count
         rows, cols, row_arg, col_arg, row_min, col_min, stats_i = ctx.saved_tensors
-        swap_norms, transform = ctx.cfg
+        swap_norms, transform, row_scale, col_scale = ctx.cfg
         ctx.token.consumed = True          # the graph is (normally) freed after this: never serve it again
+        need_r, need_c = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if not (need_r or need_c):
+            return (None,) * 9
         lib = _lib.load()
         B, N, _ = rows.shape
         M = cols.shape[1]
-        need_r, need_c = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        if not (need_r or need_c):
-            return (None,) * 7
         dev = rows.device
         with torch.cuda.device(dev):
-            g_row = None if g_row_min is None else g_row_min.contiguous()
-            g_col = None if g_col_min is None else g_col_min.contiguous()
-            w = [None] * 4
-            argmax = [None, None]
-            if g_stats is not None:
-                gs = g_stats.t().contiguous()                     # [4, B]
-                am = stats_i.t().contiguous()                     # [2, B]
-                w = [gs[0], gs[1], gs[2], gs[3]]
-                argmax = [am[0], am[1]]
+            c = lambda t: None if t is None else t.contiguous()
+            g_row, g_col = c(g_row_min), c(g_col_min)
+            w = [c(g_row_sum), c(g_row_max), c(g_col_sum), c(g_col_max)]
             grad_rows = torch.empty((B, N, 3), dtype=torch.float32, device=dev) if need_r else None
             grad_cols = torch.empty((B, M, 3), dtype=torch.float32, device=dev) if need_c else None
             gr = _cloud_args(grad_rows) if need_r else [None, 0, 0, 0]
@@ -122,12 +118,12 @@ class _NN1(torch.autograd.Function):
             st = lib.pcd_nn1_backward(*_cloud_args(rows), *_cloud_args(cols), B, N, M, swap_norms, transform,
                                       row_arg.data_ptr(), col_arg.data_ptr(), row_min.data_ptr(), col_min.data_ptr(),
                                       _ptr(g_row), _ptr(g_col),
-                                      _ptr(w[0]), _ptr(w[1]), _ptr(argmax[0]),
-                                      _ptr(w[2]), _ptr(w[3]), _ptr(argmax[1]),
-                                      *gr, *gc, _stream())
+                                      _ptr(w[0]), _ptr(w[1]), stats_i[0].data_ptr(),
+                                      _ptr(w[2]), _ptr(w[3]), stats_i[1].data_ptr(),
+                                      row_scale, col_scale, *gr, *gc, _stream())
             _lib.check(st, "pcd_nn1_backward")
         _launch_count += 2
-        return grad_rows, grad_cols, None, None, None, None, None
+        return grad_rows, grad_cols, None, None, None, None, None, None, None
 
 
 _nn1_cache = {"key": None, "val": None, "refs": None, "token": None}
@@ -140,9 +136,10 @@ def _tensor_key(t):
     return (id(root), t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()), t.requires_grad)
 
 
-def nn1(rows, cols, form, norm, swap_norms=False, transform=VALUE_SQUARED, cache=True) -> NN1Result:
+def nn1(rows, cols, form, norm, swap_norms=False, transform=VALUE_SQUARED, row_sum_scale=1.0,
+        col_sum_scale=1.0, cache=True) -> NN1Result:
     """One NN-1 sweep of every sample: row/column minima of d(i,j), lowest-index argmins and
-    per-sample sum / max (see pcd_nn1_forward in include/pcdist.h).
+    per-sample (scaled) sum / max (see pcd_nn1_forward in include/pcdist.h).
 
     rows [B,N,3], cols [B,M,3]: fp32 CUDA tensors, any strides (pass `x.transpose(1, 2)` for a
     channel-first [B,3,N] cloud).  A one-entry cache returns the previous result when called
@@ -160,12 +157,13 @@ def nn1(rows, cols, form, norm, swap_norms=False, transform=VALUE_SQUARED, cache
     key = None
     if cache:
         key = (_tensor_key(rows), _tensor_key(cols), form, norm, bool(swap_norms), transform,
-               torch.is_grad_enabled())
+               float(row_sum_scale), float(col_sum_scale), torch.is_grad_enabled())
         if _nn1_cache["key"] == key and not _nn1_cache["token"].consumed:
             return _nn1_cache["val"]
     token = _Token()
-    out = _NN1.apply(rows, cols, form, norm, bool(swap_norms), transform, token)
-    res = NN1Result(out[0], out[1], out[2], out[3], out[4].t(), out[5].t())
+    out = _NN1.apply(rows, cols, form, norm, bool(swap_norms), transform, float(row_sum_scale),
+                     float(col_sum_scale), token)
+    res = NN1Result(out[0], out[1], out[2], out[3], out[4], out[5], out[6], out[7], out[8][0], out[8][1])
     if cache:
         _nn1_cache["key"] = key
         _nn1_cache["val"] = res

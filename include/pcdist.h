@@ -82,10 +82,14 @@ const char *pcd_last_error(void);
  * rows  : [B,N,3] via strides (r_sb, r_sp, r_sc) in elements; cols likewise [B,M,3].
  * swap_norms != 0 (requires N == M): nrow[i] = |cols_i|^2 and ncol[j] = |rows_j|^2 -- the
  *   broadcast of attack/GeoA3/knn_utils.py:13-15.
- * Outputs (any of the four per-point arrays may NOT be NULL):
+ * Outputs (none may be NULL):
  *   row_min[B,N] row_arg[B,N] col_min[B,M] col_arg[B,M]   (values after `transform`)
- *   stats_f[B,4] = {sum_i row_min, max_i row_min, sum_j col_min, max_j col_min}
- *   stats_i[B,2] = {first argmax_i row_min, first argmax_j col_min}
+ *   stats_f[4,B] = {row_sum_scale * sum_i row_min, max_i row_min,
+ *                   col_sum_scale * sum_j col_min, max_j col_min}   (each row contiguous over B)
+ *   stats_i[2,B] = {first argmax_i row_min, first argmax_j col_min}
+ * row_sum_scale / col_sum_scale fold the reference's divisors into the kernel (1/N2 and 1/N1
+ * for distance.py's means, 1/3 for dis_utils_torch.chamfer's quirk, 1 for plain sums); the sums
+ * are accumulated in a fixed order (run-to-run deterministic).
  * ---------------------------------------------------------------------------------- */
 size_t pcd_nn1_workspace_bytes(int B, int N, int M);
 
@@ -93,6 +97,7 @@ int pcd_nn1_forward(const float *rows, int64_t r_sb, int64_t r_sp, int64_t r_sc,
                     const float *cols, int64_t c_sb, int64_t c_sp, int64_t c_sc,
                     int B, int N, int M,
                     int form, int norm_kind, int swap_norms, int transform,
+                    float row_sum_scale, float col_sum_scale,
                     float *row_min, int32_t *row_arg, float *col_min, int32_t *col_arg,
                     float *stats_f, int32_t *stats_i,
                     void *workspace, size_t workspace_bytes, void *stream);
@@ -106,9 +111,9 @@ int pcd_nn1_set_sweep_events(void *start_event, void *stop_event);
 /* Backward of everything derived from the NN-1 minima, through the saved argmins
  * (autograd of torch.min(dim) / torch.max / mean / cdist in the reference).
  * The upstream gradient of row minimum (b,i) is
- *     g_row[b,i] + w_row_all[b] + (i == row_argmax[b] ? w_row_max[b] : 0)
- * (each term optional: NULL = 0), the same for columns.  So Chamfer (mean of minima:
- * w_*_all = g/N), Hausdorff (max of minima: w_*_max) and knn_points(K=1).dists (g_row) are
+ *     g_row[b,i] + row_sum_scale * w_row_all[b] + (i == row_argmax[b] ? w_row_max[b] : 0)
+ * (each term optional: NULL = 0), the same for columns; w_*_all / w_*_max are the upstream
+ * gradients of the four stats_f rows.  So Chamfer (scaled sum of minima: w_*_all), Hausdorff (max of minima: w_*_max) and knn_points(K=1).dists (g_row) are
  * all one call.  For PCD_VALUE_SQRT_CLAMP row_min/col_min (the stored post-sqrt values) must
  * be given: d/dp sqrt(d2) = (p - q)/sqrt(d2), 0 where it is 0 (cdist backward).
  * grad_rows / grad_cols are written in full (no need to zero them) with the caller's strides;
@@ -124,6 +129,7 @@ int pcd_nn1_backward(const float *rows, int64_t r_sb, int64_t r_sp, int64_t r_sc
                      const float *g_row, const float *g_col,
                      const float *w_row_all, const float *w_row_max, const int32_t *row_argmax,
                      const float *w_col_all, const float *w_col_max, const int32_t *col_argmax,
+                     float row_sum_scale, float col_sum_scale,
                      float *grad_rows, int64_t gr_sb, int64_t gr_sp, int64_t gr_sc,
                      float *grad_cols, int64_t gc_sb, int64_t gc_sp, int64_t gc_sc,
                      void *stream);

@@ -53,12 +53,11 @@ def check_nn1(rows, cols, form_key, swap=False):
     assert np.array_equal(npy(r.col_min), o.col_min)
     assert np.array_equal(npy(r.row_arg), o.row_arg)
     assert np.array_equal(npy(r.col_arg), o.col_arg)
-    st = npy(r.stats)
-    np.testing.assert_allclose(st[0], o.row_min.sum(1, dtype=np.float64), rtol=2e-6)
-    np.testing.assert_allclose(st[2], o.col_min.sum(1, dtype=np.float64), rtol=2e-6)
-    assert np.array_equal(st[1], o.row_min.max(1)) and np.array_equal(st[3], o.col_min.max(1))
-    sa = npy(r.stats_arg)
-    assert np.array_equal(sa[0], o.row_min.argmax(1)) and np.array_equal(sa[1], o.col_min.argmax(1))
+    np.testing.assert_allclose(npy(r.row_sum), o.row_min.sum(1, dtype=np.float64), rtol=2e-6)
+    np.testing.assert_allclose(npy(r.col_sum), o.col_min.sum(1, dtype=np.float64), rtol=2e-6)
+    assert np.array_equal(npy(r.row_max), o.row_min.max(1)) and np.array_equal(npy(r.col_max), o.col_min.max(1))
+    assert np.array_equal(npy(r.row_argmax), o.row_min.argmax(1))
+    assert np.array_equal(npy(r.col_argmax), o.col_min.argmax(1))
 
 
 # ------------------------------------------------------------------ NN-1 sweep vs the oracle
@@ -177,12 +176,12 @@ def test_fused_chamfer_hausdorff_shares_one_sweep():
     n0 = F.launches()
     c1, c2 = pcd.distance.chamfer(p, t)
     h1, h2 = pcd.distance.hausdorff(p, t)
-    assert F.launches() - n0 == 4          # second call is served by the one-entry cache
+    assert F.launches() - n0 == 3          # second call is served by the one-entry cache
     (c1.sum() + c2.sum() + h1.sum() + h2.sum()).backward()
     with torch.no_grad():
         p.add_(0.001)                        # in-place update bumps the version -> no stale hit
     c1b, _ = pcd.distance.chamfer(p, t)
-    assert F.launches() - n0 == 4 + 2 + 4
+    assert F.launches() - n0 == 3 + 2 + 3
     assert not torch.equal(c1, c1b)
 
 
@@ -388,6 +387,6 @@ def test_errors_are_loud():
     with pytest.raises(ValueError):
         F.knn(torch.zeros(1, 4, 3, device="cuda"), torch.zeros(1, 4, 3, device="cuda"), 5)       # K > M
     lib = pcd._lib.load()
-    assert lib.pcd_nn1_forward(None, 0, 0, 0, None, 0, 0, 0, 1, 1, 1, 0, 0, 0, 0,
+    assert lib.pcd_nn1_forward(None, 0, 0, 0, None, 0, 0, 0, 1, 1, 1, 0, 0, 0, 0, 1.0, 1.0,
                                None, None, None, None, None, None, None, 0, None) == 1
     assert b"NULL" in lib.pcd_last_error()

@@ -64,8 +64,8 @@ def main():
         return
     for (B, N, M) in [(32, 4096, 4096), (1, 4096, 4096), (64, 1024, 1024), (8, 16384, 16384)]:
         pairs = B * N * M
-        for R in (2, 4, 8):
-            for MT in (64, 128, 256):
+        for R in (2, 4, 8, 16):
+            for MT in (128, 256):
                 os.environ["PCD_SWEEP_R"] = str(R); os.environ["PCD_SWEEP_MT"] = str(MT)
                 sw, tot = time_sweep(B, N, M)
                 print(f"B={B} N={N} M={M} R={R} MT={MT}: sweep {sw*1e3:8.1f} us  fwd total {tot*1e3:8.1f} us  "
