@@ -136,38 +136,44 @@ struct SweepSmem {
     uint64_t full[2];                                // mbarriers: tile[s] has landed
 };
 
+constexpr int kQuad = 4;   // columns per scheduling unit (two packed steps)
+
 template <int FORM, int R>
 __global__ void __launch_bounds__(kSweepThreads, (R >= 16) ? 2 : ((R >= 8) ? 4 : ((R >= 4) ? 5 : 6)))
 nn1_sweep_kernel(const float4 *__restrict__ rowpk, const float4 *__restrict__ colpk,
                  unsigned long long *__restrict__ rowkey, unsigned long long *__restrict__ colkey,
-                 int Npad, int Mpad, int cpt /* 32-col chunks per TMA tile */, int nqt, int nch, int units) {
+                 int Npad, int Mpad, int qpt /* quads per TMA tile */, int nqt, int nq /* quads per row tile */,
+                 int units) {
     constexpr int QW = 32 * R;            // rows per warp
     constexpr int QT = kSweepWarps * QW;  // rows per CTA tile
+    constexpr int kQuadsPerChunk = kColChunk / kQuad;
     __shared__ __align__(128) SweepSmem sm;
 
-    // Stream-K at chunk granularity: the (sample, row tile, 32-column chunk) space is cut into
-    // gridDim.x equal contiguous ranges, so every CTA sweeps the same number of pairs (+-1 chunk).
+    // Stream-K at 4-column granularity: the (sample, row tile, column quad) space is cut into
+    // gridDim.x equal contiguous ranges, so every CTA sweeps the same number of pairs (+-1 quad).
+    // Ranges may start or end inside a 32-column chunk: a row tag only says "the minimum is in
+    // this chunk", and the fix-up rescans the whole chunk, so partial chunks stay exact.
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int u0 = (int)((long long)units * blockIdx.x / gridDim.x);
     const int u1 = (int)((long long)units * (blockIdx.x + 1) / gridDim.x);
     if (u0 >= u1) return;
 
-    // a segment = the chunks [u, u+n) that share one row tile and one cpt-aligned column tile
+    // a segment = the quads [u, u+n) that share one row tile and one qpt-aligned column tile
     auto seg_len = [&](int u) -> int {
-        const int ch = u % nch;
-        int e = (ch / cpt + 1) * cpt;
-        if (e > nch) e = nch;
-        const int n = e - ch;
+        const int q = u % nq;
+        int e = (q / qpt + 1) * qpt;
+        if (e > nq) e = nq;
+        const int n = e - q;
         return n < u1 - u ? n : u1 - u;
     };
     int pu = u0;   // producer cursor (thread 0)
     auto issue = [&](int buf) {
         if (pu >= u1) return;
-        const int bq = pu / nch, ch = pu - bq * nch, b = bq / nqt;
+        const int bq = pu / nq, q = pu - bq * nq, b = bq / nqt;
         const int n = seg_len(pu);
-        const uint32_t bytes = (uint32_t)n * kColChunk * 16u;
+        const uint32_t bytes = (uint32_t)n * kQuad * 16u;
         mbar_expect_tx(&sm.full[buf], bytes);
-        tma_load_1d(sm.tile[buf], colpk + (size_t)b * Mpad + (size_t)ch * kColChunk, bytes, &sm.full[buf]);
+        tma_load_1d(sm.tile[buf], colpk + (size_t)b * Mpad + (size_t)q * kQuad, bytes, &sm.full[buf]);
         pu += n;
     };
     if (tid == 0) {
@@ -189,7 +195,7 @@ nn1_sweep_kernel(const float4 *__restrict__ rowpk, const float4 *__restrict__ co
     for (int u = u0; u < u1; ++it) {
         const int buf = it & 1;
         const uint32_t parity = (it >> 1) & 1;
-        const int bq = u / nch, ch0 = u - bq * nch;
+        const int bq = u / nq, q0 = u - bq * nq;
         const int b = bq / nqt, qt = bq - b * nqt;
         const int nseg = seg_len(u);
 
@@ -216,46 +222,53 @@ nn1_sweep_kernel(const float4 *__restrict__ rowpk, const float4 *__restrict__ co
         float4 A = t4[0], Bv = t4[1];                       // operands of the step about to run
         uint2 pend_lo = make_uint2(0x7f800000u, 0u), pend_hi = pend_lo;   // column results of the previous step
         int pend_at = -1;
-        for (int c = 0; c < nseg; ++c) {
+        int qd = 0;                                          // quad cursor inside the segment
+        while (qd < nseg) {
+            // piece = the quads of this segment that fall into one 32-column chunk
+            const int chunk = (q0 + qd) / kQuadsPerChunk;
+            int pe = (chunk + 1) * kQuadsPerChunk - q0;
+            if (pe > nseg) pe = nseg;
             float m[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) m[r] = __int_as_float(0x7f800000);
-#pragma unroll 2
-            for (int s = 0; s < kColChunk / 2; ++s) {
-                const int step = c * (kColChunk / 2) + s;
-                const float4 An = t4[step * 2 + 2], Bn = t4[step * 2 + 3];   // prefetch (pad keeps it in bounds)
-                const f32x2 X = pack2(A.x, A.y), Y = pack2(A.z, A.w);
-                const f32x2 Z = pack2(Bv.x, Bv.y), Nn = pack2(Bv.z, Bv.w);
-                float lo[R], hi[R];
+            for (; qd < pe; ++qd) {
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const f32x2 d = pair_dist_x2<FORM>(qx[r], qy[r], qz[r], qn[r], X, Y, Z, Nn);
-                    unpack2(d, lo[r], hi[r]);
-                    m[r] = min3(m[r], lo[r], hi[r]);
-                }
-                float clo = lo[0], chi = hi[0];
+                for (int h = 0; h < 2; ++h) {
+                    const int step = qd * 2 + h;
+                    const float4 An = t4[step * 2 + 2], Bn = t4[step * 2 + 3];   // prefetch (pad keeps it in bounds)
+                    const f32x2 X = pack2(A.x, A.y), Y = pack2(A.z, A.w);
+                    const f32x2 Z = pack2(Bv.x, Bv.y), Nn = pack2(Bv.z, Bv.w);
+                    float lo[R], hi[R];
 #pragma unroll
-                for (int r = 1; r + 1 < R; r += 2) {
-                    clo = min3(clo, lo[r], lo[r + 1]);
-                    chi = min3(chi, hi[r], hi[r + 1]);
+                    for (int r = 0; r < R; ++r) {
+                        const f32x2 d = pair_dist_x2<FORM>(qx[r], qy[r], qz[r], qn[r], X, Y, Z, Nn);
+                        unpack2(d, lo[r], hi[r]);
+                        m[r] = min3(m[r], lo[r], hi[r]);
+                    }
+                    float clo = lo[0], chi = hi[0];
+#pragma unroll
+                    for (int r = 1; r + 1 < R; r += 2) {
+                        clo = min3(clo, lo[r], lo[r + 1]);
+                        chi = min3(chi, hi[r], hi[r + 1]);
+                    }
+                    if ((R & 1) == 0) {
+                        clo = fminf(clo, lo[R - 1]);
+                        chi = fminf(chi, hi[R - 1]);
+                    }
+                    // retire the previous step's column results (their CREDUX latency is long gone)
+                    if (pend_at >= 0) *reinterpret_cast<uint4 *>(&cp[pend_at]) = make_uint4(pend_lo.x, pend_lo.y, pend_hi.x, pend_hi.y);
+                    const float vlo = warp_min_f32(clo), vhi = warp_min_f32(chi);
+                    pend_lo = make_uint2(__float_as_uint(vlo), __ballot_sync(0xffffffffu, clo == vlo));
+                    pend_hi = make_uint2(__float_as_uint(vhi), __ballot_sync(0xffffffffu, chi == vhi));
+                    pend_at = 2 * step;
+                    A = An; Bv = Bn;
                 }
-                if ((R & 1) == 0) {
-                    clo = fminf(clo, lo[R - 1]);
-                    chi = fminf(chi, hi[R - 1]);
-                }
-                // retire the previous step's column results (their CREDUX latency is long gone)
-                if (pend_at >= 0) *reinterpret_cast<uint4 *>(&cp[pend_at]) = make_uint4(pend_lo.x, pend_lo.y, pend_hi.x, pend_hi.y);
-                const float vlo = warp_min_f32(clo), vhi = warp_min_f32(chi);
-                pend_lo = make_uint2(__float_as_uint(vlo), __ballot_sync(0xffffffffu, clo == vlo));
-                pend_hi = make_uint2(__float_as_uint(vhi), __ballot_sync(0xffffffffu, chi == vhi));
-                pend_at = 2 * step;
-                A = An; Bv = Bn;
             }
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 if (m[r] < best[r]) {
                     best[r] = m[r];
-                    btag[r] = (uint32_t)(ch0 + c);
+                    btag[r] = (uint32_t)chunk;
                 }
             }
         }
@@ -264,7 +277,7 @@ nn1_sweep_kernel(const float4 *__restrict__ rowpk, const float4 *__restrict__ co
 
         if (tid == 0) issue(buf);
         // column flush: min over the CTA's warps (lowest warp on ties), lowest lane of its ballot
-        const int ncols = nseg * kColChunk;
+        const int ncols = nseg * kQuad;
         for (int col = tid; col < ncols; col += kSweepThreads) {
             uint2 e = sm.colpart[buf][0][col];
             float v = __uint_as_float(e.x);
@@ -275,7 +288,7 @@ nn1_sweep_kernel(const float4 *__restrict__ rowpk, const float4 *__restrict__ co
                 if (__uint_as_float(o.x) < v) { v = __uint_as_float(o.x); w = k; msk = o.y; }
             }
             if (v < __int_as_float(0x7f800000))
-                atomicMin(&colkey[(size_t)b * Mpad + (size_t)ch0 * kColChunk + col],
+                atomicMin(&colkey[(size_t)b * Mpad + (size_t)q0 * kQuad + col],
                           make_key(v, (((uint32_t)qt * kSweepWarps + w) << 5) + (uint32_t)(__ffs(msk) - 1)));
         }
         u += nseg;
@@ -310,9 +323,9 @@ nn1_fixup_kernel(const float4 *__restrict__ rowpk, const float4 *__restrict__ co
     const int n = is_col ? M : N;
     const int p = blk * kFixThreads + threadIdx.x;
     float val = -__int_as_float(0x7f800000);   // neutral for max; contributes 0 to the sum
-    bool live = p < n;
+    const bool live = p < n;
     if (live) {
-        int arg = 0;
+        int arg;
         float v;
         if (!is_col) {
             const unsigned long long key = rowkey[(size_t)b * Npad + p];
@@ -323,16 +336,16 @@ nn1_fixup_kernel(const float4 *__restrict__ rowpk, const float4 *__restrict__ co
             arg = j0;
             bool found = false;
 #pragma unroll 1
-            for (int g = 0; g < kColChunk / 2 && !found; g += 4) {
-                float4 a[4], c[4];
+            for (int g = 0; g < kColChunk / 2 && !found; g += 8) {   // 8 records = 16 columns per batch of loads
+                float4 a[8], c[8];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) { a[k] = __ldg(&rec[(g + k) * 2]); c[k] = __ldg(&rec[(g + k) * 2 + 1]); }
+                for (int k = 0; k < 8; ++k) { a[k] = __ldg(&rec[(g + k) * 2]); c[k] = __ldg(&rec[(g + k) * 2 + 1]); }
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float d0 = pair_dist_scalar<FORM>(q.x, q.y, q.z, q.w, a[k].x, a[k].z, c[k].x, c[k].z);
+                for (int k = 7; k >= 0; --k) {                       // descending: the lowest match is written last
                     const float d1 = pair_dist_scalar<FORM>(q.x, q.y, q.z, q.w, a[k].y, a[k].w, c[k].y, c[k].w);
-                    if (!found && d0 == v) { found = true; arg = j0 + (g + k) * 2; }
-                    if (!found && d1 == v) { found = true; arg = j0 + (g + k) * 2 + 1; }
+                    const float d0 = pair_dist_scalar<FORM>(q.x, q.y, q.z, q.w, a[k].x, a[k].z, c[k].x, c[k].z);
+                    if (d1 == v) { found = true; arg = j0 + (g + k) * 2 + 1; }
+                    if (d0 == v) { found = true; arg = j0 + (g + k) * 2; }
                 }
             }
             val = apply_transform(transform, v);
@@ -345,41 +358,51 @@ nn1_fixup_kernel(const float4 *__restrict__ rowpk, const float4 *__restrict__ co
             const int i0 = (int)(tag >> 5) * (32 * R) + (int)(tag & 31u) * R;
             const float *rec = reinterpret_cast<const float *>(colpk) + ((size_t)b * Mpad + (p & ~1)) * 4 + (p & 1);
             const float cx = rec[0], cy = rec[2], cz = rec[4], cn = rec[6];
+            const float4 *rq = rowpk + (size_t)b * Npad + i0;
             arg = i0;
             bool found = false;
-            for (int r = 0; r < R; ++r) {
-                const float4 q = __ldg(&rowpk[(size_t)b * Npad + i0 + r]);
-                const float d = pair_dist_scalar<FORM>(q.x, q.y, q.z, q.w, cx, cy, cz, cn);
-                if (!found && d == v) { found = true; arg = i0 + r; }
+#pragma unroll 1
+            for (int g = 0; g < R && !found; g += 8) {               // R is 2, 4, 8 or 16
+                float4 q[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) q[k] = (g + k < R) ? __ldg(&rq[g + k]) : make_float4(0.f, 0.f, 0.f, __int_as_float(0x7fc00000));
+#pragma unroll
+                for (int k = 7; k >= 0; --k) {
+                    const float d = pair_dist_scalar<FORM>(q[k].x, q[k].y, q[k].z, q[k].w, cx, cy, cz, cn);
+                    if (d == v) { found = true; arg = i0 + g + k; }   // NaN filler never matches
+                }
             }
             val = apply_transform(transform, v);
             col_min[(size_t)b * M + p] = val;
             col_arg[(size_t)b * M + p] = arg;
         }
     }
-    // ---- block reduction (fixed order) ----
-    __shared__ float ss[kFixThreads], smx[kFixThreads];
-    __shared__ int sam[kFixThreads];
-    __shared__ bool is_last;
-    ss[threadIdx.x] = live ? val : 0.f;
-    smx[threadIdx.x] = val;
-    sam[threadIdx.x] = live ? p : 0x7fffffff;
-    __syncthreads();
-    for (int o = kFixThreads / 2; o > 0; o >>= 1) {
-        if (threadIdx.x < o) {
-            ss[threadIdx.x] += ss[threadIdx.x + o];
-            const float om = smx[threadIdx.x + o];
-            const int oa = sam[threadIdx.x + o];
-            if (om > smx[threadIdx.x] || (om == smx[threadIdx.x] && oa < sam[threadIdx.x])) {
-                smx[threadIdx.x] = om; sam[threadIdx.x] = oa;
-            }
-        }
-        __syncthreads();
+    // ---- block reduction (fixed order: lanes by xor-shuffle, then the 8 warps in index order) ----
+    float s = live ? val : 0.f, mx = val;
+    int am = live ? p : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, am, o);
+        if (om > mx || (om == mx && oa < am)) { mx = om; am = oa; }
     }
+    __shared__ float ws[kFixThreads / 32], wmx[kFixThreads / 32];
+    __shared__ int wam[kFixThreads / 32];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { ws[warp] = s; wmx[warp] = mx; wam[warp] = am; }
+    __syncthreads();
     const int nblk = is_col ? nblk_c : nblk_r;
     float4 *part = partial + (size_t)b * (nblk_r + nblk_c) + (is_col ? nblk_r : 0);
     if (threadIdx.x == 0) {
-        part[blk] = make_float4(ss[0], smx[0], __int_as_float(sam[0]), 0.f);
+        float bs = 0.f, bm = -__int_as_float(0x7f800000);
+        int ba = 0x7fffffff;
+        for (int k = 0; k < kFixThreads / 32; ++k) {
+            bs += ws[k];
+            if (wmx[k] > bm || (wmx[k] == bm && wam[k] < ba)) { bm = wmx[k]; ba = wam[k]; }
+        }
+        part[blk] = make_float4(bs, bm, __int_as_float(ba), 0.f);
         __threadfence();
         const unsigned done = atomicAdd(&counter[b * 2 + (is_col ? 1 : 0)], 1u);
         is_last = (done == (unsigned)nblk - 1u);
@@ -387,17 +410,17 @@ nn1_fixup_kernel(const float4 *__restrict__ rowpk, const float4 *__restrict__ co
     __syncthreads();
     if (is_last && threadIdx.x == 0) {
         __threadfence();
-        float s = 0.f, mx = -__int_as_float(0x7f800000);
-        int am = 0;
+        float t = 0.f, tm = -__int_as_float(0x7f800000);
+        int ta = 0;
         for (int k = 0; k < nblk; ++k) {
             const float4 e = __ldcg(&part[k]);
-            s += e.x;
-            if (e.y > mx) { mx = e.y; am = __float_as_int(e.z); }
+            t += e.x;
+            if (e.y > tm) { tm = e.y; ta = __float_as_int(e.z); }
         }
         const int side = is_col ? 1 : 0;
-        stats_f[(side * 2 + 0) * B + b] = s * (is_col ? col_scale : row_scale);
-        stats_f[(side * 2 + 1) * B + b] = mx;
-        stats_i[side * B + b] = am;
+        stats_f[(side * 2 + 0) * B + b] = t * (is_col ? col_scale : row_scale);
+        stats_f[(side * 2 + 1) * B + b] = tm;
+        stats_i[side * B + b] = ta;
     }
 }
 
@@ -411,6 +434,7 @@ struct BwdArgs {
     const float *g_row, *g_col;
     const float *w_row_all, *w_row_max; const int32_t *row_argmax;
     const float *w_col_all, *w_col_max; const int32_t *col_argmax;
+    int64_t ws0, ws1, ws2, ws3;     // element strides of the four w arrays (0 = broadcast scalar)
     float row_scale, col_scale;
     float *grad_rows; int64_t gr_sb, gr_sp, gr_sc;
     float *grad_cols; int64_t gc_sb, gc_sp, gc_sc;
@@ -420,12 +444,12 @@ __device__ __forceinline__ float3 ld3(const float *base, int64_t sc) {
     return make_float3(base[0], base[sc], base[2 * sc]);
 }
 // upstream gradient of minimum (b,p) on one side
-__device__ __forceinline__ float upstream(const float *g, const float *w_all, const float *w_max,
-                                          const int32_t *argmax, int b, int p, int n, float scale) {
+__device__ __forceinline__ float upstream(const float *g, const float *w_all, int64_t s_all, const float *w_max,
+                                          int64_t s_max, const int32_t *argmax, int b, int p, int n, float scale) {
     float r = 0.f;
     if (g) r += g[(size_t)b * n + p];
-    if (w_all) r += w_all[b] * scale;
-    if (w_max && argmax[b] == p) r += w_max[b];
+    if (w_all) r += w_all[b * s_all] * scale;
+    if (w_max && argmax[b] == p) r += w_max[b * s_max];
     return r;
 }
 // d(value)/d(d2) factor: squared -> 2 * g (applied to (p - q)); sqrt -> g / v, 0 at v == 0
@@ -437,10 +461,22 @@ __device__ __forceinline__ float chain_factor(int transform, float g, const floa
     return 2.f * g;
 }
 
-// Pass 1 (plain stores, writes every gradient element): the terms indexed by the thread's own
-// point.  Pass 2 (atomics): the terms that land on the argmin partner.
-template <bool SCATTER>
+// MODE 0 (plain stores, writes every gradient element): the terms indexed by the thread's own
+// point.  MODE 1 (atomics): the terms that land on the argmin partner.  MODE 2 = both in one
+// launch with atomics only, for gradients the host has zeroed (dense outputs: one memset +
+// one kernel instead of two dependent kernels).
+template <int MODE>
+__device__ __forceinline__ void emit3(float *gp, int64_t sc, float x, float y, float z) {
+    if (MODE == 0) {
+        gp[0] = x; gp[sc] = y; gp[2 * sc] = z;
+    } else {
+        atomicAdd(gp, x); atomicAdd(gp + sc, y); atomicAdd(gp + 2 * sc, z);
+    }
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(256) nn1_bwd_kernel(BwdArgs a) {
+    constexpr bool OWN = MODE != 1, SCAT = MODE != 0;
     const long long total = (long long)a.B * (a.N + a.M);
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
          t += (long long)gridDim.x * blockDim.x) {
@@ -449,72 +485,58 @@ __global__ void __launch_bounds__(256) nn1_bwd_kernel(BwdArgs a) {
         const float *rb = a.rows + b * a.r_sb, *cb = a.cols + b * a.c_sb;
         if (p < a.N) {
             const int i = p;
-            const float g = upstream(a.g_row, a.w_row_all, a.w_row_max, a.row_argmax, b, i, a.N, a.row_scale);
+            const float g = upstream(a.g_row, a.w_row_all, a.ws0, a.w_row_max, a.ws1, a.row_argmax, b, i, a.N, a.row_scale);
             const int j = a.row_arg[(size_t)b * a.N + i];
             const float3 r = ld3(rb + i * a.r_sp, a.r_sc), c = ld3(cb + j * a.c_sp, a.c_sc);
             const float f = chain_factor(a.transform, g, a.row_min, (size_t)b * a.N + i);
-            if (!SCATTER) {
-                if (a.grad_rows) {
-                    float3 o;
-                    if (a.swap_norms) {
-                        // entry (i,j): -2 g c_j ; column-direction entry (i*, j=i): +2 g' r_i
-                        const float g2 = upstream(a.g_col, a.w_col_all, a.w_col_max, a.col_argmax, b, i, a.M, a.col_scale);
-                        o = make_float3(-f * c.x + 2.f * g2 * r.x, -f * c.y + 2.f * g2 * r.y, -f * c.z + 2.f * g2 * r.z);
-                    } else {
-                        o = make_float3(f * (r.x - c.x), f * (r.y - c.y), f * (r.z - c.z));
-                    }
-                    float *gp = a.grad_rows + b * a.gr_sb + i * a.gr_sp;
-                    gp[0] = o.x; gp[a.gr_sc] = o.y; gp[2 * a.gr_sc] = o.z;
+            if (OWN && a.grad_rows) {
+                float3 o;
+                if (a.swap_norms) {
+                    // entry (i,j): -2 g c_j ; column-direction entry (i*, j=i): +2 g' r_i
+                    const float g2 = upstream(a.g_col, a.w_col_all, a.ws2, a.w_col_max, a.ws3, a.col_argmax, b, i, a.M, a.col_scale);
+                    o = make_float3(-f * c.x + 2.f * g2 * r.x, -f * c.y + 2.f * g2 * r.y, -f * c.z + 2.f * g2 * r.z);
+                } else {
+                    o = make_float3(f * (r.x - c.x), f * (r.y - c.y), f * (r.z - c.z));
                 }
-            } else if (g != 0.f) {
+                emit3<MODE>(a.grad_rows + b * a.gr_sb + i * a.gr_sp, a.gr_sc, o.x, o.y, o.z);
+            }
+            if (SCAT && g != 0.f) {
                 if (a.grad_cols) {
                     float *gp = a.grad_cols + b * a.gc_sb + j * a.gc_sp;
-                    if (a.swap_norms) {
-                        atomicAdd(gp, -f * r.x); atomicAdd(gp + a.gc_sc, -f * r.y); atomicAdd(gp + 2 * a.gc_sc, -f * r.z);
-                    } else {
-                        atomicAdd(gp, -f * (r.x - c.x)); atomicAdd(gp + a.gc_sc, -f * (r.y - c.y));
-                        atomicAdd(gp + 2 * a.gc_sc, -f * (r.z - c.z));
-                    }
+                    if (a.swap_norms) emit3<1>(gp, a.gc_sc, -f * r.x, -f * r.y, -f * r.z);
+                    else emit3<1>(gp, a.gc_sc, -f * (r.x - c.x), -f * (r.y - c.y), -f * (r.z - c.z));
                 }
                 if (a.swap_norms && a.grad_rows) {   // |rows_j|^2 term of entry (i,j)
                     const float3 rj = ld3(rb + j * a.r_sp, a.r_sc);
-                    float *gp = a.grad_rows + b * a.gr_sb + j * a.gr_sp;
-                    atomicAdd(gp, f * rj.x); atomicAdd(gp + a.gr_sc, f * rj.y); atomicAdd(gp + 2 * a.gr_sc, f * rj.z);
+                    emit3<1>(a.grad_rows + b * a.gr_sb + j * a.gr_sp, a.gr_sc, f * rj.x, f * rj.y, f * rj.z);
                 }
             }
         } else {
             const int j = p - a.N;
-            const float g = upstream(a.g_col, a.w_col_all, a.w_col_max, a.col_argmax, b, j, a.M, a.col_scale);
+            const float g = upstream(a.g_col, a.w_col_all, a.ws2, a.w_col_max, a.ws3, a.col_argmax, b, j, a.M, a.col_scale);
             const int i = a.col_arg[(size_t)b * a.M + j];
             const float3 r = ld3(rb + i * a.r_sp, a.r_sc), c = ld3(cb + j * a.c_sp, a.c_sc);
             const float f = chain_factor(a.transform, g, a.col_min, (size_t)b * a.M + j);
-            if (!SCATTER) {
-                if (a.grad_cols) {
-                    float3 o;
-                    if (a.swap_norms) {
-                        // entry (i*,j): -2 g' r_i* ; row-direction entry (i=j, j*): +2 g c_j
-                        const float g1 = upstream(a.g_row, a.w_row_all, a.w_row_max, a.row_argmax, b, j, a.N, a.row_scale);
-                        o = make_float3(-f * r.x + 2.f * g1 * c.x, -f * r.y + 2.f * g1 * c.y, -f * r.z + 2.f * g1 * c.z);
-                    } else {
-                        o = make_float3(f * (c.x - r.x), f * (c.y - r.y), f * (c.z - r.z));
-                    }
-                    float *gp = a.grad_cols + b * a.gc_sb + j * a.gc_sp;
-                    gp[0] = o.x; gp[a.gc_sc] = o.y; gp[2 * a.gc_sc] = o.z;
+            if (OWN && a.grad_cols) {
+                float3 o;
+                if (a.swap_norms) {
+                    // entry (i*,j): -2 g' r_i* ; row-direction entry (i=j, j*): +2 g c_j
+                    const float g1 = upstream(a.g_row, a.w_row_all, a.ws0, a.w_row_max, a.ws1, a.row_argmax, b, j, a.N, a.row_scale);
+                    o = make_float3(-f * r.x + 2.f * g1 * c.x, -f * r.y + 2.f * g1 * c.y, -f * r.z + 2.f * g1 * c.z);
+                } else {
+                    o = make_float3(f * (c.x - r.x), f * (c.y - r.y), f * (c.z - r.z));
                 }
-            } else if (g != 0.f) {
+                emit3<MODE>(a.grad_cols + b * a.gc_sb + j * a.gc_sp, a.gc_sc, o.x, o.y, o.z);
+            }
+            if (SCAT && g != 0.f) {
                 if (a.grad_rows) {
                     float *gp = a.grad_rows + b * a.gr_sb + i * a.gr_sp;
-                    if (a.swap_norms) {
-                        atomicAdd(gp, -f * c.x); atomicAdd(gp + a.gr_sc, -f * c.y); atomicAdd(gp + 2 * a.gr_sc, -f * c.z);
-                    } else {
-                        atomicAdd(gp, -f * (c.x - r.x)); atomicAdd(gp + a.gr_sc, -f * (c.y - r.y));
-                        atomicAdd(gp + 2 * a.gr_sc, -f * (c.z - r.z));
-                    }
+                    if (a.swap_norms) emit3<1>(gp, a.gr_sc, -f * c.x, -f * c.y, -f * c.z);
+                    else emit3<1>(gp, a.gr_sc, -f * (c.x - r.x), -f * (c.y - r.y), -f * (c.z - r.z));
                 }
                 if (a.swap_norms && a.grad_cols) {   // |cols_i*|^2 term of entry (i*,j)
                     const float3 ci = ld3(cb + i * a.c_sp, a.c_sc);
-                    float *gp = a.grad_cols + b * a.gc_sb + i * a.gc_sp;
-                    atomicAdd(gp, f * ci.x); atomicAdd(gp + a.gc_sc, f * ci.y); atomicAdd(gp + 2 * a.gc_sc, f * ci.z);
+                    emit3<1>(a.grad_cols + b * a.gc_sb + i * a.gc_sp, a.gc_sc, f * ci.x, f * ci.y, f * ci.z);
                 }
             }
         }
@@ -538,8 +560,8 @@ static cudaError_t launch_sweep(const float4 *rowpk, const float4 *colpk, unsign
                                 int sms, cudaStream_t st) {
     const int QT = kSweepWarps * 32 * R;
     const int nqt = (N + QT - 1) / QT;                       // fully inert row tiles are skipped
-    const int nch = (M + kColChunk - 1) / kColChunk;         // ... and fully inert column chunks
-    const long long units = (long long)B * nqt * nch;
+    const int nq = (M + kQuad - 1) / kQuad;                  // ... and fully inert column quads
+    const long long units = (long long)B * nqt * nq;
     if (units >= (1LL << 31)) return cudaErrorInvalidValue;
     int occ = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nn1_sweep_kernel<FORM, R>, kSweepThreads, 0);
@@ -548,7 +570,7 @@ static cudaError_t launch_sweep(const float4 *rowpk, const float4 *colpk, unsign
     long long grid = (long long)sms * occ;
     if (grid > units) grid = units;
     nn1_sweep_kernel<FORM, R><<<(unsigned)grid, kSweepThreads, 0, st>>>(rowpk, colpk, rowkey, colkey, Npad, Mpad,
-                                                                         mt / kColChunk, nqt, nch, (int)units);
+                                                                         mt / kQuad, nqt, nq, (int)units);
     return cudaGetLastError();
 }
 
@@ -693,7 +715,7 @@ extern "C" int pcd_nn1_backward(const float *rows, int64_t r_sb, int64_t r_sp, i
                                 const float *g_row, const float *g_col,
                                 const float *w_row_all, const float *w_row_max, const int32_t *row_argmax,
                                 const float *w_col_all, const float *w_col_max, const int32_t *col_argmax,
-                                float row_sum_scale, float col_sum_scale,
+                                const int64_t *w_strides, float row_sum_scale, float col_sum_scale,
                                 float *grad_rows, int64_t gr_sb, int64_t gr_sp, int64_t gr_sc,
                                 float *grad_cols, int64_t gc_sb, int64_t gc_sp, int64_t gc_sc, void *stream) {
     if (!rows || !cols || !row_arg || !col_arg || B <= 0 || N <= 0 || M <= 0) {
@@ -717,15 +739,26 @@ extern "C" int pcd_nn1_backward(const float *rows, int64_t r_sb, int64_t r_sp, i
     if (sms <= 0) return cuda_fail(cudaGetLastError(), "no CUDA device");
     BwdArgs a{rows, r_sb, r_sp, r_sc, cols, c_sb, c_sp, c_sc, B, N, M, swap_norms, transform,
               row_arg, col_arg, row_min, col_min, g_row, g_col,
-              w_row_all, w_row_max, row_argmax, w_col_all, w_col_max, col_argmax, row_sum_scale, col_sum_scale,
+              w_row_all, w_row_max, row_argmax, w_col_all, w_col_max, col_argmax,
+              w_strides ? w_strides[0] : 1, w_strides ? w_strides[1] : 1, w_strides ? w_strides[2] : 1,
+              w_strides ? w_strides[3] : 1, row_sum_scale, col_sum_scale,
               grad_rows, gr_sb, gr_sp, gr_sc, grad_cols, gc_sb, gc_sp, gc_sc};
     const long long total = (long long)B * (N + M);
     const long long want = (total + 255) / 256;
     const int grid = (int)(want < (long long)sms * 16 ? want : (long long)sms * 16);
     cudaStream_t st = (cudaStream_t)stream;
-    nn1_bwd_kernel<false><<<grid, 256, 0, st>>>(a);
-    PCD_CUDA_CHECK(cudaGetLastError());
-    nn1_bwd_kernel<true><<<grid, 256, 0, st>>>(a);
-    PCD_CUDA_CHECK(cudaGetLastError());
+    const bool dense_r = !grad_rows || (gr_sc == 1 && gr_sp == 3 && gr_sb == (int64_t)N * 3);
+    const bool dense_c = !grad_cols || (gc_sc == 1 && gc_sp == 3 && gc_sb == (int64_t)M * 3);
+    if (dense_r && dense_c) {
+        if (grad_rows) PCD_CUDA_CHECK(cudaMemsetAsync(grad_rows, 0, (size_t)B * N * 3 * sizeof(float), st));
+        if (grad_cols) PCD_CUDA_CHECK(cudaMemsetAsync(grad_cols, 0, (size_t)B * M * 3 * sizeof(float), st));
+        nn1_bwd_kernel<2><<<grid, 256, 0, st>>>(a);
+        PCD_CUDA_CHECK(cudaGetLastError());
+    } else {
+        nn1_bwd_kernel<0><<<grid, 256, 0, st>>>(a);
+        PCD_CUDA_CHECK(cudaGetLastError());
+        nn1_bwd_kernel<1><<<grid, 256, 0, st>>>(a);
+        PCD_CUDA_CHECK(cudaGetLastError());
+    }
     return PCD_OK;
 }

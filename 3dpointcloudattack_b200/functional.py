@@ -6,6 +6,7 @@ module computes a distance with torch ops and nothing falls back to CPU.
 """
 from __future__ import annotations
 
+import ctypes
 from collections import namedtuple
 
 import torch
@@ -110,7 +111,10 @@ class _NN1(torch.autograd.Function):
         with torch.cuda.device(dev):
             c = lambda t: None if t is None else t.contiguous()
             g_row, g_col = c(g_row_min), c(g_col_min)
-            w = [c(g_row_sum), c(g_row_max), c(g_col_sum), c(g_col_max)]
+            # [B] upstream gradients are read through their stride: autograd hands out expanded
+            # (stride 0) views for sum()/mean() and we do not want a copy kernel per gradient
+            w = [g_row_sum, g_row_max, g_col_sum, g_col_max]
+            w_strides = (ctypes.c_int64 * 4)(*[0 if t is None else t.stride(0) for t in w])
             grad_rows = torch.empty((B, N, 3), dtype=torch.float32, device=dev) if need_r else None
             grad_cols = torch.empty((B, M, 3), dtype=torch.float32, device=dev) if need_c else None
             gr = _cloud_args(grad_rows) if need_r else [None, 0, 0, 0]
@@ -120,9 +124,9 @@ class _NN1(torch.autograd.Function):
                                       _ptr(g_row), _ptr(g_col),
                                       _ptr(w[0]), _ptr(w[1]), stats_i[0].data_ptr(),
                                       _ptr(w[2]), _ptr(w[3]), stats_i[1].data_ptr(),
-                                      row_scale, col_scale, *gr, *gc, _stream())
+                                      w_strides, row_scale, col_scale, *gr, *gc, _stream())
             _lib.check(st, "pcd_nn1_backward")
-        _launch_count += 2
+        _launch_count += 1
         return grad_rows, grad_cols, None, None, None, None, None, None, None
 
 

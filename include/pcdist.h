@@ -129,6 +129,8 @@ int pcd_nn1_backward(const float *rows, int64_t r_sb, int64_t r_sp, int64_t r_sc
                      const float *g_row, const float *g_col,
                      const float *w_row_all, const float *w_row_max, const int32_t *row_argmax,
                      const float *w_col_all, const float *w_col_max, const int32_t *col_argmax,
+                     const int64_t *w_strides /* HOST ptr to 4 element strides of the w arrays, NULL = {1,1,1,1};
+                                                 0 = one broadcast value (autograd's expanded gradients) */,
                      float row_sum_scale, float col_sum_scale,
                      float *grad_rows, int64_t gr_sb, int64_t gr_sp, int64_t gr_sc,
                      float *grad_cols, int64_t gc_sb, int64_t gc_sp, int64_t gc_sc,

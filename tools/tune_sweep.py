@@ -45,6 +45,7 @@ def time_sweep(B, N, M, reps=10, form=F.FORM_SUM_FIRST, norm=F.NORM_FMA):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--probe", action="store_true")
+    ap.add_argument("--scaling", action="store_true")
     args = ap.parse_args()
     print("device", torch.cuda.get_device_name(0), "fp32 peak TFLOP/s %.1f" % (F.fp32_peak_flops(2048) / 1e12))
     if args.probe:
@@ -61,6 +62,13 @@ def main():
         Mg = torch.cdist(a.permute(0, 2, 1), b.permute(0, 2, 1)).cpu().numpy()
         Mo = O.dis_pairwise_distances(a.cpu().numpy(), b.cpu().numpy())
         print("torch-GPU cdist == oracle: %.6f  max|diff| %.3e" % ((Mg == Mo).mean(), np.abs(Mg - Mo).max()))
+        return
+    if args.scaling:
+        for R in (8, 16):
+            os.environ["PCD_SWEEP_R"] = str(R)
+            for B in (8, 16, 32, 64, 128, 256):
+                sw, tot = time_sweep(B, 4096, 4096)
+                print(f"R={R} B={B:4d} N=M=4096: sweep {sw*1e3:8.1f} us   {B*4096*4096/sw/1e9:6.2f} Tpair/s")
         return
     for (B, N, M) in [(32, 4096, 4096), (1, 4096, 4096), (64, 1024, 1024), (8, 16384, 16384)]:
         pairs = B * N * M
