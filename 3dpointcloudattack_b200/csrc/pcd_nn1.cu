@@ -1,6 +1,6 @@
 // pcd_nn1.cu -- NN-1 sweep (Chamfer / Hausdorff / knn_points K=1) for sm_100a.
 //
-// Pipeline of pcd_nn1_forward (3 launches on the caller's stream, no host sync):
+// Pipeline of pcd_nn1_forward (4 launches on the caller's stream, no host sync):
 //   1. nn1_prep    pack both clouds into the sweep layout, compute |p|^2 in the reference's
 //                  rounding order, reset the (value,tag) keys.
 //   2. nn1_sweep   THE hot kernel: every (row i, col j) distance exactly once; row minima and
@@ -10,9 +10,9 @@
 //                  partition of (sample, row tile, col tile) units over a persistent grid.
 //                  Emits per point a 64-bit key = (ordered min value, tag of the 32-wide /
 //                  32R-wide chunk that produced it) with atomicMin.
-//   3. nn1_fixup   one thread per point re-evaluates its winning chunk (bit-identical
-//                  arithmetic) for the lowest index with d == min, then the per-sample
-//                  sum / max / first-argmax of both minima arrays (fixed order, last block folds).
+//   3. nn1_fixup   eight lanes per point re-evaluate its winning chunk (bit-identical
+//                  arithmetic) for the lowest index with d == min.
+//   4. nn1_reduce  per-sample scaled sum / max / first-argmax of both minima arrays (fixed order).
 //
 // Reference semantics served: utils/dis_utils_torch.py:8-28, attack/CW/CW_utils/distance.py:15-70,
 // attack/GeoA3/knn_utils.py:10-55 (K=1); see include/pcdist.h.
@@ -44,7 +44,7 @@ constexpr int kSweepThreads = kSweepWarps * 32;
 constexpr int kColChunk = 32;     // columns per row-direction tag
 constexpr int kMaxColTile = 256;  // columns per TMA stage (16 B each)
 constexpr int kRowPadUnit = 2048; // rows are padded to a multiple of 128*R, R <= 16
-constexpr int kFixThreads = 256;  // points per fix-up block
+constexpr int kFixThreads = 128;  // points per fix-up block (8 lanes each)
 constexpr int kMaxFixBlocks = 4096;
 
 struct Nn1Layout {
@@ -302,55 +302,51 @@ __device__ __forceinline__ float apply_transform(int transform, float v) {
     return transform == PCD_VALUE_SQRT_CLAMP ? sqrtf(fmaxf(v, 0.0f)) : v;
 }
 
-// One thread per point.  A row point re-evaluates the 32 columns of its winning chunk, a column
-// point the R rows of its winning lane -- with the sweep's exact arithmetic -- and takes the
-// lowest index whose distance equals the minimum.  The block then reduces its 256 values
-// (sum, max, first argmax) in a fixed order; the last block of each (sample, side) folds the
-// block partials in index order, so the statistics are run-to-run deterministic.
+// Eight lanes per point (coalesced 128-byte reads of the winning chunk).  A row point
+// re-evaluates the 32 columns of its winning chunk, a column point the R rows of its winning
+// lane -- with the sweep's exact arithmetic -- and takes the lowest index whose distance equals
+// the minimum.  The block then reduces its 128 values (sum, max, first argmax) in a fixed
+// order; the last block of each (sample, side) folds the block partials in a fixed order too,
+// so the statistics are run-to-run deterministic.
+__device__ __forceinline__ void reduce_smf(float &s, float &mx, int &am) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, am, o);
+        if (om > mx || (om == mx && oa < am)) { mx = om; am = oa; }
+    }
+}
+
 template <int FORM>
-__global__ void __launch_bounds__(kFixThreads)
+__global__ void __launch_bounds__(256)
 nn1_fixup_kernel(const float4 *__restrict__ rowpk, const float4 *__restrict__ colpk,
                  const unsigned long long *__restrict__ rowkey, const unsigned long long *__restrict__ colkey,
-                 int N, int M, int Npad, int Mpad, int R, int transform, int nblk_r, int nblk_c,
-                 float row_scale, float col_scale,
+                 int N, int M, int Npad, int Mpad, int R, int transform,
                  float *__restrict__ row_min, int32_t *__restrict__ row_arg,
-                 float *__restrict__ col_min, int32_t *__restrict__ col_arg,
-                 float4 *__restrict__ partial, unsigned int *__restrict__ counter,
-                 float *__restrict__ stats_f, int32_t *__restrict__ stats_i, int B) {
+                 float *__restrict__ col_min, int32_t *__restrict__ col_arg) {
     const int b = blockIdx.y;
-    const bool is_col = (int)blockIdx.x >= nblk_r;
-    const int blk = is_col ? blockIdx.x - nblk_r : blockIdx.x;
-    const int n = is_col ? M : N;
-    const int p = blk * kFixThreads + threadIdx.x;
-    float val = -__int_as_float(0x7f800000);   // neutral for max; contributes 0 to the sum
-    const bool live = p < n;
+    const int l8 = threadIdx.x & 7;
+    int p = blockIdx.x * 32 + (threadIdx.x >> 3);           // 32 points per block, rows first then columns
+    const bool is_col = p >= N;
+    if (is_col) p -= N;
+    const bool live = p < (is_col ? M : N);
+    int arg = 0x7fffffff;
+    float v = 0.f;
     if (live) {
-        int arg;
-        float v;
         if (!is_col) {
             const unsigned long long key = rowkey[(size_t)b * Npad + p];
             v = ordered_to_f32((uint32_t)(key >> 32));
             const int j0 = (int)(uint32_t)key * kColChunk;
             const float4 q = __ldg(&rowpk[(size_t)b * Npad + p]);
             const float4 *rec = colpk + (size_t)b * Mpad + j0;
-            arg = j0;
-            bool found = false;
-#pragma unroll 1
-            for (int g = 0; g < kColChunk / 2 && !found; g += 8) {   // 8 records = 16 columns per batch of loads
-                float4 a[8], c[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) { a[k] = __ldg(&rec[(g + k) * 2]); c[k] = __ldg(&rec[(g + k) * 2 + 1]); }
-#pragma unroll
-                for (int k = 7; k >= 0; --k) {                       // descending: the lowest match is written last
-                    const float d1 = pair_dist_scalar<FORM>(q.x, q.y, q.z, q.w, a[k].y, a[k].w, c[k].y, c[k].w);
-                    const float d0 = pair_dist_scalar<FORM>(q.x, q.y, q.z, q.w, a[k].x, a[k].z, c[k].x, c[k].z);
-                    if (d1 == v) { found = true; arg = j0 + (g + k) * 2 + 1; }
-                    if (d0 == v) { found = true; arg = j0 + (g + k) * 2; }
-                }
-            }
-            val = apply_transform(transform, v);
-            row_min[(size_t)b * N + p] = val;
-            row_arg[(size_t)b * N + p] = arg;
+            // lane l8 takes records l8 and l8+8 (columns 2*l8, 2*l8+1, 16+2*l8, 17+2*l8)
+            const float4 a0 = __ldg(&rec[2 * l8]), c0 = __ldg(&rec[2 * l8 + 1]);
+            const float4 a1 = __ldg(&rec[16 + 2 * l8]), c1 = __ldg(&rec[17 + 2 * l8]);
+            if (pair_dist_scalar<FORM>(q.x, q.y, q.z, q.w, a1.y, a1.w, c1.y, c1.w) == v) arg = j0 + 17 + 2 * l8;
+            if (pair_dist_scalar<FORM>(q.x, q.y, q.z, q.w, a1.x, a1.z, c1.x, c1.z) == v) arg = j0 + 16 + 2 * l8;
+            if (pair_dist_scalar<FORM>(q.x, q.y, q.z, q.w, a0.y, a0.w, c0.y, c0.w) == v) arg = j0 + 1 + 2 * l8;
+            if (pair_dist_scalar<FORM>(q.x, q.y, q.z, q.w, a0.x, a0.z, c0.x, c0.z) == v) arg = j0 + 2 * l8;
         } else {
             const unsigned long long key = colkey[(size_t)b * Mpad + p];
             v = ordered_to_f32((uint32_t)(key >> 32));
@@ -359,68 +355,56 @@ nn1_fixup_kernel(const float4 *__restrict__ rowpk, const float4 *__restrict__ co
             const float *rec = reinterpret_cast<const float *>(colpk) + ((size_t)b * Mpad + (p & ~1)) * 4 + (p & 1);
             const float cx = rec[0], cy = rec[2], cz = rec[4], cn = rec[6];
             const float4 *rq = rowpk + (size_t)b * Npad + i0;
-            arg = i0;
-            bool found = false;
-#pragma unroll 1
-            for (int g = 0; g < R && !found; g += 8) {               // R is 2, 4, 8 or 16
-                float4 q[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) q[k] = (g + k < R) ? __ldg(&rq[g + k]) : make_float4(0.f, 0.f, 0.f, __int_as_float(0x7fc00000));
-#pragma unroll
-                for (int k = 7; k >= 0; --k) {
-                    const float d = pair_dist_scalar<FORM>(q[k].x, q[k].y, q[k].z, q[k].w, cx, cy, cz, cn);
-                    if (d == v) { found = true; arg = i0 + g + k; }   // NaN filler never matches
-                }
+            // lane l8 takes rows l8 and l8+8 of the winning lane's R rows (R = 2, 4, 8 or 16)
+            if (l8 + 8 < R) {
+                const float4 q = __ldg(&rq[l8 + 8]);
+                if (pair_dist_scalar<FORM>(q.x, q.y, q.z, q.w, cx, cy, cz, cn) == v) arg = i0 + l8 + 8;
             }
-            val = apply_transform(transform, v);
-            col_min[(size_t)b * M + p] = val;
-            col_arg[(size_t)b * M + p] = arg;
+            if (l8 < R) {
+                const float4 q = __ldg(&rq[l8]);
+                if (pair_dist_scalar<FORM>(q.x, q.y, q.z, q.w, cx, cy, cz, cn) == v) arg = i0 + l8;
+            }
         }
     }
-    // ---- block reduction (fixed order: lanes by xor-shuffle, then the 8 warps in index order) ----
-    float s = live ? val : 0.f, mx = val;
-    int am = live ? p : 0x7fffffff;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        s += __shfl_xor_sync(0xffffffffu, s, o);
-        const float om = __shfl_xor_sync(0xffffffffu, mx, o);
-        const int oa = __shfl_xor_sync(0xffffffffu, am, o);
-        if (om > mx || (om == mx && oa < am)) { mx = om; am = oa; }
+    for (int o = 4; o > 0; o >>= 1) arg = min(arg, __shfl_xor_sync(0xffffffffu, arg, o, 8));   // all lanes take part
+    if (live && l8 == 0) {
+        if (arg == 0x7fffffff) arg = 0;        // cannot happen: the tagged chunk holds the minimum
+        const float val = apply_transform(transform, v);
+        if (!is_col) { row_min[(size_t)b * N + p] = val; row_arg[(size_t)b * N + p] = arg; }
+        else { col_min[(size_t)b * M + p] = val; col_arg[(size_t)b * M + p] = arg; }
     }
-    __shared__ float ws[kFixThreads / 32], wmx[kFixThreads / 32];
-    __shared__ int wam[kFixThreads / 32];
-    __shared__ bool is_last;
+}
+
+// Per-sample scaled sum / max / first argmax of the minima: grid (B, 2), one block per (sample,
+// side), fixed summation order (per-thread strided partials, xor-shuffle tree, warps in order).
+__global__ void __launch_bounds__(1024)
+nn1_reduce_kernel(const float *__restrict__ row_min, const float *__restrict__ col_min, int N, int M, int B,
+                  float row_scale, float col_scale, float *__restrict__ stats_f, int32_t *__restrict__ stats_i) {
+    const int b = blockIdx.x, side = blockIdx.y;
+    const int n = side ? M : N;
+    const float *v = (side ? col_min : row_min) + (size_t)b * n;
+    float s = 0.f, mx = -__int_as_float(0x7f800000);
+    int am = 0x7fffffff;
+    for (int i = threadIdx.x; i < n; i += 1024) {
+        const float x = v[i];
+        s += x;
+        if (x > mx) { mx = x; am = i; }
+    }
+    reduce_smf(s, mx, am);
+    __shared__ float ws[32], wmx[32];
+    __shared__ int wam[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) { ws[warp] = s; wmx[warp] = mx; wam[warp] = am; }
     __syncthreads();
-    const int nblk = is_col ? nblk_c : nblk_r;
-    float4 *part = partial + (size_t)b * (nblk_r + nblk_c) + (is_col ? nblk_r : 0);
-    if (threadIdx.x == 0) {
-        float bs = 0.f, bm = -__int_as_float(0x7f800000);
-        int ba = 0x7fffffff;
-        for (int k = 0; k < kFixThreads / 32; ++k) {
-            bs += ws[k];
-            if (wmx[k] > bm || (wmx[k] == bm && wam[k] < ba)) { bm = wmx[k]; ba = wam[k]; }
+    if (warp == 0) {
+        s = ws[lane]; mx = wmx[lane]; am = wam[lane];
+        reduce_smf(s, mx, am);
+        if (lane == 0) {
+            stats_f[(side * 2 + 0) * B + b] = s * (side ? col_scale : row_scale);
+            stats_f[(side * 2 + 1) * B + b] = mx;
+            stats_i[side * B + b] = am == 0x7fffffff ? 0 : am;
         }
-        part[blk] = make_float4(bs, bm, __int_as_float(ba), 0.f);
-        __threadfence();
-        const unsigned done = atomicAdd(&counter[b * 2 + (is_col ? 1 : 0)], 1u);
-        is_last = (done == (unsigned)nblk - 1u);
-    }
-    __syncthreads();
-    if (is_last && threadIdx.x == 0) {
-        __threadfence();
-        float t = 0.f, tm = -__int_as_float(0x7f800000);
-        int ta = 0;
-        for (int k = 0; k < nblk; ++k) {
-            const float4 e = __ldcg(&part[k]);
-            t += e.x;
-            if (e.y > tm) { tm = e.y; ta = __float_as_int(e.z); }
-        }
-        const int side = is_col ? 1 : 0;
-        stats_f[(side * 2 + 0) * B + b] = t * (is_col ? col_scale : row_scale);
-        stats_f[(side * 2 + 1) * B + b] = tm;
-        stats_i[side * B + b] = ta;
     }
 }
 
@@ -692,16 +676,18 @@ extern "C" int pcd_nn1_forward(const float *rows, int64_t r_sb, int64_t r_sp, in
         if (g_sweep_ev1) PCD_CUDA_CHECK(cudaEventRecord(g_sweep_ev1, st));
     }
     {
-        const dim3 grid(L.nblk_r + L.nblk_c, B);
+        const dim3 grid((N + M + 31) / 32 + 1, B);
         const float4 *colpk4 = (const float4 *)colpk;
-#define PCD_LAUNCH_FIXUP(F)                                                                                     \
-    nn1_fixup_kernel<F><<<grid, kFixThreads, 0, st>>>(rowpk, colpk4, rowkey, colkey, N, M, L.Npad, L.Mpad, R, transform, \
-                                                      L.nblk_r, L.nblk_c, row_sum_scale, col_sum_scale, row_min, row_arg, \
-                                                      col_min, col_arg, partial, counter, stats_f, stats_i, B)
+#define PCD_LAUNCH_FIXUP(F)                                                                                    \
+    nn1_fixup_kernel<F><<<grid, 256, 0, st>>>(rowpk, colpk4, rowkey, colkey, N, M, L.Npad, L.Mpad, R, transform, \
+                                              row_min, row_arg, col_min, col_arg)
         if (form == PCD_FORM_ROW_COL) PCD_LAUNCH_FIXUP(PCD_FORM_ROW_COL);
         else if (form == PCD_FORM_COL_ROW) PCD_LAUNCH_FIXUP(PCD_FORM_COL_ROW);
         else PCD_LAUNCH_FIXUP(PCD_FORM_SUM_FIRST);
 #undef PCD_LAUNCH_FIXUP
+        PCD_CUDA_CHECK(cudaGetLastError());
+        nn1_reduce_kernel<<<dim3(B, 2), 1024, 0, st>>>(row_min, col_min, N, M, B, row_sum_scale, col_sum_scale,
+                                                       stats_f, stats_i);
         PCD_CUDA_CHECK(cudaGetLastError());
     }
     return PCD_OK;

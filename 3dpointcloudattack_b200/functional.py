@@ -87,7 +87,7 @@ class _NN1(torch.autograd.Function):
                                      stats.data_ptr(), stats_i.data_ptr(),
                                      ws.data_ptr(), ws_bytes, _stream())
             _lib.check(st, "pcd_nn1_forward")
-        _launch_count += 3
+        _launch_count += 4
         ctx.save_for_backward(rows, cols, row_arg, col_arg, row_min, col_min, stats_i)
         ctx.cfg = (int(swap_norms), transform, row_scale, col_scale)
         ctx.token = token
