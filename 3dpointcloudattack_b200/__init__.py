@@ -18,7 +18,7 @@ directory name starts with a digit; import it with importlib or through the `pcd
 module at the repository root.
 """
 from . import _lib, functional  # noqa: F401
-from . import (curvenet_util, dgcnn, dis_utils_torch, dist_utils, distance, graph, install,  # noqa: F401
+from . import (curvenet_util, cw_loop, dgcnn, dis_utils_torch, dist_utils, distance, graph, install,  # noqa: F401
                knn_utils, loss_utils, pointnet2_utils, set_distance)
 
 __version__ = "0.1.0"

@@ -35,7 +35,7 @@ class GraphedLoss:
         torch.cuda.synchronize()
         self.adv.grad = None
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, stream=side):      # same stream as the warm-up (AccumulateGrad node)
             self.loss, self.aux = fn(self.adv, self.ori)
             self.loss.backward()
         self.grad = self.adv.grad

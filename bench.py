@@ -148,6 +148,61 @@ def run_reference(args):
     }))
 
 
+# ------------------------------------------------------------------------- CW attack loop
+CW_ITERS = 100
+
+
+def _cw_dist_func(pcd):
+    cd, hd = pcd.dist_utils.ChamferDist(method="avg"), pcd.dist_utils.HausdorffDist(method="avg")
+
+    def dist(adv, ori, weights, batch_avg=False):
+        return cd(adv, ori, weights=weights, batch_avg=batch_avg) + hd(adv, ori, weights=weights, batch_avg=batch_avg)
+    return dist
+
+
+def run_cw(pcd, dev, rank, world, B):
+    """CW-style attack (attack/CW/CW_attack.py loop shape) against a random-init PointNet(106),
+    B samples per GPU, N=4096, dist = w*(Chamfer(avg)+Hausdorff(avg)), kappa=30, Adam 1e-2,
+    ClipPointsLinf(0.18).  Returns local iterations/s (eager and CUDA-graph)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import victims
+    torch.manual_seed(0)
+    model = victims.PointNetVictim(106).to(dev).eval()
+    ori_h, _ = make_inputs(B, rank * B)[1], None
+    data = ori_h.to(dev)
+    target = torch.arange(B, device=dev) % 106
+    out = {}
+    for mode in ("eager", "graph"):
+        atk = pcd.cw_loop.CWAttack(model, pcd.cw_loop.UntargetedLogitsAdvLoss(kappa=30.), _cw_dist_func(pcd),
+                                   attack_lr=1e-2, init_weight=10., max_weight=80., binary_step=1, num_iter=CW_ITERS,
+                                   clip_func=pcd.cw_loop.ClipPointsLinf(0.18), global_batch=B * world,
+                                   use_graph=(mode == "graph"))
+        atk.attack(data, target, seed=1, first_sample=rank * B)         # warm-up (and graph capture check)
+        torch.cuda.synchronize()
+        atk.attack(data, target, seed=2, first_sample=rank * B)
+        out[mode] = CW_ITERS / (atk.loop_ms * 1e-3)        # CUDA events around the iteration loop
+    return out
+
+
+def cw_cpu_baseline(iters=4):
+    """The reference-shaped CW iteration on the host cores at B=1 (BASELINE configs[0])."""
+    import torch
+    from oracle import ref_torch_port as RP
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import victims
+    torch.manual_seed(0)
+    model = victims.PointNetVictim(106).eval()
+    for p in model.parameters():
+        p.requires_grad_(False)
+    data = make_inputs(1, 0)[1]
+    target = torch.zeros(1, dtype=torch.long)
+    RP.cw_iterations_cpu(model, data, target, 1)
+    t0 = time.perf_counter()
+    RP.cw_iterations_cpu(model, data, target, iters)
+    return iters / (time.perf_counter() - t0)
+
+
 # ---------------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch
@@ -286,11 +341,16 @@ def run_ours(args):
     h2d = adv_h.numel() * 4 + ori_h.numel() * 4
     d2h = loss_h.numel() * 4 + grad_h.numel() * 4
 
+    # ---------------- secondary metric: CW attack iterations/s (device-resident loop, section 8f-1) ----
+    cw = run_cw(pcd, dev, rank, world, B)
+
     # ---------------- max over ranks, final all-gather (the only collective of the path) ---------
+    cw_t = torch.tensor([cw["eager"], cw["graph"]], device=dev, dtype=torch.float64)
     t = torch.tensor([total_ms, e2e_total_ms], device=dev, dtype=torch.float64)
     gather_ms = None
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cw_t, op=dist.ReduceOp.MIN)
         all_loss = torch.empty((world, 4, B), device=dev)
         all_adv = torch.empty((world,) + tuple(adv.shape), device=dev)
         g0, g1 = ev(), ev()
@@ -345,6 +405,14 @@ def run_ours(args):
                                   "peak_source": hbm_src, "ms": bwd_avg_ms,
                                   "note": "includes autograd glue; launch-latency bound at this size (17.8 MB)"},
             "cpu_baseline": cpu,
+            "cw_attack": {"metric": "CW attack iters/s", "iters_per_s_graph": float(cw_t[1]), "iters_per_s_eager": float(cw_t[0]),
+                          "sample_iters_per_s_graph": float(cw_t[1]) * B * world,
+                          "config": f"PointNet(106) random init, B={B}/GPU N={NPTS}, w*(Chamfer+Hausdorff avg) + logits loss kappa=30, "
+                                    f"Adam 1e-2, ClipPointsLinf 0.18, {CW_ITERS} iters; slowest rank; every rank attacks its own {B} samples",
+                          "cpu_reference_iters_per_s_B1": cw_cpu_baseline(),
+                          "note": "iters_per_s = loop iterations per second with B samples per GPU advancing together; "
+                                  "sample_iters_per_s = iterations x samples over all GPUs; CPU figure is the reference-shaped "
+                                  "loop at B=1 (its only supported batch size) on the host cores"},
             "step_ms_min_med_max": [min(step_ms), sorted(step_ms)[len(step_ms) // 2], max(step_ms)],
             "final_allgather_ms": gather_ms,
         }

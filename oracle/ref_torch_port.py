@@ -54,3 +54,53 @@ def chamfer_hausdorff_fwd_bwd(adv, ori):
     loss = (c1 + c2 + h1 + h2).sum()
     loss.backward()
     return torch.stack([c1, c2, h1, h2]).detach(), adv.grad
+
+
+# ------------------------------------------------------------------ CW iteration (CPU baseline)
+class _ChamferHausdorffAvg:
+    """dist_func used by the CW benchmark: ChamferDist('avg') + HausdorffDist('avg') with per-sample
+    weights (attack/CW/CW_utils/dist_utils.py:49-109), CPU restatement."""
+
+    def __call__(self, adv_pc, ori_pc, weights):
+        c1, c2 = chamfer_distance(adv_pc, ori_pc)
+        h1, h2 = hausdorff_distance(adv_pc, ori_pc)
+        loss = ((c1 + c2) / 2. + (h1 + h2) / 2.) * weights.float()
+        return loss.mean()
+
+
+def cw_iterations_cpu(model, data, target, num_iter, attack_lr=1e-2, init_weight=10., kappa=30., budget=0.18):
+    """`num_iter` iterations of the reference's CW loop body (attack/CW/CW_attack.py:111-178) on CPU,
+    B = data.shape[0] (the reference runs B = 1), including its host-side best tracking."""
+    import numpy as np
+    B, K = data.shape[:2]
+    ori = data.float().transpose(1, 2).contiguous().detach()
+    adv = (ori.clone() + torch.randn((B, 3, K)) * 1e-7).requires_grad_(True)
+    opt = torch.optim.Adam([adv], lr=attack_lr, weight_decay=0.)
+    weight = np.ones((B,)) * init_weight
+    bestdist = np.array([1e10] * B); bestscore = np.array([-1] * B)
+    dist_func = _ChamferHausdorffAvg()
+    label_val = target.numpy()
+    for _ in range(num_iter):
+        logits = model(adv)[0]
+        pred = torch.argmax(logits, dim=1)
+        dist_val = torch.sqrt(torch.sum((adv - ori) ** 2, dim=[1, 2])).detach().numpy()
+        pred_val = pred.detach().numpy()
+        for e, (dist, p, label) in enumerate(zip(dist_val, pred_val, label_val)):
+            if dist < bestdist[e] and p != label:
+                bestdist[e] = dist; bestscore[e] = p
+        one_hot = torch.zeros_like(logits).scatter_(1, target.view(-1, 1), 1.)
+        real = torch.sum(one_hot * logits, dim=1)
+        other = torch.max((1. - one_hot) * logits - one_hot * 10000., dim=1)[0]
+        adv_loss = torch.clamp(real - other + kappa, min=0.).mean()
+        dist_loss = dist_func(adv.transpose(1, 2).contiguous(), ori.transpose(1, 2).contiguous(),
+                              torch.from_numpy(weight))
+        loss = adv_loss + dist_loss
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        with torch.no_grad():
+            diff = adv - ori
+            norm = torch.sum(diff ** 2, dim=1) ** 0.5
+            scale = torch.clamp(budget / (norm + 1e-9), max=1.)
+            adv.data = ori + diff * scale[:, None, :]
+    return float(loss.detach())

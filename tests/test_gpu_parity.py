@@ -390,3 +390,28 @@ def test_errors_are_loud():
     assert lib.pcd_nn1_forward(None, 0, 0, 0, None, 0, 0, 0, 1, 1, 1, 0, 0, 0, 0, 1.0, 1.0,
                                None, None, None, None, None, None, None, 0, None) == 1
     assert b"NULL" in lib.pcd_last_error()
+
+
+# ------------------------------------------------- section 8f-1: device-resident CW loop
+def test_cw_loop_eager_and_graph_agree():
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import victims
+    synth = importlib.import_module("3dpointcloudattack_b200.synth")
+    torch.manual_seed(0)
+    model = victims.PointNetVictim(16).cuda().eval()
+    data = synth.face_clouds(4, 512, seed=11).cuda()
+    target = torch.tensor([0, 1, 2, 3], device="cuda")
+    cd = pcd.dist_utils.ChamferDist(method="avg"); hd = pcd.dist_utils.HausdorffDist(method="avg")
+    dist = lambda a, o, w, batch_avg=False: cd(a, o, weights=w, batch_avg=batch_avg) + hd(a, o, weights=w, batch_avg=batch_avg)
+    res = {}
+    for use_graph in (False, True):
+        atk = pcd.cw_loop.CWAttack(model, pcd.cw_loop.UntargetedLogitsAdvLoss(kappa=5.), dist, attack_lr=1e-2,
+                                   binary_step=2, num_iter=12, clip_func=pcd.cw_loop.ClipPointsLinf(0.18), use_graph=use_graph)
+        best, adv, ok = atk.attack(data, target, seed=3)
+        assert adv.shape == (4, 512, 3) and best.shape == (4,) and ok.dtype == torch.bool
+        assert torch.isfinite(adv).all()
+        assert float((adv - data).norm(dim=-1).max()) <= 0.18 + 1e-5          # projection respected
+        res[use_graph] = adv
+    assert torch.allclose(res[False], res[True], atol=1e-4)                      # atomics reorder sums only
