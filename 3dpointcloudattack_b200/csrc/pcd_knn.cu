@@ -11,6 +11,8 @@
 //
 // Reference semantics: attack/GeoA3/knn_utils.py:10-55, attack/CW/CW_utils/dist_utils.py:133-143,
 // model/dgcnn.py:194-200, model/curvenet_util.py:10-26, model/pointnet2_utils.py:84-104.
+#include <cstdlib>
+
 #include "pcd_common.cuh"
 
 namespace pcd {
@@ -106,7 +108,7 @@ struct RowSelect {
 #pragma unroll
             for (int l = 1; l < NL; ++l)
                 if (((K - 1) >> 5) == l) kl = L[l];
-            thr = key_threshold(shfl_u64(kl, (K - 1) & 31));
+            thr = fminf(thr, key_threshold(shfl_u64(kl, (K - 1) & 31)));   // only ever tightens (thr may start below +inf)
             __syncwarp();
         }
     }
@@ -136,7 +138,7 @@ struct RowSelect {
 __global__ void knn3_prep_kernel(const float *__restrict__ rows, int64_t r_sb, int64_t r_sp, int64_t r_sc,
                                  const float *__restrict__ cols, int64_t c_sb, int64_t c_sp, int64_t c_sc,
                                  int B, int N, int M, int Npad, int Mpad, int norm_kind, int swap_norms,
-                                 float4 *__restrict__ rowq, float4 *__restrict__ colq) {
+                                 float4 *__restrict__ rowq, float4 *__restrict__ colq, float *__restrict__ colpk) {
     const long long per_b = (long long)Npad + Mpad;
     const long long total = per_b * B;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
@@ -159,9 +161,147 @@ __global__ void knn3_prep_kernel(const float *__restrict__ rows, int64_t r_sb, i
                 n = sq_norm3(norm_kind, x, y, z);
             }
         }
-        if (is_row) rowq[(size_t)b * Npad + i] = make_float4(-2.f * x, -2.f * y, -2.f * z, n);
-        else colq[(size_t)b * Mpad + i] = make_float4(x, y, z, n);
+        if (is_row) {
+            rowq[(size_t)b * Npad + i] = make_float4(-2.f * x, -2.f * y, -2.f * z, n);
+        } else {
+            colq[(size_t)b * Mpad + i] = make_float4(x, y, z, n);
+            float *rec = colpk + ((size_t)b * Mpad + (i & ~1)) * 4 + (i & 1);   // pair records for the pre-pass
+            rec[0] = x; rec[2] = y; rec[4] = z; rec[6] = n;
+        }
     }
+}
+
+// ------------------------------------------------------- pre-pass: chunk minima -> tight thresholds
+// The K-th smallest distance of a row is <= the K-th smallest of its per-chunk minima (each
+// chunk minimum is a distinct candidate).  A cheap row sweep (rows in lanes, packed math, one
+// FMNMX3 per two pairs -- the NN-1 sweep without its column side) yields the chunk minima, a
+// thread per row takes their K-th smallest, and the select kernel starts from that threshold
+// instead of +inf: only ~1.2 K candidates per row ever reach the staging buffer, so the bitonic
+// merges (the dominant cost of a cold-start select) almost disappear.  Exactness is unaffected:
+// the threshold is a true upper bound of the K-th distance and the select kernel keeps every
+// candidate with d <= threshold.
+constexpr int kPreR = 4;          // rows per lane
+constexpr int kPreTile = 256;     // columns per TMA stage
+constexpr int kPreMaxChunks = 64;
+
+struct PreSmem {
+    float4 tile[2][kPreTile + 2];
+    uint64_t full[2];
+};
+
+template <int FORM>
+__global__ void __launch_bounds__(128)
+knn3_chunkmin_kernel(const float4 *__restrict__ rowq, const float4 *__restrict__ colpk, int Npad, int Mpad, int M,
+                     int W /* columns per chunk, even */, int G, float *__restrict__ cm /* [B][G][Npad] */) {
+    constexpr int R = kPreR;
+    __shared__ __align__(128) PreSmem sm;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y;
+    const int row0 = blockIdx.x * (128 * R) + warp * (32 * R) + lane;       // rows row0 + 32 r
+    const int ntiles = (M + kPreTile - 1) / kPreTile;
+    const float4 *src = colpk + (size_t)b * Mpad;
+    const uint32_t tile_bytes = kPreTile * 16u;
+    if (tid == 0) {
+        mbar_init(&sm.full[0], 1);
+        mbar_init(&sm.full[1], 1);
+        fence_mbar_init();
+        fence_proxy_async();
+        mbar_expect_tx(&sm.full[0], tile_bytes);
+        tma_load_1d(sm.tile[0], src, tile_bytes, &sm.full[0]);
+        if (ntiles > 1) {
+            mbar_expect_tx(&sm.full[1], tile_bytes);
+            tma_load_1d(sm.tile[1], src + kPreTile, tile_bytes, &sm.full[1]);
+        }
+    }
+    if (tid < 4) sm.tile[tid >> 1][kPreTile + (tid & 1)] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+
+    float qx[R], qy[R], qz[R], qn[R], m[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const float4 q = __ldg(&rowq[(size_t)b * Npad + row0 + 32 * r]);
+        qx[r] = q.x; qy[r] = q.y; qz[r] = q.z; qn[r] = q.w;
+        m[r] = __int_as_float(0x7f800000);
+    }
+    float *out = cm + (size_t)b * G * Npad + row0;
+    int chunk = 0, left = W / 2;                       // packed steps left in the current chunk
+    const int total_steps = (M + 1) / 2;
+    int done = 0;
+    for (int t = 0; t < ntiles; ++t) {
+        const int buf = t & 1;
+        mbar_wait(&sm.full[buf], (t >> 1) & 1);
+        const float4 *t4 = sm.tile[buf];
+        int nsteps = total_steps - done;
+        if (nsteps > kPreTile / 2) nsteps = kPreTile / 2;
+        float4 A = t4[0], Bv = t4[1];
+        for (int s = 0; s < nsteps; ++s) {
+            const float4 An = t4[2 * s + 2], Bn = t4[2 * s + 3];
+            const f32x2 X = pack2(A.x, A.y), Y = pack2(A.z, A.w);
+            const f32x2 Z = pack2(Bv.x, Bv.y), Nn = pack2(Bv.z, Bv.w);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                f32x2 d;
+                if (FORM == PCD_FORM_COL_ROW) {
+                    // d = (t + ncol) + nrow: the row norm is the outer term and fl(. + nrow) is monotone,
+                    // so the chunk minimum of d is fl(min(t + ncol) + nrow): add it once per chunk
+                    f32x2 tt = mul2_s(qx[r], X);
+                    tt = fma2_s(qy[r], Y, tt);
+                    tt = fma2_s(qz[r], Z, tt);
+                    d = add2(tt, Nn);
+                } else {
+                    d = pair_dist_x2<FORM>(qx[r], qy[r], qz[r], qn[r], X, Y, Z, Nn);
+                }
+                float lo, hi;
+                unpack2(d, lo, hi);
+                m[r] = min3(m[r], lo, hi);
+            }
+            A = An; Bv = Bn;
+            if (--left == 0) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    out[(size_t)chunk * Npad + 32 * r] = (FORM == PCD_FORM_COL_ROW) ? __fadd_rn(m[r], qn[r]) : m[r];
+                    m[r] = __int_as_float(0x7f800000);
+                }
+                ++chunk;
+                left = W / 2;
+            }
+        }
+        done += nsteps;
+        __syncthreads();
+        if (tid == 0 && t + 2 < ntiles) {
+            mbar_expect_tx(&sm.full[buf], tile_bytes);
+            tma_load_1d(sm.tile[buf], src + (size_t)(t + 2) * kPreTile, tile_bytes, &sm.full[buf]);
+        }
+    }
+    if (chunk < G) {       // last, partial chunk
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            out[(size_t)chunk * Npad + 32 * r] = (FORM == PCD_FORM_COL_ROW) ? __fadd_rn(m[r], qn[r]) : m[r];
+    }
+}
+
+// thread per row: K-th smallest of the G chunk minima (sorted insertion list in shared memory)
+__global__ void __launch_bounds__(128)
+knn_threshold_kernel(const float *__restrict__ cm, int Npad, int G, int K, float *__restrict__ thr0) {
+    __shared__ float list[PCD_KNN_MAX_K][128];
+    const int b = blockIdx.y, i = blockIdx.x * 128 + threadIdx.x;
+    const float *src = cm + (size_t)b * G * Npad + i;
+    int cnt = 0;
+    for (int g = 0; g < G; ++g) {
+        const float v = src[(size_t)g * Npad];
+        if (cnt == K && !(v < list[K - 1][threadIdx.x])) continue;
+        int p = cnt < K ? cnt : K - 1;
+        while (p > 0 && list[p - 1][threadIdx.x] > v) { list[p][threadIdx.x] = list[p - 1][threadIdx.x]; --p; }
+        list[p][threadIdx.x] = v;
+        if (cnt < K) ++cnt;
+    }
+    float t = __int_as_float(0x7f800000);
+    if (cnt == K) {
+        const float kth = list[K - 1][threadIdx.x];
+        // smallest float above kth: the select kernel tests d < thr, and d == kth must pass
+        if (kth < __int_as_float(0x7f800000)) t = ordered_to_f32(f32_to_ordered(kth) + 1u);
+    }
+    thr0[(size_t)b * Npad + i] = t;
 }
 
 // ------------------------------------------------------------------------- xyz k-NN kernel
@@ -173,8 +313,8 @@ struct Knn3Smem {
 
 template <int FORM, int NL>
 __global__ void __launch_bounds__(kKnnThreads)
-knn3_kernel(const float4 *__restrict__ rowq, const float4 *__restrict__ colq, int N, int M, int Npad, int Mpad,
-            int K, float *__restrict__ dists, int32_t *__restrict__ idx) {
+knn3_kernel(const float4 *__restrict__ rowq, const float4 *__restrict__ colq, const float *__restrict__ thr0,
+            int N, int M, int Npad, int Mpad, int K, float *__restrict__ dists, int32_t *__restrict__ idx) {
     __shared__ __align__(128) Knn3Smem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y;
@@ -203,6 +343,7 @@ knn3_kernel(const float4 *__restrict__ rowq, const float4 *__restrict__ colq, in
     for (int r = 0; r < kKnnRQ; ++r) {
         q[r] = __ldg(&rowq[(size_t)b * Npad + row0 + r]);   // rows are padded to a multiple of 32 per CTA
         sel[r].init();
+        if (thr0) sel[r].thr = __ldg(&thr0[(size_t)b * Npad + row0 + r]);
     }
 
     for (int t = 0; t < ntiles; ++t) {
@@ -471,17 +612,20 @@ ball_query_kernel(const float *__restrict__ xyz, int64_t x_sb, int64_t x_sp, int
 
 struct KnnLayout {
     int Npad, Mpad;
-    size_t a, b, c, d, total;   // xyz: a=rowq, b=colq ; features: a=rowf b=rown c=colT d=coln
+    size_t a, b, c, d, e, total;   // xyz: a=rowq b=colq c=colpk d=cm e=thr0 ; features: a=rowf b=rown c=colT d=coln
 };
 static KnnLayout knn_layout(int B, int N, int M, int C) {
     KnnLayout L;
-    L.Npad = (int)align_up_k((size_t)N, kKnnWarps * kKnnRQ);
+    L.Npad = (int)align_up_k((size_t)N, C == 3 ? 128 * kPreR : kKnnWarps * kKnnRQ);
     size_t off = 0;
+    L.e = 0;
     if (C == 3) {
         L.Mpad = (int)align_up_k((size_t)M, kKnnTile);
         L.a = off; off = align_up_k(off + (size_t)B * L.Npad * 16, 256);
         L.b = off; off = align_up_k(off + (size_t)B * L.Mpad * 16, 256);
-        L.c = L.d = off;
+        L.c = off; off = align_up_k(off + (size_t)B * L.Mpad * 16, 256);
+        L.d = off; off = align_up_k(off + (size_t)B * kPreMaxChunks * L.Npad * 4, 256);
+        L.e = off; off = align_up_k(off + (size_t)B * L.Npad * 4, 256);
     } else {
         L.Mpad = (int)align_up_k((size_t)M, kKncTile);
         L.a = off; off = align_up_k(off + (size_t)B * L.Npad * C * 4, 256);
@@ -539,13 +683,31 @@ extern "C" int pcd_knn_forward(const float *rows, int64_t r_sb, int64_t r_sp, in
     const int NL = (K + 31) / 32;
     if (C == 3) {
         float4 *rowq = (float4 *)(ws + L.a), *colq = (float4 *)(ws + L.b);
+        float *colpk = (float *)(ws + L.c), *cm = (float *)(ws + L.d), *thr0 = (float *)(ws + L.e);
         knn3_prep_kernel<<<pgrid, 256, 0, st>>>(rows, r_sb, r_sp, r_sc, cols, c_sb, c_sp, c_sc, B, N, M, L.Npad, L.Mpad,
-                                                norm_kind, swap_norms, rowq, colq);
+                                                norm_kind, swap_norms, rowq, colq, colpk);
         PCD_CUDA_CHECK(cudaGetLastError());
+        // pre-pass: chunk width W so that 3K <= G <= 64 chunks where possible; skipped when M is too small
+        int W = (M / (3 * K)) & ~1;
+        const int wmin = ((M + kPreMaxChunks - 1) / kPreMaxChunks + 1) & ~1;
+        if (W < wmin) W = wmin;
+        if (W < 2) W = 2;
+        const int G = (M + W - 1) / W;
+        const bool prepass = G >= K && G <= kPreMaxChunks && M >= 256 && !getenv("PCD_KNN_NO_PREPASS");
+        if (prepass) {
+            const dim3 pg(L.Npad / (128 * kPreR), B);
+            if (form == PCD_FORM_ROW_COL) knn3_chunkmin_kernel<PCD_FORM_ROW_COL><<<pg, 128, 0, st>>>(rowq, (const float4 *)colpk, L.Npad, L.Mpad, M, W, G, cm);
+            else if (form == PCD_FORM_COL_ROW) knn3_chunkmin_kernel<PCD_FORM_COL_ROW><<<pg, 128, 0, st>>>(rowq, (const float4 *)colpk, L.Npad, L.Mpad, M, W, G, cm);
+            else knn3_chunkmin_kernel<PCD_FORM_SUM_FIRST><<<pg, 128, 0, st>>>(rowq, (const float4 *)colpk, L.Npad, L.Mpad, M, W, G, cm);
+            PCD_CUDA_CHECK(cudaGetLastError());
+            knn_threshold_kernel<<<dim3(L.Npad / 128, B), 128, 0, st>>>(cm, L.Npad, G, K, thr0);
+            PCD_CUDA_CHECK(cudaGetLastError());
+        }
+        const float *thr_arg = prepass ? thr0 : nullptr;
 #define PCD_LAUNCH_KNN3(F)                                                                                        \
     do {                                                                                                          \
-        if (NL == 1) knn3_kernel<F, 1><<<grid, kKnnThreads, 0, st>>>(rowq, colq, N, M, L.Npad, L.Mpad, K, dists, idx); \
-        else knn3_kernel<F, 2><<<grid, kKnnThreads, 0, st>>>(rowq, colq, N, M, L.Npad, L.Mpad, K, dists, idx);    \
+        if (NL == 1) knn3_kernel<F, 1><<<grid, kKnnThreads, 0, st>>>(rowq, colq, thr_arg, N, M, L.Npad, L.Mpad, K, dists, idx); \
+        else knn3_kernel<F, 2><<<grid, kKnnThreads, 0, st>>>(rowq, colq, thr_arg, N, M, L.Npad, L.Mpad, K, dists, idx);    \
     } while (0)
         if (form == PCD_FORM_ROW_COL) PCD_LAUNCH_KNN3(PCD_FORM_ROW_COL);
         else if (form == PCD_FORM_COL_ROW) PCD_LAUNCH_KNN3(PCD_FORM_COL_ROW);
