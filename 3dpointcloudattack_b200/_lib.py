@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpcdist.so")
+# PCDIST_LIBRARY selects another build of the same ABI (development variants built by tools/)
+LIB_PATH = os.environ.get("PCDIST_LIBRARY") or os.path.join(_HERE, "libpcdist.so")
 
 FORM_ROW_COL, FORM_COL_ROW, FORM_SUM_FIRST = 0, 1, 2
 NORM_MULSUM, NORM_FMA = 0, 1

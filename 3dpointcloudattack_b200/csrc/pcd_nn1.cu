@@ -70,13 +70,22 @@ static Nn1Layout nn1_layout(int B, int N, int M) {
 }
 
 // ------------------------------------------------------------------------------------ prep
-// rowpk[b][i] = float4(-2x, -2y, -2z, nrow)           (AoS, one LDG.128 per query)
+// Row slots.  Lane l of a sweep warp owns the R consecutive rows i = blk*32R + l*R + r; their
+// records and keys live at slot blk*32R + r*32 + l, so that the warp's loads of the records and
+// its atomicMin flushes of the keys are coalesced (one 512-B / 256-B run per r instead of 32
+// scattered lines: the flush cost 1.8 us per row tile when it was scattered).
+__host__ __device__ __forceinline__ int row_slot(int i, int R) {
+    const int blk = i / (32 * R), w = i - blk * 32 * R;
+    return blk * 32 * R + (w % R) * 32 + w / R;
+}
+
+// rowpk[b][slot(i)] = float4(-2x, -2y, -2z, nrow)     (AoS, one LDG.128 per query)
 // colpk[b][j/2] = {x0,x1,y0,y1,z0,z1,n0,n1}           (pair records: two LDS.128 feed 2 columns
 //                                                      as ready-made fp32x2 operands)
 // Padded points are inert: coordinates 0, norm +inf  => every distance through them is +inf.
 __global__ void nn1_prep_kernel(const float *__restrict__ rows, int64_t r_sb, int64_t r_sp, int64_t r_sc,
                                 const float *__restrict__ cols, int64_t c_sb, int64_t c_sp, int64_t c_sc,
-                                int B, int N, int M, int Npad, int Mpad, int norm_kind, int swap_norms,
+                                int B, int N, int M, int Npad, int Mpad, int R, int norm_kind, int swap_norms,
                                 float4 *__restrict__ rowpk, float *__restrict__ colpk,
                                 unsigned long long *__restrict__ rowkey, unsigned long long *__restrict__ colkey,
                                 unsigned int *__restrict__ counter) {
@@ -100,7 +109,7 @@ __global__ void nn1_prep_kernel(const float *__restrict__ rows, int64_t r_sb, in
                     n = sq_norm3(norm_kind, x, y, z);
                 }
             }
-            rowpk[(size_t)b * Npad + i] = make_float4(-2.f * x, -2.f * y, -2.f * z, n);
+            rowpk[(size_t)b * Npad + row_slot(i, R)] = make_float4(-2.f * x, -2.f * y, -2.f * z, n);
             rowkey[(size_t)b * Npad + i] = ~0ull;
         } else {
             const int j = p - Npad;
@@ -138,6 +147,16 @@ struct SweepSmem {
 
 constexpr int kQuad = 4;   // columns per scheduling unit (two packed steps)
 
+#ifdef PCD_SWEEP_TRACE
+// development build only (tools/trace_sweep.py): per-CTA timestamps of the sweep
+__device__ unsigned long long *g_sweep_trace = nullptr;
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
+
 template <int FORM, int R>
 __global__ void __launch_bounds__(kSweepThreads, (R >= 16) ? 2 : ((R >= 8) ? 4 : ((R >= 4) ? 5 : 6)))
 nn1_sweep_kernel(const float4 *__restrict__ rowpk, const float4 *__restrict__ colpk,
@@ -154,6 +173,15 @@ nn1_sweep_kernel(const float4 *__restrict__ rowpk, const float4 *__restrict__ co
     // Ranges may start or end inside a 32-column chunk: a row tag only says "the minimum is in
     // this chunk", and the fix-up rescans the whole chunk, so partial chunks stay exact.
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef PCD_SWEEP_TRACE
+    unsigned long long *trace = g_sweep_trace;
+    if (trace && tid == 0) {
+        unsigned int smid;
+        asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        trace[blockIdx.x * 8 + 0] = globaltimer_ns();
+        trace[blockIdx.x * 8 + 3] = smid;
+    }
+#endif
     const int u0 = (int)((long long)units * blockIdx.x / gridDim.x);
     const int u1 = (int)((long long)units * (blockIdx.x + 1) / gridDim.x);
     if (u0 >= u1) return;
@@ -202,13 +230,13 @@ nn1_sweep_kernel(const float4 *__restrict__ rowpk, const float4 *__restrict__ co
         if (bq != cur_bq) {
             if (cur_bq >= 0) {
 #pragma unroll
-                for (int r = 0; r < R; ++r) atomicMin(&rowkey[row_base + r], make_key(best[r], btag[r]));
+                for (int r = 0; r < R; ++r) atomicMin(&rowkey[row_base + r * 32], make_key(best[r], btag[r]));
             }
             cur_bq = bq;
-            row_base = (size_t)b * Npad + (size_t)qt * QT + warp * QW + lane * R;
+            row_base = (size_t)b * Npad + (size_t)qt * QT + warp * QW + lane;    // slot of row r: + r*32
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const float4 q = __ldg(&rowpk[row_base + r]);
+                const float4 q = __ldg(&rowpk[row_base + r * 32]);
                 qx[r] = q.x; qy[r] = q.y; qz[r] = q.z; qn[r] = q.w;
                 best[r] = __int_as_float(0x7f800000);
                 btag[r] = 0;
@@ -216,6 +244,9 @@ nn1_sweep_kernel(const float4 *__restrict__ rowpk, const float4 *__restrict__ co
         }
 
         mbar_wait(&sm.full[buf], parity);
+#ifdef PCD_SWEEP_TRACE
+        if (trace && tid == 0 && it == 0) trace[blockIdx.x * 8 + 4] = globaltimer_ns();
+#endif
 
         const float4 *t4 = sm.tile[buf];
         uint2 *cp = sm.colpart[buf][warp];
@@ -293,8 +324,15 @@ nn1_sweep_kernel(const float4 *__restrict__ rowpk, const float4 *__restrict__ co
         }
         u += nseg;
     }
+#ifdef PCD_SWEEP_TRACE
+    if (trace && tid == 0) trace[blockIdx.x * 8 + 1] = globaltimer_ns();
+#endif
 #pragma unroll
-    for (int r = 0; r < R; ++r) atomicMin(&rowkey[row_base + r], make_key(best[r], btag[r]));
+    for (int r = 0; r < R; ++r) atomicMin(&rowkey[row_base + r * 32], make_key(best[r], btag[r]));
+#ifdef PCD_SWEEP_TRACE
+    __syncthreads();
+    if (trace && tid == 0) trace[blockIdx.x * 8 + 2] = globaltimer_ns();
+#endif
 }
 
 // --------------------------------------------------------------------- fix-up + reduction
@@ -335,10 +373,11 @@ nn1_fixup_kernel(const float4 *__restrict__ rowpk, const float4 *__restrict__ co
     float v = 0.f;
     if (live) {
         if (!is_col) {
-            const unsigned long long key = rowkey[(size_t)b * Npad + p];
+            const int slot = row_slot(p, R);
+            const unsigned long long key = rowkey[(size_t)b * Npad + slot];
             v = ordered_to_f32((uint32_t)(key >> 32));
             const int j0 = (int)(uint32_t)key * kColChunk;
-            const float4 q = __ldg(&rowpk[(size_t)b * Npad + p]);
+            const float4 q = __ldg(&rowpk[(size_t)b * Npad + slot]);
             const float4 *rec = colpk + (size_t)b * Mpad + j0;
             // lane l8 takes records l8 and l8+8 (columns 2*l8, 2*l8+1, 16+2*l8, 17+2*l8)
             const float4 a0 = __ldg(&rec[2 * l8]), c0 = __ldg(&rec[2 * l8 + 1]);
@@ -351,17 +390,18 @@ nn1_fixup_kernel(const float4 *__restrict__ rowpk, const float4 *__restrict__ co
             const unsigned long long key = colkey[(size_t)b * Mpad + p];
             v = ordered_to_f32((uint32_t)(key >> 32));
             const uint32_t tag = (uint32_t)key;
-            const int i0 = (int)(tag >> 5) * (32 * R) + (int)(tag & 31u) * R;
+            const int i0 = (int)(tag >> 5) * (32 * R) + (int)(tag & 31u) * R;   // rows i0 .. i0+R-1
+            const int s0 = (int)(tag >> 5) * (32 * R) + (int)(tag & 31u);       // their slots: s0 + r*32
             const float *rec = reinterpret_cast<const float *>(colpk) + ((size_t)b * Mpad + (p & ~1)) * 4 + (p & 1);
             const float cx = rec[0], cy = rec[2], cz = rec[4], cn = rec[6];
-            const float4 *rq = rowpk + (size_t)b * Npad + i0;
+            const float4 *rq = rowpk + (size_t)b * Npad + s0;
             // lane l8 takes rows l8 and l8+8 of the winning lane's R rows (R = 2, 4, 8 or 16)
             if (l8 + 8 < R) {
-                const float4 q = __ldg(&rq[l8 + 8]);
+                const float4 q = __ldg(&rq[(l8 + 8) * 32]);
                 if (pair_dist_scalar<FORM>(q.x, q.y, q.z, q.w, cx, cy, cz, cn) == v) arg = i0 + l8 + 8;
             }
             if (l8 < R) {
-                const float4 q = __ldg(&rq[l8]);
+                const float4 q = __ldg(&rq[l8 * 32]);
                 if (pair_dist_scalar<FORM>(q.x, q.y, q.z, q.w, cx, cy, cz, cn) == v) arg = i0 + l8;
             }
         }
@@ -607,6 +647,14 @@ extern "C" int pcd_nn1_set_sweep_events(void *start_event, void *stop_event) {
     return PCD_OK;
 }
 
+#ifdef PCD_SWEEP_TRACE
+extern "C" int pcd_debug_set_sweep_trace(void *buf) {
+    unsigned long long *p = (unsigned long long *)buf;
+    PCD_CUDA_CHECK(cudaMemcpyToSymbol(g_sweep_trace, &p, sizeof(p)));
+    return PCD_OK;
+}
+#endif
+
 extern "C" size_t pcd_nn1_workspace_bytes(int B, int N, int M) {
     if (B <= 0 || N <= 0 || M <= 0) return 0;
     return nn1_layout(B, N, M).total;
@@ -660,7 +708,7 @@ extern "C" int pcd_nn1_forward(const float *rows, int64_t r_sb, int64_t r_sp, in
         const long long total = (long long)B * (L.Npad + L.Mpad);
         const int grid = (int)((total + 255) / 256 < (long long)sms * 8 ? (total + 255) / 256 : (long long)sms * 8);
         nn1_prep_kernel<<<grid, 256, 0, st>>>(rows, r_sb, r_sp, r_sc, cols, c_sb, c_sp, c_sc, B, N, M, L.Npad,
-                                              L.Mpad, norm_kind, swap_norms, rowpk, colpk, rowkey, colkey, counter);
+                                              L.Mpad, R, norm_kind, swap_norms, rowpk, colpk, rowkey, colkey, counter);
         PCD_CUDA_CHECK(cudaGetLastError());
     }
     {
