@@ -44,7 +44,8 @@ __device__ __forceinline__ unsigned long long warp_sort32(unsigned long long key
             const unsigned long long o = shfl_xor_u64(key, j);
             const bool up = (lane & k) == 0 || k == 32;
             const bool lower = (lane & j) == 0;
-            key = (lower == up) ? umin64(key, o) : umax64(key, o);
+            // keep the smaller key iff (lower == up): one 64-bit compare (swapping equal keys is harmless)
+            key = ((o < key) == (lower == up)) ? o : key;
         }
     }
     return key;
@@ -54,7 +55,7 @@ __device__ __forceinline__ unsigned long long warp_bitonic_merge32(unsigned long
 #pragma unroll
     for (int j = 16; j > 0; j >>= 1) {
         const unsigned long long o = shfl_xor_u64(key, j);
-        key = ((lane & j) == 0) ? umin64(key, o) : umax64(key, o);
+        key = ((o < key) == ((lane & j) == 0)) ? o : key;
     }
     return key;
 }
@@ -77,57 +78,73 @@ __device__ __forceinline__ float key_threshold(unsigned long long kth) {
 }
 
 // Per-row select state shared by the xyz and the feature kernels.
+//
+// The heavy part -- sort the 32 staged keys, merge them into the row's sorted lists, carry the
+// overflow, tighten the threshold -- is ONE out-of-line function per NL.  Inlined into every
+// unrolled offer() it made the select kernels 9.5 K SASS instructions long and the instruction
+// cache their bottleneck (ncu: stall_no_instruction 7.1 per issue on knnc_kernel).
 template <int NL>
-struct RowSelect {
+struct SelState {
     unsigned long long L[NL];
     float thr;
+};
+
+template <int NL>
+__device__ __noinline__ SelState<NL> merge_staged(SelState<NL> s, unsigned long long *buf, int cnt, int lane, int K) {
+    // cnt >= 32: buf[0..31] is merged, buf[32..cnt-1] carried to the front; cnt < 32 (final
+    // flush): buf[0..cnt-1] is merged
+    __syncwarp();
+    const unsigned long long run = warp_sort32((cnt >= 32 || lane < cnt) ? buf[lane] : kEmptyKey, lane);
+    merge_run<NL>(s.L, run, lane);
+    const int rem = cnt - 32;
+    const unsigned long long carry = (lane < rem) ? buf[32 + lane] : kEmptyKey;
+    __syncwarp();
+    if (lane < rem) buf[lane] = carry;
+    unsigned long long kl = s.L[0];
+#pragma unroll
+    for (int l = 1; l < NL; ++l)
+        if (((K - 1) >> 5) == l) kl = s.L[l];
+    s.thr = fminf(s.thr, key_threshold(shfl_u64(kl, (K - 1) & 31)));   // only ever tightens (thr may start below +inf)
+    __syncwarp();
+    return s;
+}
+
+template <int NL>
+struct RowSelect {
+    SelState<NL> st;
     int cnt;
     __device__ __forceinline__ void init() {
 #pragma unroll
-        for (int l = 0; l < NL; ++l) L[l] = kEmptyKey;
-        thr = __int_as_float(0x7f800000);
+        for (int l = 0; l < NL; ++l) st.L[l] = kEmptyKey;
+        st.thr = __int_as_float(0x7f800000);
         cnt = 0;
     }
     // stage the passing lanes of one 32-candidate step; merge when 32 are staged
+    // (buf holds 63 keys: at most 31 waiting + 32 new)
     __device__ __forceinline__ void offer(float d, int j, unsigned long long *buf, int lane, int K) {
-        const bool pass = d < thr;
+        const bool pass = d < st.thr;
         const unsigned mask = __ballot_sync(0xffffffffu, pass);
         if (mask == 0) return;
         if (pass) buf[cnt + __popc(mask & ((1u << lane) - 1u))] = make_key(d, (uint32_t)j);
         cnt += __popc(mask);
         if (cnt >= 32) {
-            __syncwarp();
-            const unsigned long long run = warp_sort32(buf[lane], lane);
-            merge_run<NL>(L, run, lane);
-            const int rem = cnt - 32;
-            const unsigned long long carry = (lane < rem) ? buf[32 + lane] : kEmptyKey;
-            __syncwarp();
-            if (lane < rem) buf[lane] = carry;
-            cnt = rem;
-            unsigned long long kl = L[0];
-#pragma unroll
-            for (int l = 1; l < NL; ++l)
-                if (((K - 1) >> 5) == l) kl = L[l];
-            thr = fminf(thr, key_threshold(shfl_u64(kl, (K - 1) & 31)));   // only ever tightens (thr may start below +inf)
-            __syncwarp();
+            st = merge_staged<NL>(st, buf, cnt, lane, K);
+            cnt -= 32;
         }
     }
-    __device__ __forceinline__ void finish(unsigned long long *buf, int lane) {
-        __syncwarp();
+    __device__ __forceinline__ void finish(unsigned long long *buf, int lane, int K) {
         if (cnt > 0) {
-            const unsigned long long run = warp_sort32(lane < cnt ? buf[lane] : kEmptyKey, lane);
-            merge_run<NL>(L, run, lane);
+            st = merge_staged<NL>(st, buf, cnt, lane, K);
             cnt = 0;
         }
-        __syncwarp();
     }
     __device__ __forceinline__ void store(float *dists, int32_t *idx, size_t base, int lane, int K) const {
 #pragma unroll
         for (int l = 0; l < NL; ++l) {
             const int k = l * 32 + lane;
             if (k < K) {
-                if (dists) dists[base + k] = ordered_to_f32((uint32_t)(L[l] >> 32));
-                idx[base + k] = (int32_t)(uint32_t)L[l];
+                if (dists) dists[base + k] = ordered_to_f32((uint32_t)(st.L[l] >> 32));
+                idx[base + k] = (int32_t)(uint32_t)st.L[l];
             }
         }
     }
@@ -343,7 +360,7 @@ knn3_kernel(const float4 *__restrict__ rowq, const float4 *__restrict__ colq, co
     for (int r = 0; r < kKnnRQ; ++r) {
         q[r] = __ldg(&rowq[(size_t)b * Npad + row0 + r]);   // rows are padded to a multiple of 32 per CTA
         sel[r].init();
-        if (thr0) sel[r].thr = __ldg(&thr0[(size_t)b * Npad + row0 + r]);
+        if (thr0) sel[r].st.thr = __ldg(&thr0[(size_t)b * Npad + row0 + r]);
     }
 
     for (int t = 0; t < ntiles; ++t) {
@@ -369,20 +386,25 @@ knn3_kernel(const float4 *__restrict__ rowq, const float4 *__restrict__ colq, co
     }
 #pragma unroll
     for (int r = 0; r < kKnnRQ; ++r) {
-        sel[r].finish(sm.stage[warp][r], lane);
+        sel[r].finish(sm.stage[warp][r], lane, K);
         const int i = row0 + r;
         if (i < N) sel[r].store(dists, idx, ((size_t)b * N + i) * K, lane, K);
     }
 }
 
 // ------------------------------------------------------------- C-channel (feature) k-NN
-// Workspace: rowf[b][Npad][C] (= -2 * feature), rown[b][Npad], colT[b][C][Mpad] (channel-major so
-// that a lane reads consecutive candidates), coln[b][Mpad].
+constexpr int kFcRows = 8;                          // query rows per warp
+constexpr int kFcCtaRows = kKnnWarps * kFcRows;     // 64 query rows per CTA
+constexpr int kFcTile = 128;                        // candidates per stage (4 per lane)
+constexpr int kFcStage = 63;                        // staging keys per row (31 waiting + 32 new - 1)
+// Workspace: rowT[b][C][Npad] (= -2 * feature, channel-major), rown[b][Npad], and the candidates
+// in STAGE-major order colS[b][Mpad/128][C+1][128] -- the C channel rows of a 128-candidate
+// stage followed by its norms -- so that one 1-D TMA bulk copy fetches a whole stage.
 __global__ void knnc_prep_kernel(const float *__restrict__ rows, int64_t r_sb, int64_t r_sp, int64_t r_sc,
                                  const float *__restrict__ cols, int64_t c_sb, int64_t c_sp, int64_t c_sc,
                                  int B, int N, int M, int C, int Npad, int Mpad, int norm_kind, int swap_norms,
-                                 float *__restrict__ rowf, float *__restrict__ rown,
-                                 float *__restrict__ colT, float *__restrict__ coln) {
+                                 float *__restrict__ rowT, float *__restrict__ rown,
+                                 float *__restrict__ colS) {
     const long long per_b = (long long)Npad + Mpad;
     const long long total = per_b * B;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
@@ -411,91 +433,141 @@ __global__ void knnc_prep_kernel(const float *__restrict__ rows, int64_t r_sb, i
             }
         }
         if (is_row) {
-            for (int k = 0; k < C; ++k) rowf[((size_t)b * Npad + i) * C + k] = live ? -2.f * own[k * osc] : 0.f;
+            for (int k = 0; k < C; ++k) rowT[((size_t)b * C + k) * Npad + i] = live ? -2.f * own[k * osc] : 0.f;
             rown[(size_t)b * Npad + i] = n;
         } else {
-            for (int k = 0; k < C; ++k) colT[((size_t)b * C + k) * Mpad + i] = live ? own[k * osc] : 0.f;
-            coln[(size_t)b * Mpad + i] = n;
+            float *dst = colS + ((size_t)b * (Mpad / kFcTile) + i / kFcTile) * (size_t)(C + 1) * kFcTile + i % kFcTile;
+            for (int k = 0; k < C; ++k) dst[(size_t)k * kFcTile] = live ? own[k * osc] : 0.f;
+            dst[(size_t)C * kFcTile] = n;
         }
     }
 }
 
-constexpr int kKncTile = 64;   // candidates per step (2 per lane)
+// Register blocking: a warp owns 8 query rows, a lane 4 consecutive candidates of the 128-wide
+// stage -> 32 accumulators per lane held as 16 packed pairs; per channel 2 broadcast LDS.128
+// (8 query values) + 1 LDS.128 (4 candidates) feed 16 FFMA2 (the 4 x 2 blocking it replaces fed
+// 8 FFMA from 3 LDS and ran at 28 % of the FMA peak).  Every pair is still the sequential fp32
+// chain fmul, fma, fma, ... over the channels (packed halves round independently), then the two
+// norm additions in the order of `form`: bit-identical to the oracle.
+// Candidate stages (C channel rows of 512 B + the norms, contiguous in the workspace) arrive by
+// one 1-D TMA bulk copy each behind an mbarrier, double buffered.  A row's four candidates are
+// tested against its threshold with ONE vote per row, all eight votes issued before the first
+// branch, so the common "nothing passes" case is a short branch-free sequence.
+
+static inline size_t knnc_smem_bytes(int C) {
+    return 128 + (size_t)C * kFcCtaRows * 4 + 2 * ((size_t)C * kFcTile + kFcTile) * 4 +
+           (size_t)kFcCtaRows * kFcStage * 8;
+}
 
 template <int NL>
 __global__ void __launch_bounds__(kKnnThreads)
-knnc_kernel(const float *__restrict__ rowf, const float *__restrict__ rown, const float *__restrict__ colT,
-            const float *__restrict__ coln, int N, int M, int C, int Npad, int Mpad, int K, int form,
+knnc_kernel(const float *__restrict__ rowT, const float *__restrict__ rown, const float *__restrict__ colS,
+            int N, int M, int C, int Npad, int Mpad, int K, int form,
             float *__restrict__ dists, int32_t *__restrict__ idx) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: qs[warps][C][RQ] | ct[C][64] | cn[64] | stage[warps][RQ][64] u64
-    float *qs = reinterpret_cast<float *>(smem_raw);
-    float *ct = qs + kKnnWarps * C * kKnnRQ;
-    float *cn = ct + C * kKncTile;
-    unsigned long long *stage = reinterpret_cast<unsigned long long *>(cn + kKncTile);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // layout: full[2] | qs[C][64] | ct[2][C*128 + 128] | stage[64 rows][63] u64
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
+    float *qs = reinterpret_cast<float *>(smem_raw + 128);
+    float *ct = qs + (size_t)C * kFcCtaRows;
+    const size_t ct_stride = (size_t)C * kFcTile + kFcTile;
+    unsigned long long *stage = reinterpret_cast<unsigned long long *>(ct + 2 * ct_stride);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y;
-    const int row0 = (blockIdx.x * kKnnWarps + warp) * kKnnRQ;
+    const int cta_row0 = blockIdx.x * kFcCtaRows;
+    const int row0 = cta_row0 + warp * kFcRows;
+    const int ntiles = (M + kFcTile - 1) / kFcTile;
+    const float *cbase = colS + (size_t)b * (Mpad / kFcTile) * ct_stride;
+    const uint32_t stage_bytes = (uint32_t)ct_stride * 4u;
 
-    float *myq = qs + warp * C * kKnnRQ;
-    for (int e = lane; e < C * kKnnRQ; e += 32) {
-        const int k = e / kKnnRQ, r = e - k * kKnnRQ;
-        myq[e] = rowf[((size_t)b * Npad + row0 + r) * C + k];
+    auto issue = [&](int t) {                    // one thread
+        const int buf = t & 1;
+        mbar_expect_tx(&full[buf], stage_bytes);
+        tma_load_1d(ct + buf * ct_stride, cbase + (size_t)t * ct_stride, stage_bytes, &full[buf]);
+    };
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        fence_mbar_init();
+        fence_proxy_async();
     }
-    float qn[kKnnRQ];
-    RowSelect<NL> sel[kKnnRQ];
+    __syncthreads();
+    if (tid == 0) {
+        issue(0);
+        if (ntiles > 1) issue(1);
+    }
+    // the CTA's query rows, channel-major: qs[k][r]
+    for (int e = tid; e < C * kFcCtaRows; e += kKnnThreads) {
+        const int k = e / kFcCtaRows, r = e - k * kFcCtaRows;
+        qs[e] = rowT[((size_t)b * C + k) * Npad + cta_row0 + r];
+    }
+    float qn[kFcRows];
+    RowSelect<NL> sel[kFcRows];
 #pragma unroll
-    for (int r = 0; r < kKnnRQ; ++r) {
+    for (int r = 0; r < kFcRows; ++r) {
         qn[r] = rown[(size_t)b * Npad + row0 + r];
         sel[r].init();
     }
-    unsigned long long *mystage = stage + (size_t)warp * kKnnRQ * 64;
+    unsigned long long *mystage = stage + (size_t)warp * kFcRows * kFcStage;
+    __syncthreads();
 
-    const float *cbase = colT + (size_t)b * C * Mpad;
-    for (int j0 = 0; j0 < M; j0 += kKncTile) {
-        __syncthreads();
-        for (int e = tid; e < C * kKncTile; e += kKnnThreads) {
-            const int k = e / kKncTile, jj = e - k * kKncTile;
-            ct[e] = cbase[(size_t)k * Mpad + j0 + jj];
-        }
-        if (tid < kKncTile) cn[tid] = coln[(size_t)b * Mpad + j0 + tid];
-        __syncthreads();
-
-        float acc0[kKnnRQ], acc1[kKnnRQ];
+    const float4 *q4 = reinterpret_cast<const float4 *>(qs) + warp * 2;          // + k * 16
+    for (int t = 0; t < ntiles; ++t) {
+        const int buf = t & 1;
+        mbar_wait(&full[buf], (t >> 1) & 1);
+        const float *tile = ct + buf * ct_stride;
+        const float4 *c4p = reinterpret_cast<const float4 *>(tile) + lane;       // + k * 32
+        f32x2 acc[kFcRows][2];
         {
-            const float4 q4 = *reinterpret_cast<const float4 *>(myq);
-            const float c0 = ct[lane], c1 = ct[32 + lane];
-            acc0[0] = __fmul_rn(q4.x, c0); acc0[1] = __fmul_rn(q4.y, c0); acc0[2] = __fmul_rn(q4.z, c0); acc0[3] = __fmul_rn(q4.w, c0);
-            acc1[0] = __fmul_rn(q4.x, c1); acc1[1] = __fmul_rn(q4.y, c1); acc1[2] = __fmul_rn(q4.z, c1); acc1[3] = __fmul_rn(q4.w, c1);
+            const float4 qa = q4[0], qb = q4[1], c = c4p[0];
+            const f32x2 c01 = pack2(c.x, c.y), c23 = pack2(c.z, c.w);
+            const float q[kFcRows] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+            for (int r = 0; r < kFcRows; ++r) { acc[r][0] = mul2_s(q[r], c01); acc[r][1] = mul2_s(q[r], c23); }
         }
 #pragma unroll 4
         for (int k = 1; k < C; ++k) {
-            const float4 q4 = *reinterpret_cast<const float4 *>(myq + k * kKnnRQ);
-            const float c0 = ct[k * kKncTile + lane], c1 = ct[k * kKncTile + 32 + lane];
-            acc0[0] = __fmaf_rn(q4.x, c0, acc0[0]); acc0[1] = __fmaf_rn(q4.y, c0, acc0[1]);
-            acc0[2] = __fmaf_rn(q4.z, c0, acc0[2]); acc0[3] = __fmaf_rn(q4.w, c0, acc0[3]);
-            acc1[0] = __fmaf_rn(q4.x, c1, acc1[0]); acc1[1] = __fmaf_rn(q4.y, c1, acc1[1]);
-            acc1[2] = __fmaf_rn(q4.z, c1, acc1[2]); acc1[3] = __fmaf_rn(q4.w, c1, acc1[3]);
-        }
-        const float n0 = cn[lane], n1 = cn[32 + lane];
+            const float4 qa = q4[k * 16], qb = q4[k * 16 + 1], c = c4p[k * 32];
+            const f32x2 c01 = pack2(c.x, c.y), c23 = pack2(c.z, c.w);
+            const float q[kFcRows] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
 #pragma unroll
-        for (int r = 0; r < kKnnRQ; ++r) {
-            float d0, d1;
+            for (int r = 0; r < kFcRows; ++r) { acc[r][0] = fma2_s(q[r], c01, acc[r][0]); acc[r][1] = fma2_s(q[r], c23, acc[r][1]); }
+        }
+        const float4 n4 = reinterpret_cast<const float4 *>(tile + (size_t)C * kFcTile)[lane];
+        const f32x2 n01 = pack2(n4.x, n4.y), n23 = pack2(n4.z, n4.w);
+        const int j = t * kFcTile + lane * 4;
+        float d[kFcRows][4];
+        unsigned hit[kFcRows];
+#pragma unroll
+        for (int r = 0; r < kFcRows; ++r) {
+            f32x2 d01, d23;
             if (form == PCD_FORM_ROW_COL) {
-                d0 = __fadd_rn(__fadd_rn(acc0[r], qn[r]), n0); d1 = __fadd_rn(__fadd_rn(acc1[r], qn[r]), n1);
+                d01 = add2(add2_s(qn[r], acc[r][0]), n01); d23 = add2(add2_s(qn[r], acc[r][1]), n23);
             } else if (form == PCD_FORM_COL_ROW) {
-                d0 = __fadd_rn(__fadd_rn(acc0[r], n0), qn[r]); d1 = __fadd_rn(__fadd_rn(acc1[r], n1), qn[r]);
+                d01 = add2_s(qn[r], add2(acc[r][0], n01)); d23 = add2_s(qn[r], add2(acc[r][1], n23));
             } else {
-                d0 = __fadd_rn(__fadd_rn(qn[r], n0), acc0[r]); d1 = __fadd_rn(__fadd_rn(qn[r], n1), acc1[r]);
+                d01 = add2(add2_s(qn[r], n01), acc[r][0]); d23 = add2(add2_s(qn[r], n23), acc[r][1]);
             }
-            sel[r].offer(d0, j0 + lane, mystage + r * 64, lane, K);
-            sel[r].offer(d1, j0 + 32 + lane, mystage + r * 64, lane, K);
+            unpack2(d01, d[r][0], d[r][1]); unpack2(d23, d[r][2], d[r][3]);
+            const float thr = sel[r].st.thr;
+            hit[r] = __ballot_sync(0xffffffffu, (d[r][0] < thr) | (d[r][1] < thr) | (d[r][2] < thr) | (d[r][3] < thr));
+        }
+#pragma unroll
+        for (int r = 0; r < kFcRows; ++r) {
+            if (hit[r]) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) sel[r].offer(d[r][e], j + e, mystage + r * kFcStage, lane, K);
+            }
+        }
+        __syncthreads();                         // stage buf fully read
+        if (tid == 0 && t + 2 < ntiles) {
+            fence_proxy_async();
+            issue(t + 2);
         }
     }
 #pragma unroll
-    for (int r = 0; r < kKnnRQ; ++r) {
-        sel[r].finish(mystage + r * 64, lane);
+    for (int r = 0; r < kFcRows; ++r) {
+        sel[r].finish(mystage + r * kFcStage, lane, K);
         const int i = row0 + r;
         if (i < N) sel[r].store(dists, idx, ((size_t)b * N + i) * K, lane, K);
     }
@@ -612,11 +684,11 @@ ball_query_kernel(const float *__restrict__ xyz, int64_t x_sb, int64_t x_sp, int
 
 struct KnnLayout {
     int Npad, Mpad;
-    size_t a, b, c, d, e, total;   // xyz: a=rowq b=colq c=colpk d=cm e=thr0 ; features: a=rowf b=rown c=colT d=coln
+    size_t a, b, c, d, e, total;   // xyz: a=rowq b=colq c=colpk d=cm e=thr0 ; features: a=rowT b=rown c=colS
 };
 static KnnLayout knn_layout(int B, int N, int M, int C) {
     KnnLayout L;
-    L.Npad = (int)align_up_k((size_t)N, C == 3 ? 128 * kPreR : kKnnWarps * kKnnRQ);
+    L.Npad = (int)align_up_k((size_t)N, C == 3 ? 128 * kPreR : kFcCtaRows);
     size_t off = 0;
     L.e = 0;
     if (C == 3) {
@@ -627,11 +699,11 @@ static KnnLayout knn_layout(int B, int N, int M, int C) {
         L.d = off; off = align_up_k(off + (size_t)B * kPreMaxChunks * L.Npad * 4, 256);
         L.e = off; off = align_up_k(off + (size_t)B * L.Npad * 4, 256);
     } else {
-        L.Mpad = (int)align_up_k((size_t)M, kKncTile);
+        L.Mpad = (int)align_up_k((size_t)M, kFcTile);
         L.a = off; off = align_up_k(off + (size_t)B * L.Npad * C * 4, 256);
         L.b = off; off = align_up_k(off + (size_t)B * L.Npad * 4, 256);
-        L.c = off; off = align_up_k(off + (size_t)B * L.Mpad * C * 4, 256);
-        L.d = off; off = align_up_k(off + (size_t)B * L.Mpad * 4, 256);
+        L.c = off; off = align_up_k(off + (size_t)B * L.Mpad * (C + 1) * 4, 256);
+        L.d = off;
     }
     L.total = off;
     return L;
@@ -716,18 +788,18 @@ extern "C" int pcd_knn_forward(const float *rows, int64_t r_sb, int64_t r_sp, in
         PCD_CUDA_CHECK(cudaGetLastError());
     } else {
         float *rowf = (float *)(ws + L.a), *rown = (float *)(ws + L.b);
-        float *colT = (float *)(ws + L.c), *coln = (float *)(ws + L.d);
+        float *colS = (float *)(ws + L.c);
         knnc_prep_kernel<<<pgrid, 256, 0, st>>>(rows, r_sb, r_sp, r_sc, cols, c_sb, c_sp, c_sc, B, N, M, C, L.Npad,
-                                                L.Mpad, norm_kind, swap_norms, rowf, rown, colT, coln);
+                                                L.Mpad, norm_kind, swap_norms, rowf, rown, colS);
         PCD_CUDA_CHECK(cudaGetLastError());
-        const size_t smem = (size_t)kKnnWarps * C * kKnnRQ * 4 + (size_t)C * kKncTile * 4 + kKncTile * 4 +
-                            (size_t)kKnnWarps * kKnnRQ * 64 * 8;
+        const size_t smem = knnc_smem_bytes(C);
+        const dim3 fgrid(L.Npad / kFcCtaRows, B);
         if (NL == 1) {
             PCD_CUDA_CHECK(cudaFuncSetAttribute(knnc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            knnc_kernel<1><<<grid, kKnnThreads, smem, st>>>(rowf, rown, colT, coln, N, M, C, L.Npad, L.Mpad, K, form, dists, idx);
+            knnc_kernel<1><<<fgrid, kKnnThreads, smem, st>>>(rowf, rown, colS, N, M, C, L.Npad, L.Mpad, K, form, dists, idx);
         } else {
             PCD_CUDA_CHECK(cudaFuncSetAttribute(knnc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            knnc_kernel<2><<<grid, kKnnThreads, smem, st>>>(rowf, rown, colT, coln, N, M, C, L.Npad, L.Mpad, K, form, dists, idx);
+            knnc_kernel<2><<<fgrid, kKnnThreads, smem, st>>>(rowf, rown, colS, N, M, C, L.Npad, L.Mpad, K, form, dists, idx);
         }
         PCD_CUDA_CHECK(cudaGetLastError());
     }

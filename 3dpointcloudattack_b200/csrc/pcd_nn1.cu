@@ -49,7 +49,7 @@ constexpr int kMaxFixBlocks = 4096;
 
 struct Nn1Layout {
     int Npad, Mpad, nblk_r, nblk_c;
-    size_t rowpk, colpk, rowkey, colkey, partial, counter, total;
+    size_t rowpk, rowpp, colpk, rowkey, colkey, partial, counter, total;
 };
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static Nn1Layout nn1_layout(int B, int N, int M) {
@@ -60,6 +60,7 @@ static Nn1Layout nn1_layout(int B, int N, int M) {
     L.nblk_c = (M + kFixThreads - 1) / kFixThreads;
     size_t off = 0;
     L.rowpk = off; off = align_up(off + (size_t)B * L.Npad * 16, 256);
+    L.rowpp = off; off = align_up(off + (size_t)B * L.Npad * 16, 256);   // the same records in sweep (slot) order
     L.colpk = off; off = align_up(off + (size_t)B * L.Mpad * 16 + 64, 256);   // +64: the sweep prefetches one record past a tile
     L.rowkey = off; off = align_up(off + (size_t)B * L.Npad * 8, 256);
     L.colkey = off; off = align_up(off + (size_t)B * L.Mpad * 8, 256);
@@ -70,23 +71,24 @@ static Nn1Layout nn1_layout(int B, int N, int M) {
 }
 
 // ------------------------------------------------------------------------------------ prep
-// Row slots.  Lane l of a sweep warp owns the R consecutive rows i = blk*32R + l*R + r; their
-// records and keys live at slot blk*32R + r*32 + l, so that the warp's loads of the records and
-// its atomicMin flushes of the keys are coalesced (one 512-B / 256-B run per r instead of 32
-// scattered lines: the flush cost 1.8 us per row tile when it was scattered).
+// Row key slots.  Lane l of a sweep warp owns the R consecutive rows i = blk*32R + l*R + r; the
+// key of row i lives at slot blk*32R + r*32 + l, so that the warp's atomicMin flushes are
+// coalesced (one 256-B run per r instead of 32 scattered lines: the scattered flush cost 1.8 us
+// per row tile, 8 us of 131 at BASELINE config 2).  The records exist twice: rowpp in slot order
+// for the sweep's coalesced loads (another 4 us), rowpk in row order for the fix-up.
 __host__ __device__ __forceinline__ int row_slot(int i, int R) {
     const int blk = i / (32 * R), w = i - blk * 32 * R;
     return blk * 32 * R + (w % R) * 32 + w / R;
 }
 
-// rowpk[b][slot(i)] = float4(-2x, -2y, -2z, nrow)     (AoS, one LDG.128 per query)
+// rowpk[b][i] = float4(-2x, -2y, -2z, nrow)           (AoS, one LDG.128 per query)
 // colpk[b][j/2] = {x0,x1,y0,y1,z0,z1,n0,n1}           (pair records: two LDS.128 feed 2 columns
 //                                                      as ready-made fp32x2 operands)
 // Padded points are inert: coordinates 0, norm +inf  => every distance through them is +inf.
 __global__ void nn1_prep_kernel(const float *__restrict__ rows, int64_t r_sb, int64_t r_sp, int64_t r_sc,
                                 const float *__restrict__ cols, int64_t c_sb, int64_t c_sp, int64_t c_sc,
                                 int B, int N, int M, int Npad, int Mpad, int R, int norm_kind, int swap_norms,
-                                float4 *__restrict__ rowpk, float *__restrict__ colpk,
+                                float4 *__restrict__ rowpk, float4 *__restrict__ rowpp, float *__restrict__ colpk,
                                 unsigned long long *__restrict__ rowkey, unsigned long long *__restrict__ colkey,
                                 unsigned int *__restrict__ counter) {
     const long long per_b = (long long)Npad + Mpad;
@@ -109,7 +111,9 @@ __global__ void nn1_prep_kernel(const float *__restrict__ rows, int64_t r_sb, in
                     n = sq_norm3(norm_kind, x, y, z);
                 }
             }
-            rowpk[(size_t)b * Npad + row_slot(i, R)] = make_float4(-2.f * x, -2.f * y, -2.f * z, n);
+            const float4 rec = make_float4(-2.f * x, -2.f * y, -2.f * z, n);
+            rowpk[(size_t)b * Npad + i] = rec;
+            rowpp[(size_t)b * Npad + row_slot(i, R)] = rec;
             rowkey[(size_t)b * Npad + i] = ~0ull;
         } else {
             const int j = p - Npad;
@@ -159,7 +163,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 
 template <int FORM, int R>
 __global__ void __launch_bounds__(kSweepThreads, (R >= 16) ? 2 : ((R >= 8) ? 4 : ((R >= 4) ? 5 : 6)))
-nn1_sweep_kernel(const float4 *__restrict__ rowpk, const float4 *__restrict__ colpk,
+nn1_sweep_kernel(const float4 *__restrict__ rowpp /* slot order */, const float4 *__restrict__ colpk,
                  unsigned long long *__restrict__ rowkey, unsigned long long *__restrict__ colkey,
                  int Npad, int Mpad, int qpt /* quads per TMA tile */, int nqt, int nq /* quads per row tile */,
                  int units) {
@@ -233,10 +237,10 @@ nn1_sweep_kernel(const float4 *__restrict__ rowpk, const float4 *__restrict__ co
                 for (int r = 0; r < R; ++r) atomicMin(&rowkey[row_base + r * 32], make_key(best[r], btag[r]));
             }
             cur_bq = bq;
-            row_base = (size_t)b * Npad + (size_t)qt * QT + warp * QW + lane;    // slot of row r: + r*32
+            row_base = (size_t)b * Npad + (size_t)qt * QT + warp * QW + lane;    // key slot of row r: + r*32
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const float4 q = __ldg(&rowpk[row_base + r * 32]);
+                const float4 q = __ldg(&rowpp[row_base + r * 32]);
                 qx[r] = q.x; qy[r] = q.y; qz[r] = q.z; qn[r] = q.w;
                 best[r] = __int_as_float(0x7f800000);
                 btag[r] = 0;
@@ -373,11 +377,10 @@ nn1_fixup_kernel(const float4 *__restrict__ rowpk, const float4 *__restrict__ co
     float v = 0.f;
     if (live) {
         if (!is_col) {
-            const int slot = row_slot(p, R);
-            const unsigned long long key = rowkey[(size_t)b * Npad + slot];
+            const unsigned long long key = rowkey[(size_t)b * Npad + row_slot(p, R)];
             v = ordered_to_f32((uint32_t)(key >> 32));
             const int j0 = (int)(uint32_t)key * kColChunk;
-            const float4 q = __ldg(&rowpk[(size_t)b * Npad + slot]);
+            const float4 q = __ldg(&rowpk[(size_t)b * Npad + p]);
             const float4 *rec = colpk + (size_t)b * Mpad + j0;
             // lane l8 takes records l8 and l8+8 (columns 2*l8, 2*l8+1, 16+2*l8, 17+2*l8)
             const float4 a0 = __ldg(&rec[2 * l8]), c0 = __ldg(&rec[2 * l8 + 1]);
@@ -390,18 +393,17 @@ nn1_fixup_kernel(const float4 *__restrict__ rowpk, const float4 *__restrict__ co
             const unsigned long long key = colkey[(size_t)b * Mpad + p];
             v = ordered_to_f32((uint32_t)(key >> 32));
             const uint32_t tag = (uint32_t)key;
-            const int i0 = (int)(tag >> 5) * (32 * R) + (int)(tag & 31u) * R;   // rows i0 .. i0+R-1
-            const int s0 = (int)(tag >> 5) * (32 * R) + (int)(tag & 31u);       // their slots: s0 + r*32
+            const int i0 = (int)(tag >> 5) * (32 * R) + (int)(tag & 31u) * R;
             const float *rec = reinterpret_cast<const float *>(colpk) + ((size_t)b * Mpad + (p & ~1)) * 4 + (p & 1);
             const float cx = rec[0], cy = rec[2], cz = rec[4], cn = rec[6];
-            const float4 *rq = rowpk + (size_t)b * Npad + s0;
+            const float4 *rq = rowpk + (size_t)b * Npad + i0;
             // lane l8 takes rows l8 and l8+8 of the winning lane's R rows (R = 2, 4, 8 or 16)
             if (l8 + 8 < R) {
-                const float4 q = __ldg(&rq[(l8 + 8) * 32]);
+                const float4 q = __ldg(&rq[l8 + 8]);
                 if (pair_dist_scalar<FORM>(q.x, q.y, q.z, q.w, cx, cy, cz, cn) == v) arg = i0 + l8 + 8;
             }
             if (l8 < R) {
-                const float4 q = __ldg(&rq[l8 * 32]);
+                const float4 q = __ldg(&rq[l8]);
                 if (pair_dist_scalar<FORM>(q.x, q.y, q.z, q.w, cx, cy, cz, cn) == v) arg = i0 + l8;
             }
         }
@@ -695,6 +697,7 @@ extern "C" int pcd_nn1_forward(const float *rows, int64_t r_sb, int64_t r_sp, in
     cudaStream_t st = (cudaStream_t)stream;
     char *ws = (char *)workspace;
     float4 *rowpk = (float4 *)(ws + L.rowpk);
+    float4 *rowpp = (float4 *)(ws + L.rowpp);
     float *colpk = (float *)(ws + L.colpk);
     unsigned long long *rowkey = (unsigned long long *)(ws + L.rowkey);
     unsigned long long *colkey = (unsigned long long *)(ws + L.colkey);
@@ -708,18 +711,18 @@ extern "C" int pcd_nn1_forward(const float *rows, int64_t r_sb, int64_t r_sp, in
         const long long total = (long long)B * (L.Npad + L.Mpad);
         const int grid = (int)((total + 255) / 256 < (long long)sms * 8 ? (total + 255) / 256 : (long long)sms * 8);
         nn1_prep_kernel<<<grid, 256, 0, st>>>(rows, r_sb, r_sp, r_sc, cols, c_sb, c_sp, c_sc, B, N, M, L.Npad,
-                                              L.Mpad, R, norm_kind, swap_norms, rowpk, colpk, rowkey, colkey, counter);
+                                              L.Mpad, R, norm_kind, swap_norms, rowpk, rowpp, colpk, rowkey, colkey, counter);
         PCD_CUDA_CHECK(cudaGetLastError());
     }
     {
         cudaError_t e;
         if (g_sweep_ev0) PCD_CUDA_CHECK(cudaEventRecord(g_sweep_ev0, st));
         if (form == PCD_FORM_ROW_COL)
-            e = launch_sweep_r<PCD_FORM_ROW_COL>(R, rowpk, (const float4 *)colpk, rowkey, colkey, B, N, M, L.Npad, L.Mpad, mt, sms, st);
+            e = launch_sweep_r<PCD_FORM_ROW_COL>(R, rowpp, (const float4 *)colpk, rowkey, colkey, B, N, M, L.Npad, L.Mpad, mt, sms, st);
         else if (form == PCD_FORM_COL_ROW)
-            e = launch_sweep_r<PCD_FORM_COL_ROW>(R, rowpk, (const float4 *)colpk, rowkey, colkey, B, N, M, L.Npad, L.Mpad, mt, sms, st);
+            e = launch_sweep_r<PCD_FORM_COL_ROW>(R, rowpp, (const float4 *)colpk, rowkey, colkey, B, N, M, L.Npad, L.Mpad, mt, sms, st);
         else
-            e = launch_sweep_r<PCD_FORM_SUM_FIRST>(R, rowpk, (const float4 *)colpk, rowkey, colkey, B, N, M, L.Npad, L.Mpad, mt, sms, st);
+            e = launch_sweep_r<PCD_FORM_SUM_FIRST>(R, rowpp, (const float4 *)colpk, rowkey, colkey, B, N, M, L.Npad, L.Mpad, mt, sms, st);
         PCD_CUDA_CHECK(e);
         if (g_sweep_ev1) PCD_CUDA_CHECK(cudaEventRecord(g_sweep_ev1, st));
     }

@@ -29,8 +29,28 @@ def ref_knn(x, k):          # model/dgcnn.py:194-200 formulation
     return (-xx - inner - xx.transpose(2, 1)).topk(k=k, dim=-1)[1]
 
 
+def breakdown():
+    """per-kernel device time of our k-NN path (torch profiler)"""
+    from torch.profiler import profile, ProfilerActivity
+    for (B, N, C, K) in [(128, 2048, 3, 20), (64, 1024, 3, 17), (128, 2048, 64, 20)]:
+        x = torch.randn(B, C, N, device="cuda")
+        pts = x.transpose(1, 2)
+        for _ in range(3):
+            F.knn(pts, pts, K)
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(5):
+                F.knn(pts, pts, K)
+            torch.cuda.synchronize()
+        print(f"--- B={B} N={N} C={C} K={K}")
+        for e in sorted(prof.key_averages(), key=lambda e: -e.device_time_total)[:6]:
+            print(f"   {e.device_time_total / e.count:9.1f} us x{e.count:3d}  {e.key[:90]}")
+
+
 def main():
     torch.backends.cuda.matmul.allow_tf32 = False
+    if "--breakdown" in sys.argv:
+        return breakdown()
     for (B, N, C, K) in [(64, 1024, 3, 17), (128, 2048, 3, 20), (128, 2048, 64, 20), (128, 2048, 128, 20), (32, 4096, 3, 17)]:
         x = torch.randn(B, C, N, device="cuda")
         pts = x.transpose(1, 2)
