@@ -14,6 +14,7 @@ FORM_ROW_COL, FORM_COL_ROW, FORM_SUM_FIRST = 0, 1, 2
 NORM_MULSUM, NORM_FMA = 0, 1
 VALUE_SQUARED, VALUE_SQRT_CLAMP = 0, 1
 KNN_MAX_K, KNN_MAX_C = 64, 128
+EDGE_CENTER, EDGE_NEIGHBOR, EDGE_DIFF = 0, 1, 2
 
 _c = ctypes
 _P, _I, _L, _F, _Z = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float, _c.c_size_t
@@ -31,6 +32,9 @@ SIGNATURES = {
     "pcd_knn_forward": (_I, _CLOUD + _CLOUD + [_I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),
     "pcd_knn_backward": (_I, _CLOUD + _CLOUD + [_I, _I, _I, _I, _I, _P, _P] + _CLOUD + _CLOUD + [_P]),
     "pcd_ball_query": (_I, _CLOUD + _CLOUD + [_I, _I, _I, _F, _I, _P, _P]),
+    "pcd_edge_feature_forward": (_I, [_P, _P, _I, _I, _I, _I, _I, _c.POINTER(_I), _P, _P]),
+    "pcd_edge_feature_backward": (_I, [_P, _P, _I, _I, _I, _I, _I, _c.POINTER(_I), _P, _P]),
+    "pcd_fps": (_I, [_P, _L, _L, _L, _I, _I, _I, _P, _P, _P]),
     "pcd_measure_fp32_peak": (_I, [_I, _c.POINTER(_c.c_double), _P]),
 }
 

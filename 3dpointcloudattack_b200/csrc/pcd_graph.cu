@@ -1,0 +1,326 @@
+// pcd_graph.cu -- the callers either side of the k-NN path:
+//
+//   * edge features of a k-NN graph: DGCNN get_graph_feature (model/dgcnn.py:203-227) and
+//     CurveNet LPFA.group_feature (model/curvenet_util.py:206-236) -- a gather through idx fused
+//     with the centre subtraction / concatenation / permute(0,3,1,2), and its scatter-add backward;
+//   * farthest point sampling (model/pointnet2_utils.py:59-81, model/curvenet_util.py:69-90):
+//     the reference's Python loop of `npoint` iterations x 6 kernel launches as ONE persistent
+//     CTA per sample with the points and their running distances in registers.
+//
+// Both are HBM / latency bound byte movers: no tensor cores, no tiles of math.
+#include "pcd_common.cuh"
+
+namespace pcd {
+
+// ------------------------------------------------------------------------- edge features
+// out[b, q*C + c, n, j] = op_q( x[b,c,n] (centre), x[b,c,idx[b,n,j]] (neighbour) ),  q < nblocks
+//   CENTER   -> centre            NEIGHBOR -> neighbour            DIFF -> neighbour - centre
+// ops are packed two bits per block.  One thread owns VEC consecutive (n,j) slots (the same n
+// when VEC = 4 divides k) and walks a group of CG channels with the indices in registers; the
+// x rows of the group (N floats each) are re-read through L1, the output -- the only large
+// stream: B * nblocks*C * N*k floats, 5.4 GB for DGCNN's last layer at BASELINE config 4 -- is
+// written once with streaming stores.
+constexpr int kEdgeThreads = 256;
+
+__device__ __forceinline__ float edge_value(int op, float ctr, float nb) {
+    return op == PCD_EDGE_CENTER ? ctr : (op == PCD_EDGE_NEIGHBOR ? nb : __fadd_rn(nb, -ctr));
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kEdgeThreads)
+edge_feature_fwd_kernel(const float *__restrict__ x, const int32_t *__restrict__ idx, int C, int N, int k, int nblocks,
+                        int ops, int CG, float *__restrict__ out) {
+    const long long NK = (long long)N * k;
+    const long long e0 = ((long long)blockIdx.x * kEdgeThreads + threadIdx.x) * VEC;
+    if (e0 >= NK) return;
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * CG;
+    const int c1 = c0 + CG < C ? c0 + CG : C;
+    int m[VEC], n[VEC];
+    if (VEC == 4) {
+        const int4 v = *reinterpret_cast<const int4 *>(idx + (size_t)b * NK + e0);
+        m[0] = v.x; m[1 % VEC] = v.y; m[2 % VEC] = v.z; m[3 % VEC] = v.w;
+        const int nn = (int)(e0 / k);                       // k % 4 == 0: the four slots share n
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) n[i] = nn;
+    } else {
+        m[0] = idx[(size_t)b * NK + e0];
+        n[0] = (int)(e0 / k);
+    }
+    for (int c = c0; c < c1; ++c) {
+        const float *xr = x + ((size_t)b * C + c) * N;
+        float ctr[VEC], nb[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) { ctr[i] = __ldg(xr + n[i]); nb[i] = __ldg(xr + m[i]); }
+        for (int q = 0; q < nblocks; ++q) {
+            const int op = (ops >> (2 * q)) & 3;
+            float *dst = out + (((size_t)b * nblocks + q) * C + c) * NK + e0;
+            if (VEC == 4) {
+                __stcs(reinterpret_cast<float4 *>(dst),
+                       make_float4(edge_value(op, ctr[0], nb[0]), edge_value(op, ctr[1 % VEC], nb[1 % VEC]),
+                                   edge_value(op, ctr[2 % VEC], nb[2 % VEC]), edge_value(op, ctr[3 % VEC], nb[3 % VEC])));
+            } else {
+                __stcs(dst, edge_value(op, ctr[0], nb[0]));
+            }
+        }
+    }
+}
+
+// Backward: gx[b,c,n] = sum_j s_ctr(n,j) + sum_{(n',j): idx[b,n',j] = n} s_nbr(n',j) with
+//   s_nbr = sum of g over NEIGHBOR and DIFF blocks,  s_ctr = sum over CENTER blocks - sum over DIFF blocks.
+// One CTA per (sample, channel): the N accumulators live in shared memory, a thread owns a
+// centre n, sums its own term over j and scatters the neighbour terms with shared-memory
+// atomics (random targets: few conflicts); the upstream gradient -- again the only large
+// stream -- is read once.  Summation order of the scatter is not fixed (as in the reference's
+// index backward), the result differs run to run only in the last bits.
+__global__ void __launch_bounds__(kEdgeThreads)
+edge_feature_bwd_kernel(const float *__restrict__ g, const int32_t *__restrict__ idx, int C, int N, int k, int nblocks,
+                        int ops, float *__restrict__ gx) {
+    extern __shared__ float acc[];
+    const int c = blockIdx.x, b = blockIdx.y;
+    const long long NK = (long long)N * k;
+    for (int i = threadIdx.x; i < N; i += kEdgeThreads) acc[i] = 0.f;
+    __syncthreads();
+    const int32_t *ib = idx + (size_t)b * NK;
+    const bool vec = (k & 3) == 0;
+    for (int n = threadIdx.x; n < N; n += kEdgeThreads) {
+        float own = 0.f;
+        if (vec) {
+            for (int j = 0; j < k; j += 4) {
+                const int4 mv = *reinterpret_cast<const int4 *>(ib + (size_t)n * k + j);
+                float sn[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int q = 0; q < nblocks; ++q) {
+                    const int op = (ops >> (2 * q)) & 3;
+                    const float4 gv = __ldcs(reinterpret_cast<const float4 *>(
+                        g + (((size_t)b * nblocks + q) * C + c) * NK + (size_t)n * k + j));
+                    const float ga[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (op != PCD_EDGE_CENTER) sn[i] += ga[i];
+                        if (op == PCD_EDGE_CENTER) own += ga[i];
+                        if (op == PCD_EDGE_DIFF) own -= ga[i];
+                    }
+                }
+                atomicAdd(&acc[mv.x], sn[0]); atomicAdd(&acc[mv.y], sn[1]);
+                atomicAdd(&acc[mv.z], sn[2]); atomicAdd(&acc[mv.w], sn[3]);
+            }
+        } else {
+            for (int j = 0; j < k; ++j) {
+                const int m = ib[(size_t)n * k + j];
+                float sn = 0.f;
+                for (int q = 0; q < nblocks; ++q) {
+                    const int op = (ops >> (2 * q)) & 3;
+                    const float gv = __ldcs(g + (((size_t)b * nblocks + q) * C + c) * NK + (size_t)n * k + j);
+                    if (op != PCD_EDGE_CENTER) sn += gv;
+                    if (op == PCD_EDGE_CENTER) own += gv;
+                    if (op == PCD_EDGE_DIFF) own -= gv;
+                }
+                atomicAdd(&acc[m], sn);
+            }
+        }
+        atomicAdd(&acc[n], own);
+    }
+    __syncthreads();
+    float *dst = gx + ((size_t)b * C + c) * N;
+    for (int i = threadIdx.x; i < N; i += kEdgeThreads) dst[i] = acc[i];
+}
+
+// ----------------------------------------------------------------- farthest point sampling
+// One CTA per sample.  Thread t owns the points i = t + s*T (s < PPT) and their running
+// minimum distance to the chosen set in registers.  Per iteration: the new centroid is one
+// broadcast load, every thread updates its PPT distances with the reference's arithmetic
+// ((dx*dx + dy*dy) + dz*dz, then `dist < distance`), the block arg-max (first index on ties,
+// as torch.max(dim)) is two REDUX per warp plus one shared-memory exchange -- ONE
+// __syncthreads per iteration.
+template <int T, int PPT>
+__global__ void __launch_bounds__(T)
+fps_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sp, int64_t sc, int N, int npoint,
+           const int32_t *__restrict__ start, int32_t *__restrict__ out) {
+    constexpr int W = T / 32;
+    __shared__ unsigned long long wbest[2][W];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *pb = xyz + b * sb;
+    float px[PPT], py[PPT], pz[PPT], dist[PPT];
+#pragma unroll
+    for (int s = 0; s < PPT; ++s) {
+        const int i = tid + s * T;
+        if (i < N) {
+            px[s] = pb[i * sp]; py[s] = pb[i * sp + sc]; pz[s] = pb[i * sp + 2 * sc];
+            dist[s] = 1e10f;
+        } else {
+            px[s] = py[s] = pz[s] = 0.f;
+            dist[s] = -1.f;                                 // never the maximum, never updated
+        }
+    }
+    int far = start ? start[b] : 0;
+    if (far < 0 || far >= N) far = 0;
+    for (int it = 0; it < npoint; ++it) {
+        if (tid == 0) out[(size_t)b * npoint + it] = far;
+        if (it + 1 == npoint) break;
+        const float cx = __ldg(pb + far * sp), cy = __ldg(pb + far * sp + sc), cz = __ldg(pb + far * sp + 2 * sc);
+        uint32_t bd = 0u, bi = 0xffffffffu;                  // best (distance bits, index) of this thread
+#pragma unroll
+        for (int s = 0; s < PPT; ++s) {
+            const float dx = __fadd_rn(px[s], -cx), dy = __fadd_rn(py[s], -cy), dz = __fadd_rn(pz[s], -cz);
+            const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            if (dist[s] >= 0.f && d < dist[s]) dist[s] = d;
+            if (dist[s] >= 0.f) {
+                const uint32_t u = __float_as_uint(dist[s]);   // dist >= 0: the bit pattern orders like the value
+                if (u > bd || bi == 0xffffffffu) { bd = u; bi = (uint32_t)(tid + s * T); }   // s ascending: first index kept on ties
+            }
+        }
+        const uint32_t wd = __reduce_max_sync(0xffffffffu, bd);
+        const uint32_t wi = __reduce_min_sync(0xffffffffu, bd == wd ? bi : 0xffffffffu);
+        if (lane == 0) wbest[it & 1][warp] = ((unsigned long long)wd << 32) | (0xffffffffu - wi);
+        __syncthreads();
+        unsigned long long kbest = lane < W ? wbest[it & 1][lane] : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, kbest, o);
+            kbest = other > kbest ? other : kbest;
+        }
+        far = (int)(0xffffffffu - (uint32_t)kbest);
+    }
+}
+
+// N beyond the register variants: running distances in shared memory, points re-read through L1.
+template <int T>
+__global__ void __launch_bounds__(T)
+fps_large_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sp, int64_t sc, int N, int npoint,
+                 const int32_t *__restrict__ start, int32_t *__restrict__ out) {
+    constexpr int W = T / 32;
+    extern __shared__ float dist_s[];
+    __shared__ unsigned long long wbest[2][W];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *pb = xyz + b * sb;
+    for (int i = tid; i < N; i += T) dist_s[i] = 1e10f;
+    int far = start ? start[b] : 0;
+    if (far < 0 || far >= N) far = 0;
+    for (int it = 0; it < npoint; ++it) {
+        if (tid == 0) out[(size_t)b * npoint + it] = far;
+        if (it + 1 == npoint) break;
+        const float cx = __ldg(pb + far * sp), cy = __ldg(pb + far * sp + sc), cz = __ldg(pb + far * sp + 2 * sc);
+        uint32_t bd = 0u, bi = 0xffffffffu;
+        for (int i = tid; i < N; i += T) {
+            const float dx = __fadd_rn(__ldg(pb + i * sp), -cx), dy = __fadd_rn(__ldg(pb + i * sp + sc), -cy),
+                        dz = __fadd_rn(__ldg(pb + i * sp + 2 * sc), -cz);
+            const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            float cur = dist_s[i];
+            if (d < cur) { cur = d; dist_s[i] = d; }
+            const uint32_t u = __float_as_uint(cur);
+            if (u > bd || bi == 0xffffffffu) { bd = u; bi = (uint32_t)i; }
+        }
+        const uint32_t wd = __reduce_max_sync(0xffffffffu, bd);
+        const uint32_t wi = __reduce_min_sync(0xffffffffu, bd == wd ? bi : 0xffffffffu);
+        if (lane == 0) wbest[it & 1][warp] = ((unsigned long long)wd << 32) | (0xffffffffu - wi);
+        __syncthreads();
+        unsigned long long kbest = lane < W ? wbest[it & 1][lane] : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, kbest, o);
+            kbest = other > kbest ? other : kbest;
+        }
+        far = (int)(0xffffffffu - (uint32_t)kbest);
+    }
+}
+
+static int pack_ops(int nblocks, const int *ops, int *packed) {
+    if (nblocks < 1 || nblocks > 4 || !ops) return 0;
+    int p = 0;
+    for (int q = 0; q < nblocks; ++q) {
+        if (ops[q] < 0 || ops[q] > 2) return 0;
+        p |= ops[q] << (2 * q);
+    }
+    *packed = p;
+    return 1;
+}
+
+}  // namespace pcd
+
+using namespace pcd;
+
+extern "C" int pcd_edge_feature_forward(const float *x, const int32_t *idx, int B, int C, int N, int k, int nblocks,
+                                        const int *ops, float *out, void *stream) {
+    int packed = 0;
+    if (!x || !idx || !out || B <= 0 || C <= 0 || N <= 0 || k <= 0 || B > 65535 || !pack_ops(nblocks, ops, &packed)) {
+        set_error("pcd_edge_feature_forward: bad argument B=%d C=%d N=%d k=%d nblocks=%d", B, C, N, k, nblocks);
+        return PCD_ERR_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long NK = (long long)N * k;
+    const int CG = C < 8 ? C : 8;
+    const int cgroups = (C + CG - 1) / CG;
+    if (cgroups > 65535) {
+        set_error("pcd_edge_feature_forward: C=%d too large", C);
+        return PCD_ERR_UNSUPPORTED;
+    }
+    const bool vec = (k & 3) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)idx & 15) == 0;
+    if (vec) {
+        const dim3 grid((unsigned)((NK / 4 + kEdgeThreads - 1) / kEdgeThreads), cgroups, B);
+        edge_feature_fwd_kernel<4><<<grid, kEdgeThreads, 0, st>>>(x, idx, C, N, k, nblocks, packed, CG, out);
+    } else {
+        const dim3 grid((unsigned)((NK + kEdgeThreads - 1) / kEdgeThreads), cgroups, B);
+        edge_feature_fwd_kernel<1><<<grid, kEdgeThreads, 0, st>>>(x, idx, C, N, k, nblocks, packed, CG, out);
+    }
+    PCD_CUDA_CHECK(cudaGetLastError());
+    return PCD_OK;
+}
+
+extern "C" int pcd_edge_feature_backward(const float *g, const int32_t *idx, int B, int C, int N, int k, int nblocks,
+                                         const int *ops, float *gx, void *stream) {
+    int packed = 0;
+    if (!g || !idx || !gx || B <= 0 || C <= 0 || N <= 0 || k <= 0 || B > 65535 || !pack_ops(nblocks, ops, &packed)) {
+        set_error("pcd_edge_feature_backward: bad argument B=%d C=%d N=%d k=%d nblocks=%d", B, C, N, k, nblocks);
+        return PCD_ERR_ARG;
+    }
+    const size_t smem = (size_t)N * sizeof(float);
+    if (smem > 200 * 1024) {
+        set_error("pcd_edge_feature_backward: N=%d exceeds the shared-memory accumulator (N <= 51200)", N);
+        return PCD_ERR_UNSUPPORTED;
+    }
+    if (((uintptr_t)g & 15) != 0 || ((uintptr_t)idx & 15) != 0) {
+        set_error("pcd_edge_feature_backward: g and idx must be 16-byte aligned");
+        return PCD_ERR_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    static size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) {
+        PCD_CUDA_CHECK(cudaFuncSetAttribute(edge_feature_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    edge_feature_bwd_kernel<<<dim3(C, B), kEdgeThreads, smem, st>>>(g, idx, C, N, k, nblocks, packed, gx);
+    PCD_CUDA_CHECK(cudaGetLastError());
+    return PCD_OK;
+}
+
+extern "C" int pcd_fps(const float *xyz, int64_t sb, int64_t sp, int64_t sc, int B, int N, int npoint,
+                       const int32_t *start, int32_t *out, void *stream) {
+    if (!xyz || !out || B <= 0 || N <= 0 || npoint <= 0) {
+        set_error("pcd_fps: bad argument B=%d N=%d npoint=%d", B, N, npoint);
+        return PCD_ERR_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+#define PCD_FPS(T, PPT) fps_kernel<T, PPT><<<B, T, 0, st>>>(xyz, sb, sp, sc, N, npoint, start, out)
+    if (N <= 256) PCD_FPS(256, 1);
+    else if (N <= 512) PCD_FPS(512, 1);
+    else if (N <= 1024) PCD_FPS(512, 2);
+    else if (N <= 2048) PCD_FPS(512, 4);
+    else if (N <= 4096) PCD_FPS(512, 8);
+    else if (N <= 8192) PCD_FPS(1024, 8);
+    else {
+        const size_t smem = (size_t)N * sizeof(float);
+        if (smem > 200 * 1024) {
+            set_error("pcd_fps: N=%d exceeds the shared-memory distance array (N <= 51200)", N);
+            return PCD_ERR_UNSUPPORTED;
+        }
+        static size_t smem_set = 0;
+        if (smem > 48 * 1024 && smem > smem_set) {
+            PCD_CUDA_CHECK(cudaFuncSetAttribute(fps_large_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            smem_set = smem;
+        }
+        fps_large_kernel<1024><<<B, 1024, smem, st>>>(xyz, sb, sp, sc, N, npoint, start, out);
+    }
+#undef PCD_FPS
+    PCD_CUDA_CHECK(cudaGetLastError());
+    return PCD_OK;
+}

@@ -15,18 +15,17 @@ def knn(x, k):
 
 
 def get_graph_feature(x, k=20, idx=None):
-    """model/dgcnn.py:203-227 -> [B, 2C, N, k] = cat(feature - x, x); the hard-coded `cuda:0`
-    (:209) becomes x.device."""
+    """model/dgcnn.py:203-227 -> [B, 2C, N, k] = cat(feature - x, x) permuted channel-first.
+    The reference's flat gather + repeat + cat + permute().contiguous() chain (four
+    [B,N,k,2C]-sized intermediates) is one gather kernel writing the output once; its
+    backward is one kernel with shared-memory accumulators.  The hard-coded `cuda:0` (:209)
+    becomes x.device.  Like the reference, `k` must equal idx.shape[2] when idx is given."""
     batch_size = x.size(0)
     num_points = x.size(2)
     x = x.view(batch_size, -1, num_points)
     if idx is None:
-        idx = knn(x, k=k)
-    idx_base = torch.arange(0, batch_size, device=x.device).view(-1, 1, 1) * num_points
-    idx = (idx + idx_base).view(-1)
-    _, num_dims, _ = x.size()
-    x = x.transpose(2, 1).contiguous()
-    feature = x.view(batch_size * num_points, -1)[idx, :]
-    feature = feature.view(batch_size, num_points, k, num_dims)
-    x = x.view(batch_size, num_points, 1, num_dims).repeat(1, 1, k, 1)
-    return torch.cat((feature - x, x), dim=3).permute(0, 3, 1, 2).contiguous()
+        pts = x.detach().transpose(2, 1)
+        _, idx = F.knn(pts, pts, k, form=F.FORM_COL_ROW, norm=F.NORM_MULSUM)      # int32, no .long() round trip
+    elif idx.shape[2] != k:
+        raise RuntimeError(f"shape mismatch: idx has {idx.shape[2]} neighbours, k={k}")   # the reference's view() raises here
+    return F.edge_feature(x, idx, (F.EDGE_DIFF, F.EDGE_CENTER))

@@ -12,10 +12,11 @@ from collections import namedtuple
 import torch
 
 from . import _lib
-from ._lib import (FORM_COL_ROW, FORM_ROW_COL, FORM_SUM_FIRST, NORM_FMA, NORM_MULSUM,
+from ._lib import (EDGE_CENTER, EDGE_DIFF, EDGE_NEIGHBOR, FORM_COL_ROW, FORM_ROW_COL, FORM_SUM_FIRST, NORM_FMA, NORM_MULSUM,
                    VALUE_SQRT_CLAMP, VALUE_SQUARED)
 
-__all__ = ["nn1", "NN1Result", "knn", "ball_query", "fp32_peak_flops",
+__all__ = ["nn1", "NN1Result", "knn", "ball_query", "edge_feature", "farthest_point_sample", "fp32_peak_flops",
+           "EDGE_CENTER", "EDGE_NEIGHBOR", "EDGE_DIFF",
            "FORM_ROW_COL", "FORM_COL_ROW", "FORM_SUM_FIRST", "NORM_MULSUM", "NORM_FMA",
            "VALUE_SQUARED", "VALUE_SQRT_CLAMP"]
 
@@ -268,6 +269,89 @@ def ball_query(radius, nsample, xyz, new_xyz):
         _lib.check(st, "pcd_ball_query")
     _launch_count += 1
     return idx
+
+
+# ------------------------------------------------ k-NN graph edge features, farthest point sampling
+class _EdgeFeature(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, idx, ops):
+        global _launch_count
+        lib = _lib.load()
+        B, C, N = x.shape
+        k = idx.shape[2]
+        dev = x.device
+        c_ops = (ctypes.c_int * len(ops))(*ops)
+        with torch.cuda.device(dev):
+            out = torch.empty((B, len(ops) * C, N, k), dtype=torch.float32, device=dev)
+            st = lib.pcd_edge_feature_forward(x.data_ptr(), idx.data_ptr(), B, C, N, k, len(ops), c_ops,
+                                              out.data_ptr(), _stream())
+            _lib.check(st, "pcd_edge_feature_forward")
+        _launch_count += 1
+        ctx.save_for_backward(idx)
+        ctx.cfg = (ops, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        global _launch_count
+        if g is None or not ctx.needs_input_grad[0]:
+            return None, None, None
+        (idx,) = ctx.saved_tensors
+        ops, C = ctx.cfg
+        lib = _lib.load()
+        B, _, N, k = g.shape
+        dev = g.device
+        c_ops = (ctypes.c_int * len(ops))(*ops)
+        with torch.cuda.device(dev):
+            g = g.contiguous()
+            gx = torch.empty((B, C, N), dtype=torch.float32, device=dev)
+            st = lib.pcd_edge_feature_backward(g.data_ptr(), idx.data_ptr(), B, C, N, k, len(ops), c_ops,
+                                               gx.data_ptr(), _stream())
+            _lib.check(st, "pcd_edge_feature_backward")
+        _launch_count += 1
+        return gx, None, None
+
+
+def edge_feature(x, idx, ops):
+    """Edge features of a k-NN graph (pcd_edge_feature_forward in include/pcdist.h):
+    x [B,C,N] fp32 channel-first, idx [B,N,k] integer with entries in [0,N), ops a tuple of
+    EDGE_CENTER / EDGE_NEIGHBOR / EDGE_DIFF -> out [B, len(ops)*C, N, k]; differentiable in x."""
+    if not isinstance(x, torch.Tensor) or x.dim() != 3:
+        raise ValueError("x must be a 3-D tensor [B, C, N]")
+    if not x.is_cuda:
+        raise RuntimeError(f"x is on {x.device}: this path runs on CUDA only (no CPU fallback)")
+    if x.dtype != torch.float32:
+        raise TypeError(f"x must be float32, got {x.dtype}")
+    if idx.dim() != 3 or idx.shape[0] != x.shape[0] or idx.shape[1] != x.shape[2]:
+        raise ValueError(f"idx must be [B, N, k] matching x {tuple(x.shape)}, got {tuple(idx.shape)}")
+    ops = tuple(int(o) for o in ops)
+    if not 1 <= len(ops) <= 4 or any(o not in (EDGE_CENTER, EDGE_NEIGHBOR, EDGE_DIFF) for o in ops):
+        raise ValueError("ops must hold 1..4 of EDGE_CENTER / EDGE_NEIGHBOR / EDGE_DIFF")
+    idx32 = idx.detach().to(device=x.device, dtype=torch.int32).contiguous()
+    return _EdgeFeature.apply(x.contiguous(), idx32, ops)
+
+
+def farthest_point_sample(xyz, npoint, start=None):
+    """model/pointnet2_utils.py:59-81 as one persistent CTA per sample (pcd_fps): xyz [B,N,3]
+    (any strides), start [B] integer tensor or None (= index 0, model/curvenet_util.py:81)
+    -> centroids [B,npoint] int32 with centroids[:,0] = start."""
+    global _launch_count
+    _check_cloud(xyz, "xyz")
+    lib = _lib.load()
+    B, N, _ = xyz.shape
+    npoint = int(npoint)
+    if npoint < 1:
+        raise ValueError("npoint must be >= 1")
+    dev = xyz.device
+    with torch.cuda.device(dev):
+        st32 = None if start is None else start.detach().to(device=dev, dtype=torch.int32).contiguous()
+        out = torch.empty((B, npoint), dtype=torch.int32, device=dev)
+        x = xyz.detach()
+        st = lib.pcd_fps(x.data_ptr(), x.stride(0), x.stride(1), x.stride(2), B, N, npoint, _ptr(st32),
+                         out.data_ptr(), _stream())
+        _lib.check(st, "pcd_fps")
+    _launch_count += 1
+    return out
 
 
 def fp32_peak_flops(iters=2048):

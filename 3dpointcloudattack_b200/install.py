@@ -31,9 +31,9 @@ PATCHES = {
     "attack.GeoA3.utility": (knn_utils, ["knn_points", "knn_gather"]),
     "model.dgcnn": (dgcnn, ["knn", "get_graph_feature"]),
     "pointnet.model": (dgcnn, ["knn", "get_graph_feature"]),
-    "model.curvenet_util": (curvenet_util, ["knn", "normal_knn"]),
-    "model.pointnet2_utils": (pointnet2_utils, ["query_ball_point"]),
-    "pointnet.pointnet2_utils": (pointnet2_utils, ["query_ball_point"]),
+    "model.curvenet_util": (curvenet_util, ["knn", "normal_knn", "farthest_point_sample"]),
+    "model.pointnet2_utils": (pointnet2_utils, ["query_ball_point", "farthest_point_sample"]),
+    "pointnet.pointnet2_utils": (pointnet2_utils, ["query_ball_point", "farthest_point_sample"]),
 }
 
 
@@ -54,6 +54,9 @@ def install(modules=None, strict=False):
         for n in names:
             if hasattr(ours, n):
                 setattr(ref, n, getattr(ours, n))
+        if name == "model.curvenet_util":
+            ref.query_ball_point = pointnet2_utils.query_ball_point          # copy at curvenet_util.py:93-113
+            ref.LPFA.group_feature = curvenet_util.group_feature             # method :206-236
         if name.endswith("dist_utils") and hasattr(ref, "chamfer"):
             ref.chamfer, ref.hausdorff = distance.chamfer, distance.hausdorff
         report[name] = "patched"

@@ -22,3 +22,39 @@ def query_ball_point(radius, nsample, xyz, new_xyz):
     [B,S,N] int64 tensor and fully sorts every row; here one warp per query sweeps the
     columns in order and stops after nsample hits."""
     return F.ball_query(radius, nsample, xyz, new_xyz).long()
+
+
+def farthest_point_sample(xyz, npoint):
+    """:59-81 -> centroids [B,npoint] int64.  The start index is drawn exactly as the reference
+    draws it (torch.randint on the CPU generator, :71), so a seeded run picks the same points;
+    the npoint-iteration Python loop (6 launches per iteration) is one persistent kernel."""
+    B, N, _ = xyz.shape
+    start = torch.randint(0, N, (B,), dtype=torch.long)
+    return F.farthest_point_sample(xyz, npoint, start).long()
+
+
+def index_points(points, idx):
+    """:41-57: points[B,N,C], idx[B,S] or [B,S,K] -> points[b, idx[b,...], :] (differentiable
+    gather; plain torch indexing, one kernel either way)."""
+    B = points.shape[0]
+    view_shape = [B] + [1] * (idx.dim() - 1)
+    batch_indices = torch.arange(B, dtype=torch.long, device=points.device).view(view_shape)
+    return points[batch_indices, idx.long(), :]
+
+
+def sample_and_group(npoint, radius, nsample, xyz, points, returnfps=False):
+    """:107-135 with the FPS and ball-query kernels."""
+    B, N, C = xyz.shape
+    S = npoint
+    fps_idx = farthest_point_sample(xyz, npoint)
+    new_xyz = index_points(xyz, fps_idx)
+    idx = query_ball_point(radius, nsample, xyz, new_xyz)
+    grouped_xyz = index_points(xyz, idx)
+    grouped_xyz_norm = grouped_xyz - new_xyz.view(B, S, 1, C)
+    if points is not None:
+        new_points = torch.cat([grouped_xyz_norm, index_points(points, idx)], dim=-1)
+    else:
+        new_points = grouped_xyz_norm
+    if returnfps:
+        return new_xyz, new_points, grouped_xyz, fps_idx
+    return new_xyz, new_points

@@ -181,6 +181,37 @@ int pcd_ball_query(const float *xyz, int64_t x_sb, int64_t x_sp, int64_t x_sc,
                    int32_t *idx, void *stream);
 
 /* ------------------------------------------------------------------------------------
+ * Edge features of a k-NN graph (the step after the k-NN select in the DGCNN / CurveNet victims).
+ * Replaces the gather + subtract + cat + permute(0,3,1,2).contiguous() chains of
+ *   model/dgcnn.py:203-227          get_graph_feature   ops = {DIFF, CENTER}           -> [B,2C,N,k]
+ *   model/curvenet_util.py:206-236  LPFA.group_feature  ops = {CENTER, NEIGHBOR, DIFF} (xyz, 9 ch)
+ *                                                        ops = {DIFF}                   (features)
+ * x [B,C,N] contiguous fp32 (channel-first, as the victims hold it), idx [B,N,k] int32 with
+ * entries in [0,N), out [B, nblocks*C, N, k] contiguous:
+ *   out[b, q*C + c, n, j] = ops[q](centre = x[b,c,n], neighbour = x[b,c,idx[b,n,j]])
+ * `ops` is a HOST array of nblocks (1..4) pcd_edge_op values.  The backward accumulates
+ * gx[b,c,n] from g [B, nblocks*C, N, k] (own terms plus the scatter through idx); gx is
+ * written in full; N <= 51200; g and idx 16-byte aligned.
+ * ---------------------------------------------------------------------------------- */
+enum pcd_edge_op { PCD_EDGE_CENTER = 0, PCD_EDGE_NEIGHBOR = 1, PCD_EDGE_DIFF = 2 };
+
+int pcd_edge_feature_forward(const float *x, const int32_t *idx, int B, int C, int N, int k,
+                             int nblocks, const int *ops, float *out, void *stream);
+int pcd_edge_feature_backward(const float *g, const int32_t *idx, int B, int C, int N, int k,
+                              int nblocks, const int *ops, float *gx, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * Farthest point sampling.  Replaces the npoint-iteration Python loop of
+ *   model/pointnet2_utils.py:59-81 (random start, :71), model/curvenet_util.py:69-90 (start 0)
+ * with one persistent CTA per sample.  Same arithmetic and tie rule: dist = ((dx*dx + dy*dy) +
+ * dz*dz), distance = min(distance, dist) from 1e10, next = FIRST index of the maximum.
+ * xyz [B,N,3] via strides; start [B] int32 (device; NULL = start at 0, out-of-range entries
+ * = 0); out [B,npoint] int32 with out[b,0] = start[b].  N <= 51200.
+ * ---------------------------------------------------------------------------------- */
+int pcd_fps(const float *xyz, int64_t sb, int64_t sp, int64_t sc, int B, int N, int npoint,
+            const int32_t *start, int32_t *out, void *stream);
+
+/* ------------------------------------------------------------------------------------
  * Measurement helper (bench.py): runs an FFMA-only micro-kernel and returns the achieved
  * fp32 FLOP/s in *flops_per_s (host pointer).  This is the measured roofline denominator for
  * the sweep kernels (the FP32 FMA peak is not in MEASURED_PEAKS.json).

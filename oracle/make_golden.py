@@ -78,9 +78,75 @@ def save(name, **kw):
     print("wrote", name, {k: getattr(v, "shape", None) for k, v in kw.items()})
 
 
+class _TorchOnCPU:
+    """Stands in for the `torch` global of a reference module whose functions hard-code a CUDA
+    device (model/dgcnn.py:209 `torch.device('cuda:0')`): every attribute is torch's own, only
+    `device(...)` answers cpu.  The reference's arithmetic is untouched."""
+
+    def __getattr__(self, name):
+        return getattr(torch, name)
+
+    @staticmethod
+    def device(*a, **k):
+        return torch.device("cpu")
+
+
+def graph_and_sampling():
+    """f-2 / f-3: get_graph_feature, LPFA.group_feature, FPS, index_points."""
+    rs = np.random.RandomState(20261019)
+    ori = np.stack([face_fixture(1024, 0), face_fixture(1024, 1)])
+    adv = (ori + 0.01 * rs.randn(*ori.shape)).astype(np.float32)
+    adv_cf = np.ascontiguousarray(adv[:, :384].transpose(0, 2, 1))     # graph features on 384 points (fixture size)
+    from model import dgcnn, curvenet_util, pointnet2_utils as P2
+    out = {}
+    saved = dgcnn.torch
+    dgcnn.torch = _TorchOnCPU()
+    try:
+        x_ = t(adv_cf, True)
+        f = dgcnn.get_graph_feature(x_, k=20)
+        gw = rs.randn(*f.shape).astype(np.float32)
+        (f * t(gw)).sum().backward()
+        out.update(ggf3=n(f), ggf3_idx=n(dgcnn.knn(t(adv_cf), 20)), ggf3_gw=gw, ggf3_gx=n(x_.grad))
+        f16 = rs.randn(2, 16, 128).astype(np.float32)
+        x_ = t(f16, True)
+        f = dgcnn.get_graph_feature(x_, k=10)
+        gw = rs.randn(*f.shape).astype(np.float32)
+        (f * t(gw)).sum().backward()
+        out.update(f16=f16, ggf16=n(f), ggf16_idx=n(dgcnn.knn(t(f16), 10)), ggf16_gw=gw, ggf16_gx=n(x_.grad))
+        # caller-supplied idx with an odd k (scalar path)
+        idx7 = rs.randint(0, 128, size=(2, 128, 7)).astype(np.int64)
+        out.update(idx7=idx7, ggf16_idx7=n(dgcnn.get_graph_feature(t(f16), k=7, idx=torch.from_numpy(idx7))))
+    finally:
+        dgcnn.torch = saved
+    lp = curvenet_util.LPFA(9, 32, k=20, mlp_num=1, initial=True)
+    lp.device = torch.device("cpu")
+    xyz_ = t(adv_cf, True)
+    pf = lp.group_feature(None if False else t(adv_cf), xyz_, None)
+    gw = rs.randn(*pf.shape).astype(np.float32)
+    (pf * t(gw)).sum().backward()
+    out.update(lpfa9=n(pf), lpfa9_idx=n(curvenet_util.knn(t(adv_cf), 20)[:, :, :20]), lpfa9_gw=gw, lpfa9_gx=n(xyz_.grad))
+    # farthest point sampling: random start (pointnet2_utils.py:71) and start 0 (curvenet_util.py:81)
+    torch.manual_seed(7)
+    st = torch.get_rng_state()
+    start = torch.randint(0, 1024, (2,), dtype=torch.long)
+    torch.set_rng_state(st)
+    out.update(fps_start=n(start), fps_512=n(P2.farthest_point_sample(t(adv), 512)),
+               fps0_128=n(curvenet_util.farthest_point_sample(t(adv), 128)))
+    out["fps0_all"] = n(curvenet_util.farthest_point_sample(t(adv[:, :300]), 300))   # npoint == N
+    fidx = torch.from_numpy(out["fps_512"])
+    out["index_points_2d"] = n(P2.index_points(t(adv), fidx))
+    bq = P2.query_ball_point(0.2, 32, t(adv), P2.index_points(t(adv), fidx))
+    out["ball_idx"] = n(bq)
+    out["index_points_3d"] = n(P2.index_points(t(adv), bq[:, :64]))
+    save("f_graph_sampling", adv=adv, adv_cf=adv_cf, **out)
+
+
 def main():
     torch.set_num_threads(1)
     _prepare_reference()
+    if "--graph" in sys.argv:          # only the section added after the first fixtures were committed
+        graph_and_sampling()
+        return
     rs = np.random.RandomState(20261018)
 
     face = face_fixture(1024, 0)                                  # [1024,3]

@@ -168,3 +168,31 @@ void orc_ball_query(const float *row, const float *col, const float *nrow,
             for (int s = cnt; s < nsample; ++s) o[s] = first;
         }
 }
+
+/* farthest_point_sample (model/pointnet2_utils.py:59-81; model/curvenet_util.py:69-90 with
+ * start index 0): distance = 1e10; per iteration: record farthest, dist = sum((xyz-c)^2,-1)
+ * = ((dx*dx + dy*dy) + dz*dz) (torch.sum over the contiguous last dim of 3, sequential),
+ * distance = where(dist < distance, dist, distance), farthest = FIRST index of max(distance).
+ * xyz[B,N,3] point-major, start[B] (NULL = 0), out[B,npoint]. */
+void orc_fps(const float *xyz, int B, int N, int npoint, const int32_t *start, int32_t *out) {
+    #pragma omp parallel for schedule(static)
+    for (int b = 0; b < B; ++b) {
+        const float *p = xyz + (int64_t)b * N * 3;
+        float *distance = (float *)malloc(sizeof(float) * (size_t)N);
+        for (int i = 0; i < N; ++i) distance[i] = 1e10f;
+        int far = start ? start[b] : 0;
+        for (int it = 0; it < npoint; ++it) {
+            out[(int64_t)b * npoint + it] = far;
+            float cx = p[far * 3], cy = p[far * 3 + 1], cz = p[far * 3 + 2];
+            float best = -1.0f; int bi = 0;
+            for (int i = 0; i < N; ++i) {
+                float dx = p[i * 3] - cx, dy = p[i * 3 + 1] - cy, dz = p[i * 3 + 2] - cz;
+                float s = dx * dx; s = s + dy * dy; s = s + dz * dz;
+                if (s < distance[i]) distance[i] = s;
+                if (distance[i] > best) { best = distance[i]; bi = i; }
+            }
+            far = bi;
+        }
+        free(distance);
+    }
+}

@@ -328,3 +328,72 @@ def square_distance(src, dst):
 
 def query_ball_point(radius, nsample, xyz, new_xyz):
     return ball_query(radius, nsample, xyz, new_xyz)
+
+
+# ------------------------------ f-2: model/dgcnn.py:203-227, model/curvenet_util.py:206-236
+EDGE_CENTER, EDGE_NEIGHBOR, EDGE_DIFF = 0, 1, 2
+
+
+def edge_feature(x, idx, ops):
+    """out[b, q*C + c, n, j] = ops[q](centre x[b,c,n], neighbour x[b,c,idx[b,n,j]]):
+    CENTER -> centre, NEIGHBOR -> neighbour, DIFF -> neighbour - centre (one fp32 subtraction,
+    exact restatement of `feature - x`).  x[B,C,N], idx[B,N,k] -> [B, len(ops)*C, N, k]."""
+    x = _f32(x); idx = np.asarray(idx)
+    B, C, N = x.shape
+    k = idx.shape[2]
+    nb = x[np.arange(B)[:, None, None, None], np.arange(C)[None, :, None, None], idx[:, None].astype(np.int64)]
+    ctr = np.broadcast_to(x[:, :, :, None], (B, C, N, k))
+    blocks = []
+    for op in ops:
+        blocks.append(ctr if op == EDGE_CENTER else nb if op == EDGE_NEIGHBOR else nb - ctr)
+    return np.ascontiguousarray(np.concatenate(blocks, axis=1), dtype=np.float32)
+
+
+def edge_feature_grad(g, idx, ops, C):
+    """float64 closed form of d(sum(g*out))/dx for edge_feature: own terms plus the scatter
+    through idx (what autograd's index / cat / sub backward computes)."""
+    g = np.asarray(g, np.float64); idx = np.asarray(idx).astype(np.int64)
+    B, _, N, k = g.shape
+    gx = np.zeros((B, C, N), np.float64)
+    for q, op in enumerate(ops):
+        gq = g[:, q * C:(q + 1) * C]                       # [B,C,N,k]
+        if op in (EDGE_CENTER, EDGE_DIFF):
+            gx += gq.sum(3) * (1.0 if op == EDGE_CENTER else -1.0)
+        if op in (EDGE_NEIGHBOR, EDGE_DIFF):
+            for b in range(B):
+                for c in range(C):
+                    np.add.at(gx[b, c], idx[b].reshape(-1), gq[b, c].reshape(-1))
+    return gx
+
+
+def get_graph_feature(x, k=20, idx=None):
+    """model/dgcnn.py:203-227: cat(feature - x, x) permuted to [B,2C,N,k]."""
+    if idx is None:
+        idx = dgcnn_knn(x, k)
+    return edge_feature(x, idx, (EDGE_DIFF, EDGE_CENTER))
+
+
+def lpfa_point_feature(xyz, idx):
+    """model/curvenet_util.py:219-227: cat(points, point_feature, point_feature - points) -> [B,9,N,k]."""
+    return edge_feature(xyz, idx, (EDGE_CENTER, EDGE_NEIGHBOR, EDGE_DIFF))
+
+
+# ---------------- f-3: model/pointnet2_utils.py:41-81, model/curvenet_util.py:69-90 (start 0)
+def farthest_point_sample(xyz, npoint, start=None):
+    """xyz[B,N,3] -> centroids[B,npoint] int64; start[B] = the reference's torch.randint draw
+    (pointnet2_utils.py:71) or None for CurveNet's fixed start 0."""
+    xyz = _f32(xyz)
+    B, N, _ = xyz.shape
+    out = np.empty((B, npoint), np.int32)
+    st = None if start is None else np.ascontiguousarray(start, dtype=np.int32)
+    lib().orc_fps(_p(xyz), ctypes.c_int(B), ctypes.c_int(N), ctypes.c_int(npoint),
+                  None if st is None else _p(st), _p(out))
+    return out.astype(np.int64)
+
+
+def index_points(points, idx):
+    """model/pointnet2_utils.py:41-57: points[B,N,C], idx[B,S] or [B,S,K] -> gathered."""
+    points = np.asarray(points); idx = np.asarray(idx)
+    B = points.shape[0]
+    bi = np.arange(B).reshape((B,) + (1,) * (idx.ndim - 1))
+    return points[bi, idx]

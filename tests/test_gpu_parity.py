@@ -415,3 +415,76 @@ def test_cw_loop_eager_and_graph_agree():
         assert float((adv - data).norm(dim=-1).max()) <= 0.18 + 1e-5          # projection respected
         res[use_graph] = adv
     assert torch.allclose(res[False], res[True], atol=1e-4)                      # atomics reorder sums only
+
+
+# ------------------------------------------------------------- f-2 / f-3
+def test_f_get_graph_feature_vs_reference():
+    g = load_golden("f_graph_sampling")
+    x = cu(g["adv_cf"], True)
+    f = pcd.dgcnn.get_graph_feature(x, k=20)
+    assert f.shape == g["ggf3"].shape and np.array_equal(npy(f), g["ggf3"])       # bit-exact incl. the kNN
+    (f * cu(g["ggf3_gw"])).sum().backward()
+    assert rel_inf(g["ggf3_gx"], npy(x.grad)) < RTOL
+    x = cu(g["f16"], True)
+    f = pcd.dgcnn.get_graph_feature(x, k=10, idx=cu(g["ggf16_idx"]))
+    assert np.array_equal(npy(f), g["ggf16"])
+    (f * cu(g["ggf16_gw"])).sum().backward()
+    assert rel_inf(g["ggf16_gx"], npy(x.grad)) < RTOL
+    # odd k: scalar (non-float4) path
+    f = pcd.dgcnn.get_graph_feature(cu(g["f16"]), k=7, idx=cu(g["idx7"]))
+    assert np.array_equal(npy(f), g["ggf16_idx7"])
+    with pytest.raises(RuntimeError):
+        pcd.dgcnn.get_graph_feature(cu(g["f16"]), k=5, idx=cu(g["idx7"]))
+
+
+def test_f_lpfa_group_feature_vs_reference():
+    g = load_golden("f_graph_sampling")
+    xyz = cu(g["adv_cf"], True)
+    idx = pcd.curvenet_util.knn(xyz, 20)[:, :, :20]
+    assert np.array_equal(npy(idx), g["lpfa9_idx"])
+    pf = pcd.curvenet_util.lpfa_point_feature(xyz, idx)
+    assert np.array_equal(npy(pf), g["lpfa9"])
+    (pf * cu(g["lpfa9_gw"])).sum().backward()
+    assert rel_inf(g["lpfa9_gx"], npy(xyz.grad)) < RTOL
+
+
+@pytest.mark.parametrize("B,C,N,k,ops", [(3, 64, 500, 20, (2, 0)), (2, 5, 1000, 9, (0, 1, 2)), (1, 128, 2048, 20, (2,)),
+                                         (2, 3, 4096, 32, (1, 2, 0, 2)), (2, 1, 33, 4, (2, 0))])
+def test_f_edge_feature_random(B, C, N, k, ops):
+    rs = np.random.RandomState(B * 1000 + C)
+    x = rs.randn(B, C, N).astype(np.float32)
+    idx = rs.randint(0, N, size=(B, N, k))
+    xt = cu(x, True)
+    out = F.edge_feature(xt, cu(idx), ops)
+    assert np.array_equal(npy(out), O.edge_feature(x, idx, ops))
+    gw = rs.randn(*out.shape).astype(np.float32)
+    (out * cu(gw)).sum().backward()
+    assert rel_inf(O.edge_feature_grad(gw, idx, ops, C), npy(xt.grad)) < RTOL
+
+
+def test_f_farthest_point_sample_vs_reference():
+    g = load_golden("f_graph_sampling")
+    adv = cu(g["adv"])
+    assert np.array_equal(npy(F.farthest_point_sample(adv, 512, cu(g["fps_start"]))), g["fps_512"])
+    torch.manual_seed(7)                      # the seed make_golden.py drew the start indices under
+    assert np.array_equal(npy(pcd.pointnet2_utils.farthest_point_sample(adv, 512)), g["fps_512"])
+    assert np.array_equal(npy(pcd.curvenet_util.farthest_point_sample(adv, 128)), g["fps0_128"])
+    assert np.array_equal(npy(pcd.curvenet_util.farthest_point_sample(adv[:, :300], 300)), g["fps0_all"])
+    fidx = cu(g["fps_512"])
+    assert np.array_equal(npy(pcd.pointnet2_utils.index_points(adv, fidx)), g["index_points_2d"])
+    bq = pcd.pointnet2_utils.query_ball_point(0.2, 32, adv, pcd.pointnet2_utils.index_points(adv, fidx))
+    assert np.array_equal(npy(bq), g["ball_idx"])
+    assert np.array_equal(npy(pcd.pointnet2_utils.index_points(adv, bq[:, :64])), g["index_points_3d"])
+
+
+@pytest.mark.parametrize("N,npoint", [(100, 100), (257, 64), (513, 128), (1500, 512), (3000, 256), (4096, 1024),
+                                      (6000, 128), (10000, 64)])
+def test_f_farthest_point_sample_every_variant(N, npoint):
+    rs = np.random.RandomState(N)
+    xyz = rs.rand(3, N, 3).astype(np.float32)
+    xyz[1, N // 2:] = xyz[1, :N - N // 2]                        # duplicated points: first-index ties
+    start = rs.randint(0, N, size=3)
+    got = F.farthest_point_sample(cu(xyz), npoint, cu(start))
+    assert np.array_equal(npy(got), O.farthest_point_sample(xyz, npoint, start))
+    cf = cu(np.ascontiguousarray(xyz.transpose(0, 2, 1)))         # channel-first storage through strides
+    assert np.array_equal(npy(F.farthest_point_sample(cf.transpose(1, 2), npoint, cu(start))), npy(got))

@@ -166,3 +166,31 @@ def test_a3_knn_gradients_closed_form_vs_reference_autograd():
             assert rel_inf(g[tag + "_g1"], g1 + g2) < 1e-5
         else:
             assert rel_inf(g[tag + "_g1"], g1) < 1e-5 and rel_inf(g[tag + "_g2"], g2) < 1e-5
+
+
+# ------------------------------------------------------------- f-2 / f-3
+def test_f_graph_feature_bit_exact():
+    g = load_golden("f_graph_sampling")
+    assert np.array_equal(O.dgcnn_knn(g["adv_cf"], 20), g["ggf3_idx"])
+    assert np.array_equal(O.get_graph_feature(g["adv_cf"], 20), g["ggf3"])
+    assert np.array_equal(O.get_graph_feature(g["f16"], 10, idx=g["ggf16_idx"]), g["ggf16"])
+    assert np.array_equal(O.get_graph_feature(g["f16"], 7, idx=g["idx7"]), g["ggf16_idx7"])
+    assert np.array_equal(O.lpfa_point_feature(g["adv_cf"], g["lpfa9_idx"]), g["lpfa9"])
+
+
+def test_f_graph_feature_grads():
+    g = load_golden("f_graph_sampling")
+    E = (O.EDGE_DIFF, O.EDGE_CENTER)
+    assert rel_inf(g["ggf3_gx"], O.edge_feature_grad(g["ggf3_gw"], g["ggf3_idx"], E, 3)) < 1e-5
+    assert rel_inf(g["ggf16_gx"], O.edge_feature_grad(g["ggf16_gw"], g["ggf16_idx"], E, 16)) < 1e-5
+    L = (O.EDGE_CENTER, O.EDGE_NEIGHBOR, O.EDGE_DIFF)
+    assert rel_inf(g["lpfa9_gx"], O.edge_feature_grad(g["lpfa9_gw"], g["lpfa9_idx"], L, 3)) < 1e-5
+
+
+def test_f_farthest_point_sample_bit_exact():
+    g = load_golden("f_graph_sampling")
+    assert np.array_equal(O.farthest_point_sample(g["adv"], 512, g["fps_start"]), g["fps_512"])
+    assert np.array_equal(O.farthest_point_sample(g["adv"], 128), g["fps0_128"])
+    assert np.array_equal(O.farthest_point_sample(g["adv"][:, :300], 300), g["fps0_all"])
+    assert np.array_equal(O.index_points(g["adv"], g["fps_512"]), g["index_points_2d"])
+    assert np.array_equal(O.index_points(g["adv"], g["ball_idx"][:, :64]), g["index_points_3d"])
