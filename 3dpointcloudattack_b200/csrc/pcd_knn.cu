@@ -60,6 +60,21 @@ __device__ __forceinline__ unsigned long long warp_bitonic_merge32(unsigned long
     return key;
 }
 
+// full bitonic sort of one fp32 value per lane, ascending in lane order (SHFL + FMNMX per stage)
+__device__ __forceinline__ float warp_sort32_f32(float v, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const float o = __shfl_xor_sync(0xffffffffu, v, j);
+            const bool up = (lane & k) == 0 || k == 32;
+            const bool lower = (lane & j) == 0;
+            v = (lower == up) ? fminf(v, o) : fmaxf(v, o);
+        }
+    }
+    return v;
+}
+
 // Merge an ascending run `s` (one key per lane) into the NL sorted lists of a row.
 template <int NL>
 __device__ __forceinline__ void merge_run(unsigned long long (&L)[NL], unsigned long long s, int lane) {
@@ -132,6 +147,8 @@ struct RowSelect {
             cnt -= 32;
         }
     }
+    // Four candidates per lane (indices j..j+3) in one out-of-line compaction (stage4 below).
+    __device__ __forceinline__ void offer4(const float (&d)[4], int j, unsigned long long *buf, int lane, int K);
     __device__ __forceinline__ void finish(unsigned long long *buf, int lane, int K) {
         if (cnt > 0) {
             st = merge_staged<NL>(st, buf, cnt, lane, K);
@@ -149,6 +166,71 @@ struct RowSelect {
         }
     }
 };
+
+// Stage the passing ones of four candidates per lane (indices j..j+3) with ONE compaction: the
+// per-lane pass counts (0..4) are prefix-summed over the warp with three bit-plane ballots.
+// When more than 32 pass (the staging buffer holds 31 waiting + 32 new keys) the candidates go
+// through four single rounds.  Out of line for the same instruction-cache reason as merge_staged.
+template <int NL>
+struct SelStateCnt {
+    SelState<NL> st;
+    int cnt;
+};
+
+template <int NL>
+__device__ __noinline__ SelStateCnt<NL> stage4(SelStateCnt<NL> s, float d0, float d1, float d2, float d3, int j,
+                                               unsigned long long *buf, int lane, int K) {
+    const float thr = s.st.thr;
+    const bool p0 = d0 < thr, p1 = d1 < thr, p2 = d2 < thr, p3 = d3 < thr;
+    const int c = (int)p0 + (int)p1 + (int)p2 + (int)p3;
+    const unsigned b0 = __ballot_sync(0xffffffffu, c & 1), b1 = __ballot_sync(0xffffffffu, c & 2),
+                   b2 = __ballot_sync(0xffffffffu, c & 4);
+    const int total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+    if (total == 0) return s;
+    if (total <= 32) {
+        const unsigned lt = (1u << lane) - 1u;
+        int pos = s.cnt + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
+        if (p0) buf[pos++] = make_key(d0, (uint32_t)j);
+        if (p1) buf[pos++] = make_key(d1, (uint32_t)(j + 1));
+        if (p2) buf[pos++] = make_key(d2, (uint32_t)(j + 2));
+        if (p3) buf[pos] = make_key(d3, (uint32_t)(j + 3));
+        s.cnt += total;
+        if (s.cnt >= 32) {
+            s.st = merge_staged<NL>(s.st, buf, s.cnt, lane, K);
+            s.cnt -= 32;
+        }
+        return s;
+    }
+    const float dd[4] = {d0, d1, d2, d3};
+#pragma unroll 1
+    for (int e = 0; e < 4; ++e) {
+        const bool pass = dd[e] < s.st.thr;
+        const unsigned mask = __ballot_sync(0xffffffffu, pass);
+        if (mask == 0) continue;
+        if (pass) buf[s.cnt + __popc(mask & ((1u << lane) - 1u))] = make_key(dd[e], (uint32_t)(j + e));
+        s.cnt += __popc(mask);
+        if (s.cnt >= 32) {
+            s.st = merge_staged<NL>(s.st, buf, s.cnt, lane, K);
+            s.cnt -= 32;
+        }
+    }
+    return s;
+}
+
+template <int NL>
+__device__ __forceinline__ void RowSelect<NL>::offer4(const float (&d)[4], int j, unsigned long long *buf, int lane, int K) {
+    SelStateCnt<NL> s;
+    s.st = st; s.cnt = cnt;
+    s = stage4<NL>(s, d[0], d[1], d[2], d[3], j, buf, lane, K);
+    st = s.st; cnt = s.cnt;
+}
+
+// K-th smallest (0-based rank K-1 < 32) of one fp32 value per lane, bumped to the next float up
+// (thresholds are tested with d < thr and d == kth must pass); +inf / NaN stay +inf.  Out of line.
+__device__ __noinline__ float warp_kth_bound(float v, int lane, int K) {
+    const float kth = __shfl_sync(0xffffffffu, warp_sort32_f32(v, lane), K - 1);
+    return kth < __int_as_float(0x7f800000) ? ordered_to_f32(f32_to_ordered(kth) + 1u) : __int_as_float(0x7f800000);
+}
 
 // -------------------------------------------------------------------------- prep (xyz clouds)
 // rowq[b][i] = (-2x,-2y,-2z,nrow)   colq[b][j] = (x,y,z,ncol)   padded points inert (n = +inf)
@@ -465,8 +547,9 @@ knnc_kernel(const float *__restrict__ rowT, const float *__restrict__ rown, cons
             int N, int M, int C, int Npad, int Mpad, int K, int form,
             float *__restrict__ dists, int32_t *__restrict__ idx) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // layout: full[2] | qs[C][64] | ct[2][C*128 + 128] | stage[64 rows][63] u64
+    // layout: full[2], empty[2] | qs[C][64] | ct[2][C*128 + 128] | stage[64 rows][63] u64
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
+    uint64_t *empty = full + 2;                  // one arrival per warp when it has finished reading a stage
     float *qs = reinterpret_cast<float *>(smem_raw + 128);
     float *ct = qs + (size_t)C * kFcCtaRows;
     const size_t ct_stride = (size_t)C * kFcTile + kFcTile;
@@ -488,6 +571,8 @@ knnc_kernel(const float *__restrict__ rowT, const float *__restrict__ rown, cons
     if (tid == 0) {
         mbar_init(&full[0], 1);
         mbar_init(&full[1], 1);
+        mbar_init(&empty[0], kKnnWarps);
+        mbar_init(&empty[1], kKnnWarps);
         fence_mbar_init();
         fence_proxy_async();
     }
@@ -514,6 +599,13 @@ knnc_kernel(const float *__restrict__ rowT, const float *__restrict__ rown, cons
     const float4 *q4 = reinterpret_cast<const float4 *>(qs) + warp * 2;          // + k * 16
     for (int t = 0; t < ntiles; ++t) {
         const int buf = t & 1;
+        // No CTA barrier in the loop: the warps drift apart by up to one stage.  The producer
+        // refills the stage of tile t-1 with tile t+1 once all eight warps have released it.
+        if (tid == 0 && t >= 1 && t + 1 < ntiles) {
+            mbar_wait(&empty[buf ^ 1], ((t - 1) >> 1) & 1);
+            fence_proxy_async();
+            issue(t + 1);
+        }
         mbar_wait(&full[buf], (t >> 1) & 1);
         const float *tile = ct + buf * ct_stride;
         const float4 *c4p = reinterpret_cast<const float4 *>(tile) + lane;       // + k * 32
@@ -549,20 +641,26 @@ knnc_kernel(const float *__restrict__ rowT, const float *__restrict__ rown, cons
                 d01 = add2(add2_s(qn[r], n01), acc[r][0]); d23 = add2(add2_s(qn[r], n23), acc[r][1]);
             }
             unpack2(d01, d[r][0], d[r][1]); unpack2(d23, d[r][2], d[r][3]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[buf]);  // this warp is done with the stage (distances are in registers)
+        if (NL == 1 && t == 0) {
+            // First stage: instead of staging all 128 candidates against thr = +inf (four sort +
+            // merge rounds per row), start from a cheap exact upper bound of the K-th distance:
+            // the K-th smallest of the 32 lane minima (32 distinct candidates; K <= 32 here).
+#pragma unroll
+            for (int r = 0; r < kFcRows; ++r) {
+                sel[r].st.thr = warp_kth_bound(fminf(min3(d[r][0], d[r][1], d[r][2]), d[r][3]), lane, K);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < kFcRows; ++r) {
             const float thr = sel[r].st.thr;
             hit[r] = __ballot_sync(0xffffffffu, (d[r][0] < thr) | (d[r][1] < thr) | (d[r][2] < thr) | (d[r][3] < thr));
         }
 #pragma unroll
         for (int r = 0; r < kFcRows; ++r) {
-            if (hit[r]) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) sel[r].offer(d[r][e], j + e, mystage + r * kFcStage, lane, K);
-            }
-        }
-        __syncthreads();                         // stage buf fully read
-        if (tid == 0 && t + 2 < ntiles) {
-            fence_proxy_async();
-            issue(t + 2);
+            if (hit[r]) sel[r].offer4(d[r], j, mystage + r * kFcStage, lane, K);
         }
     }
 #pragma unroll
