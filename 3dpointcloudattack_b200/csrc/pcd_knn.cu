@@ -379,28 +379,285 @@ knn3_chunkmin_kernel(const float4 *__restrict__ rowq, const float4 *__restrict__
     }
 }
 
-// thread per row: K-th smallest of the G chunk minima (sorted insertion list in shared memory)
+// thread per row: K-th smallest of the G <= GP chunk minima with a fully unrolled bitonic sorting
+// network over registers (no shared memory, no divergence; 2 FMNMX per compare-exchange).  The
+// shared-memory insertion list it replaces took longer than the chunk-minima sweep itself.
+template <int GP>
 __global__ void __launch_bounds__(128)
 knn_threshold_kernel(const float *__restrict__ cm, int Npad, int G, int K, float *__restrict__ thr0) {
-    __shared__ float list[PCD_KNN_MAX_K][128];
     const int b = blockIdx.y, i = blockIdx.x * 128 + threadIdx.x;
     const float *src = cm + (size_t)b * G * Npad + i;
-    int cnt = 0;
-    for (int g = 0; g < G; ++g) {
-        const float v = src[(size_t)g * Npad];
-        if (cnt == K && !(v < list[K - 1][threadIdx.x])) continue;
-        int p = cnt < K ? cnt : K - 1;
-        while (p > 0 && list[p - 1][threadIdx.x] > v) { list[p][threadIdx.x] = list[p - 1][threadIdx.x]; --p; }
-        list[p][threadIdx.x] = v;
-        if (cnt < K) ++cnt;
+    const float inf = __int_as_float(0x7f800000);
+    float v[GP];
+#pragma unroll
+    for (int g = 0; g < GP; ++g) v[g] = g < G ? src[(size_t)g * Npad] : inf;
+#pragma unroll
+    for (int k = 2; k <= GP; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (int e = 0; e < GP; ++e) {
+                const int l = e ^ j;
+                if (l > e) {
+                    const float x = v[e], y = v[l];
+                    const bool up = (e & k) == 0;
+                    v[e] = up ? fminf(x, y) : fmaxf(x, y);
+                    v[l] = up ? fmaxf(x, y) : fminf(x, y);
+                }
+            }
+        }
     }
-    float t = __int_as_float(0x7f800000);
-    if (cnt == K) {
-        const float kth = list[K - 1][threadIdx.x];
-        // smallest float above kth: the select kernel tests d < thr, and d == kth must pass
-        if (kth < __int_as_float(0x7f800000)) t = ordered_to_f32(f32_to_ordered(kth) + 1u);
+    float kth = inf;
+#pragma unroll
+    for (int g = 0; g < GP; ++g)
+        if (g == K - 1) kth = v[g];
+    // smallest float above kth: candidates are tested with d < thr, and d == kth must pass
+    thr0[(size_t)b * Npad + i] = kth < inf ? ordered_to_f32(f32_to_ordered(kth) + 1u) : inf;
+}
+
+// ------------------------------------------------- collect pass: candidates below the threshold
+// Rows in lanes, packed math -- the chunk-minima sweep again -- but now every row knows a tight
+// exact upper bound thr of its K-th distance, so only ~1.2 K of its M candidates matter.
+//   phase 1 (per 256-column stage): the minimum of every 8-column group is compared with the
+//     row's bound; hits are pushed to a lane-private byte queue in shared memory (predicated
+//     store, no branch).  For form COL_ROW the outer row norm is moved into the bound
+//     (4 instead of 5 math instructions per pair); the moved bound is widened by a few ulp so
+//     the filter can only err towards extra hits.
+//   phase 2: each lane drains its queue: the 8 columns of a hit are re-evaluated with the exact
+//     arithmetic of `FORM`, and those with d < thr are appended (as (ordered distance, index)
+//     keys) to the row's candidate list in the workspace -- lane-private rows and per-split
+//     lists, so no atomics.
+// knn3_final_kernel then keeps the K smallest keys of every row (thread per row, insertion
+// network in registers).  A row whose list overflows is handed to knn3_kernel (the warp-per-row
+// select) through a per-sample overflow list, so the result is exact for any input.
+constexpr int kColGroup = 8;                                   // columns per tested group
+constexpr int kColGroups = kPreTile / kColGroup;               // 32 groups per stage
+
+struct CollectSmem {
+    float4 tile[2][kPreTile + 2];
+    uint64_t full[2];
+    unsigned int cnt[kPreR][128];
+    float4 rowrec[kPreR][128];                       // the lane's row records and bounds for phase 2 (dynamic row index)
+    float rowthr[kPreR][128];
+    unsigned char queue[kColGroups * kPreR][128];
+};
+
+template <int FORM>
+__global__ void __launch_bounds__(128)
+knn3_collect_kernel(const float4 *__restrict__ rowq, const float4 *__restrict__ colpk, const float *__restrict__ thr0,
+                    int B, int Npad, int Mpad, int M, int nsplit, int tps /* stages per split */, int caps,
+                    unsigned long long *__restrict__ cand, unsigned int *__restrict__ cnt_g) {
+    constexpr int R = kPreR;
+    __shared__ __align__(128) CollectSmem sm;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y;
+    const int rt = blockIdx.x / nsplit, sp = blockIdx.x - rt * nsplit;
+    const int row0 = rt * (128 * R) + warp * (32 * R) + lane;               // rows row0 + 32 r
+    const int ntiles_all = (M + kPreTile - 1) / kPreTile;
+    const int t_begin = sp * tps;
+    const int t_end = (t_begin + tps < ntiles_all) ? t_begin + tps : ntiles_all;
+    const int ntiles = t_end - t_begin;
+    const float4 *src = colpk + (size_t)b * Mpad + (size_t)t_begin * kPreTile;
+    const uint32_t tile_bytes = kPreTile * 16u;
+    if (tid == 0) {
+        mbar_init(&sm.full[0], 1);
+        mbar_init(&sm.full[1], 1);
+        fence_mbar_init();
+        fence_proxy_async();
+        if (ntiles > 0) {
+            mbar_expect_tx(&sm.full[0], tile_bytes);
+            tma_load_1d(sm.tile[0], src, tile_bytes, &sm.full[0]);
+        }
+        if (ntiles > 1) {
+            mbar_expect_tx(&sm.full[1], tile_bytes);
+            tma_load_1d(sm.tile[1], src + kPreTile, tile_bytes, &sm.full[1]);
+        }
     }
-    thr0[(size_t)b * Npad + i] = t;
+    __syncthreads();
+
+    const float inf = __int_as_float(0x7f800000);
+    float qx[R], qy[R], qz[R], qn[R], bound[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const float4 q = __ldg(&rowq[(size_t)b * Npad + row0 + 32 * r]);
+        const float thr = __ldg(&thr0[(size_t)b * Npad + row0 + 32 * r]);
+        qx[r] = q.x; qy[r] = q.y; qz[r] = q.z; qn[r] = q.w;
+        if (FORM == PCD_FORM_COL_ROW) {
+            // fl(u + n) < thr  ==>  u < (thr - n) + ulp(thr):  widen the computed difference by 2^-21 of the magnitudes
+            const float c = __fadd_rn(thr, -q.w);
+            bound[r] = __fadd_rn(c, __fmaf_rn(__fadd_rn(fabsf(c), fabsf(thr)), 4.76837158e-7f, 1e-37f));
+        } else {
+            bound[r] = thr;
+        }
+        sm.cnt[r][tid] = 0u;
+        sm.rowrec[r][tid] = q;
+        sm.rowthr[r][tid] = thr;
+    }
+    const size_t list_base = ((size_t)sp * B + b) * (size_t)caps * Npad;     // + slot * Npad + row
+
+    for (int t = 0; t < ntiles; ++t) {
+        const int buf = t & 1;
+        mbar_wait(&sm.full[buf], (t >> 1) & 1);
+        const float4 *t4 = sm.tile[buf];
+        // ---- phase 1
+        int qcount = 0;
+#pragma unroll 1
+        for (int g = 0; g < kColGroups; ++g) {
+            float m[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) m[r] = inf;
+#pragma unroll
+            for (int s4 = 0; s4 < kColGroup / 2; ++s4) {
+                const int step = g * (kColGroup / 2) + s4;
+                const float4 A = t4[2 * step], Bv = t4[2 * step + 1];
+                const f32x2 X = pack2(A.x, A.y), Y = pack2(A.z, A.w);
+                const f32x2 Z = pack2(Bv.x, Bv.y), Nn = pack2(Bv.z, Bv.w);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    f32x2 d;
+                    if (FORM == PCD_FORM_COL_ROW) {
+                        f32x2 tt = mul2_s(qx[r], X);
+                        tt = fma2_s(qy[r], Y, tt);
+                        tt = fma2_s(qz[r], Z, tt);
+                        d = add2(tt, Nn);
+                    } else {
+                        d = pair_dist_x2<FORM>(qx[r], qy[r], qz[r], qn[r], X, Y, Z, Nn);
+                    }
+                    float lo, hi;
+                    unpack2(d, lo, hi);
+                    m[r] = min3(m[r], lo, hi);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (m[r] < bound[r]) {
+                    sm.queue[qcount][tid] = (unsigned char)(r * kColGroups + g);
+                    ++qcount;
+                }
+            }
+        }
+        // ---- phase 2
+        const int jbase = (t_begin + t) * kPreTile;
+        for (int e = 0; e < qcount; ++e) {
+            const int code = sm.queue[e][tid];
+            const int r = code / kColGroups, g = code - r * kColGroups;
+            const int row = row0 + 32 * r;
+            const float4 q = sm.rowrec[r][tid];
+            const float thr = sm.rowthr[r][tid];
+            unsigned int slot = sm.cnt[r][tid];
+            unsigned long long *dst = cand + list_base + row;
+            float dd[kColGroup];
+            unsigned int pm = 0u;                            // bit = column offset inside the group
+#pragma unroll
+            for (int s4 = 0; s4 < kColGroup / 2; ++s4) {
+                // lanes visit the four pair records of their group in rotated order: the groups are 128 B
+                // apart (one bank row), unrotated every lane would hit the same four banks
+                const int rs = (s4 + lane) & (kColGroup / 2 - 1);
+                const int step = g * (kColGroup / 2) + rs;
+                const float4 A = t4[2 * step], Bv = t4[2 * step + 1];
+                const f32x2 d = pair_dist_x2<FORM>(q.x, q.y, q.z, q.w, pack2(A.x, A.y), pack2(A.z, A.w),
+                                                   pack2(Bv.x, Bv.y), pack2(Bv.z, Bv.w));
+                unpack2(d, dd[2 * s4], dd[2 * s4 + 1]);
+                pm |= ((dd[2 * s4] < thr ? 1u : 0u) | (dd[2 * s4 + 1] < thr ? 2u : 0u)) << (2 * rs);
+            }
+            while (pm) {                                     // usually one pass: the group's single candidate
+                const int co = __ffs(pm) - 1;
+                pm &= pm - 1u;
+                const int k = 2 * (((co >> 1) - lane) & (kColGroup / 2 - 1)) + (co & 1);     // register holding column co
+                float v = dd[0];
+#pragma unroll
+                for (int u = 1; u < kColGroup; ++u) v = (k == u) ? dd[u] : v;
+                if (slot < (unsigned)caps) dst[(size_t)slot * Npad] = make_key(v, (uint32_t)(jbase + g * kColGroup + co));
+                ++slot;
+            }
+            sm.cnt[r][tid] = slot;
+        }
+        __syncthreads();                                   // stage fully read by every warp
+        if (tid == 0 && t + 2 < ntiles) {
+            mbar_expect_tx(&sm.full[buf], tile_bytes);
+            tma_load_1d(sm.tile[buf], src + (size_t)(t + 2) * kPreTile, tile_bytes, &sm.full[buf]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+        cnt_g[((size_t)sp * B + b) * Npad + row0 + 32 * r] = sm.cnt[r][tid];
+}
+
+// thread per row: the K smallest of the row's candidate keys, ascending (insertion network over
+// KT >= K registers).  Rows with an overflowed list go to the per-sample overflow list instead
+// (knn3_kernel rewrites their outputs afterwards).  Results leave through shared memory so that
+// a warp writes its 32 x K outputs as one contiguous, coalesced block.
+template <int KT>
+__global__ void __launch_bounds__(128)
+knn3_final_kernel(const unsigned long long *__restrict__ cand, const unsigned int *__restrict__ cnt_g, int B, int N,
+                  int Npad, int nsplit, int caps, int K, float *__restrict__ dists, int32_t *__restrict__ idx,
+                  int *__restrict__ ovf_cnt, int *__restrict__ ovf_rows) {
+    __shared__ uint32_t stage[4][32 * PCD_KNN_MAX_K];
+    __shared__ unsigned short s_n[16][128];
+    const int b = blockIdx.y, i = blockIdx.x * 128 + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long L[KT];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) L[k] = kEmptyKey;
+    if (i < N) {
+        // all list lengths first (independent loads), kept in shared memory for the flat walk below
+        unsigned int total = 0;
+        bool over = false;
+        for (int sp = 0; sp < nsplit; ++sp) {
+            const unsigned int n = cnt_g[((size_t)sp * B + b) * Npad + i];
+            s_n[sp][threadIdx.x] = (unsigned short)(n > 0xffffu ? 0xffffu : n);
+            over |= n > (unsigned)caps;
+            total += n;
+        }
+        if (over) {
+            const int pos = atomicAdd(&ovf_cnt[b], 1);
+            ovf_rows[(size_t)b * Npad + pos] = i;
+        } else {
+            // One flat walk over the row's lists (a warp iterates max-over-lanes of the TOTAL count, not
+            // the sum of per-list maxima); the next key is in flight while the current one is inserted.
+            // Insertion = shift: every position compares and selects independently (no serial
+            // min/max chain through the KT registers), ONE instance of the network in the kernel.
+            const size_t split_stride = (size_t)B * caps * Npad;
+            const unsigned long long *src = cand + (size_t)b * caps * Npad + i;
+            int sp = 0;
+            unsigned int s = 0, n_cur = s_n[0][threadIdx.x];
+            while (s >= n_cur && sp + 1 < nsplit) { ++sp; s = 0; n_cur = s_n[sp][threadIdx.x]; src += split_stride; }
+            unsigned long long next = total ? src[0] : kEmptyKey;
+#pragma unroll 1
+            for (unsigned int t = 0; t < total; ++t) {
+                const unsigned long long c = next;
+                ++s;
+                while (s >= n_cur && sp + 1 < nsplit) { ++sp; s = 0; n_cur = s_n[sp][threadIdx.x]; src += split_stride; }
+                next = (t + 1 < total) ? src[(size_t)s * Npad] : kEmptyKey;
+                if (c < L[KT - 1]) {
+#pragma unroll
+                    for (int k = KT - 1; k >= 0; --k) {
+                        const bool pk = c < L[k];
+                        const bool pk1 = k > 0 ? (c < L[k > 0 ? k - 1 : 0]) : false;
+                        L[k] = pk ? (pk1 ? L[k > 0 ? k - 1 : 0] : c) : L[k];
+                    }
+                }
+            }
+        }
+    }
+    const int i0 = blockIdx.x * 128 + warp * 32;             // first row of this warp
+    const int nvalid = N - i0 < 32 ? N - i0 : 32;
+    if (nvalid <= 0) return;
+    const size_t base = ((size_t)b * N + i0) * K;
+    uint32_t *sg = stage[warp];
+    if (dists) {
+#pragma unroll
+        for (int k = 0; k < KT; ++k)
+            if (k < K) sg[lane * K + k] = __float_as_uint(ordered_to_f32((uint32_t)(L[k] >> 32)));
+        __syncwarp();
+        for (int e = lane; e < nvalid * K; e += 32) dists[base + e] = __uint_as_float(sg[e]);
+        __syncwarp();
+    }
+#pragma unroll
+    for (int k = 0; k < KT; ++k)
+        if (k < K) sg[lane * K + k] = (uint32_t)L[k];
+    __syncwarp();
+    for (int e = lane; e < nvalid * K; e += 32) idx[base + e] = (int32_t)sg[e];
 }
 
 // ------------------------------------------------------------------------- xyz k-NN kernel
@@ -413,10 +670,14 @@ struct Knn3Smem {
 template <int FORM, int NL>
 __global__ void __launch_bounds__(kKnnThreads)
 knn3_kernel(const float4 *__restrict__ rowq, const float4 *__restrict__ colq, const float *__restrict__ thr0,
-            int N, int M, int Npad, int Mpad, int K, float *__restrict__ dists, int32_t *__restrict__ idx) {
+            int N, int M, int Npad, int Mpad, int K, float *__restrict__ dists, int32_t *__restrict__ idx,
+            const int *__restrict__ ovf_cnt, const int *__restrict__ ovf_rows) {
     __shared__ __align__(128) Knn3Smem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y;
+    // overflow mode (ovf_rows != NULL): the CTA serves 32 entries of the sample's overflow list
+    const int nlist = ovf_rows ? ovf_cnt[b] : 0;
+    if (ovf_rows && (int)blockIdx.x * kKnnWarps * kKnnRQ >= nlist) return;
     const int row0 = (blockIdx.x * kKnnWarps + warp) * kKnnRQ;
     const int ntiles = (M + kKnnTile - 1) / kKnnTile;
     const float4 *src = colq + (size_t)b * Mpad;
@@ -437,12 +698,15 @@ knn3_kernel(const float4 *__restrict__ rowq, const float4 *__restrict__ colq, co
     __syncthreads();
 
     float4 q[kKnnRQ];
+    int rowi[kKnnRQ];
     RowSelect<NL> sel[kKnnRQ];
 #pragma unroll
     for (int r = 0; r < kKnnRQ; ++r) {
-        q[r] = __ldg(&rowq[(size_t)b * Npad + row0 + r]);   // rows are padded to a multiple of 32 per CTA
+        rowi[r] = row0 + r;                                  // rows are padded to a multiple of 32 per CTA
+        if (ovf_rows) rowi[r] = (row0 + r < nlist) ? ovf_rows[(size_t)b * Npad + row0 + r] : N;   // N: padded row, never stored
+        q[r] = __ldg(&rowq[(size_t)b * Npad + (rowi[r] < Npad ? rowi[r] : 0)]);
         sel[r].init();
-        if (thr0) sel[r].st.thr = __ldg(&thr0[(size_t)b * Npad + row0 + r]);
+        if (thr0) sel[r].st.thr = __ldg(&thr0[(size_t)b * Npad + (rowi[r] < Npad ? rowi[r] : 0)]);
     }
 
     for (int t = 0; t < ntiles; ++t) {
@@ -469,7 +733,7 @@ knn3_kernel(const float4 *__restrict__ rowq, const float4 *__restrict__ colq, co
 #pragma unroll
     for (int r = 0; r < kKnnRQ; ++r) {
         sel[r].finish(sm.stage[warp][r], lane, K);
-        const int i = row0 + r;
+        const int i = rowi[r];
         if (i < N) sel[r].store(dists, idx, ((size_t)b * N + i) * K, lane, K);
     }
 }
@@ -783,9 +1047,18 @@ ball_query_kernel(const float *__restrict__ xyz, int64_t x_sb, int64_t x_sp, int
 struct KnnLayout {
     int Npad, Mpad;
     size_t a, b, c, d, e, total;   // xyz: a=rowq b=colq c=colpk d=cm e=thr0 ; features: a=rowT b=rown c=colS
+    // xyz pre-pass + collect plan
+    bool prepass;
+    int W, G, nsplit, tps, caps;
+    size_t cand, cnt, ovf_cnt, ovf_rows;
 };
-static KnnLayout knn_layout(int B, int N, int M, int C) {
+constexpr int kPlanSMs = 148;     // B200; the plan must not depend on a device query (workspace sizes are host-only)
+
+static KnnLayout knn_layout(int B, int N, int M, int C, int K) {
     KnnLayout L;
+    L.prepass = false;
+    L.W = L.G = L.nsplit = L.tps = L.caps = 0;
+    L.cand = L.cnt = L.ovf_cnt = L.ovf_rows = 0;
     L.Npad = (int)align_up_k((size_t)N, C == 3 ? 128 * kPreR : kFcCtaRows);
     size_t off = 0;
     L.e = 0;
@@ -796,6 +1069,31 @@ static KnnLayout knn_layout(int B, int N, int M, int C) {
         L.c = off; off = align_up_k(off + (size_t)B * L.Mpad * 16, 256);
         L.d = off; off = align_up_k(off + (size_t)B * kPreMaxChunks * L.Npad * 4, 256);
         L.e = off; off = align_up_k(off + (size_t)B * L.Npad * 4, 256);
+        // pre-pass: chunk width W so that 3K <= G <= 64 chunks where possible; skipped when M is too small
+        int W = (M / (3 * (K > 0 ? K : 1))) & ~1;
+        const int wmin = ((M + kPreMaxChunks - 1) / kPreMaxChunks + 1) & ~1;
+        if (W < wmin) W = wmin;
+        if (W < 2) W = 2;
+        L.W = W;
+        L.G = (M + W - 1) / W;
+        L.prepass = K >= 1 && L.G >= K && L.G <= kPreMaxChunks && M >= 256;
+        if (L.prepass) {
+            // collect pass: split the column stages of a row tile over nsplit CTAs until the grid fills the GPU
+            const int ntiles = (M + kPreTile - 1) / kPreTile;
+            const long long base = (long long)B * (L.Npad / (128 * kPreR));
+            // (>= 4 full waves of 8 resident CTAs per SM, or one stage per CTA)
+            long long want = ((long long)kPlanSMs * 8 * 4 + base - 1) / base;
+            if (want < 1) want = 1;
+            if (want > 16) want = 16;
+            if (want > ntiles) want = ntiles;
+            L.tps = (ntiles + (int)want - 1) / (int)want;
+            L.nsplit = (ntiles + L.tps - 1) / L.tps;
+            L.caps = (2 * K + L.nsplit - 1) / L.nsplit + 12;           // expected ~1.2 K / nsplit candidates per list
+            L.cand = off; off = align_up_k(off + (size_t)L.nsplit * B * L.caps * L.Npad * 8, 256);
+            L.cnt = off; off = align_up_k(off + (size_t)L.nsplit * B * L.Npad * 4, 256);
+            L.ovf_cnt = off; off = align_up_k(off + (size_t)B * 4, 256);
+            L.ovf_rows = off; off = align_up_k(off + (size_t)B * L.Npad * 4, 256);
+        }
     } else {
         L.Mpad = (int)align_up_k((size_t)M, kFcTile);
         L.a = off; off = align_up_k(off + (size_t)B * L.Npad * C * 4, 256);
@@ -812,9 +1110,8 @@ static KnnLayout knn_layout(int B, int N, int M, int C) {
 using namespace pcd;
 
 extern "C" size_t pcd_knn_workspace_bytes(int B, int N, int M, int C, int K) {
-    (void)K;
     if (B <= 0 || N <= 0 || M <= 0 || C <= 0) return 0;
-    return knn_layout(B, N, M, C).total;
+    return knn_layout(B, N, M, C, K).total;
 }
 
 extern "C" int pcd_knn_forward(const float *rows, int64_t r_sb, int64_t r_sp, int64_t r_sc,
@@ -837,7 +1134,7 @@ extern "C" int pcd_knn_forward(const float *rows, int64_t r_sb, int64_t r_sp, in
         set_error("pcd_knn_forward: swap_norms requires N == M");
         return PCD_ERR_ARG;
     }
-    const KnnLayout L = knn_layout(B, N, M, C);
+    const KnnLayout L = knn_layout(B, N, M, C, K);
     if (workspace_bytes < L.total) {
         set_error("pcd_knn_forward: workspace %zu < required %zu bytes", workspace_bytes, L.total);
         return PCD_ERR_WORKSPACE;
@@ -857,31 +1154,53 @@ extern "C" int pcd_knn_forward(const float *rows, int64_t r_sb, int64_t r_sp, in
         knn3_prep_kernel<<<pgrid, 256, 0, st>>>(rows, r_sb, r_sp, r_sc, cols, c_sb, c_sp, c_sc, B, N, M, L.Npad, L.Mpad,
                                                 norm_kind, swap_norms, rowq, colq, colpk);
         PCD_CUDA_CHECK(cudaGetLastError());
-        // pre-pass: chunk width W so that 3K <= G <= 64 chunks where possible; skipped when M is too small
-        int W = (M / (3 * K)) & ~1;
-        const int wmin = ((M + kPreMaxChunks - 1) / kPreMaxChunks + 1) & ~1;
-        if (W < wmin) W = wmin;
-        if (W < 2) W = 2;
-        const int G = (M + W - 1) / W;
-        const bool prepass = G >= K && G <= kPreMaxChunks && M >= 256 && !getenv("PCD_KNN_NO_PREPASS");
+        const bool prepass = L.prepass && !getenv("PCD_KNN_NO_PREPASS");
+        const bool collect = prepass && !getenv("PCD_KNN_NO_COLLECT");
+        int *ovf_cnt = (int *)(ws + L.ovf_cnt), *ovf_rows = (int *)(ws + L.ovf_rows);
         if (prepass) {
+            const int W = L.W, G = L.G;
             const dim3 pg(L.Npad / (128 * kPreR), B);
             if (form == PCD_FORM_ROW_COL) knn3_chunkmin_kernel<PCD_FORM_ROW_COL><<<pg, 128, 0, st>>>(rowq, (const float4 *)colpk, L.Npad, L.Mpad, M, W, G, cm);
             else if (form == PCD_FORM_COL_ROW) knn3_chunkmin_kernel<PCD_FORM_COL_ROW><<<pg, 128, 0, st>>>(rowq, (const float4 *)colpk, L.Npad, L.Mpad, M, W, G, cm);
             else knn3_chunkmin_kernel<PCD_FORM_SUM_FIRST><<<pg, 128, 0, st>>>(rowq, (const float4 *)colpk, L.Npad, L.Mpad, M, W, G, cm);
             PCD_CUDA_CHECK(cudaGetLastError());
-            knn_threshold_kernel<<<dim3(L.Npad / 128, B), 128, 0, st>>>(cm, L.Npad, G, K, thr0);
+            if (G <= 32) knn_threshold_kernel<32><<<dim3(L.Npad / 128, B), 128, 0, st>>>(cm, L.Npad, G, K, thr0);
+            else knn_threshold_kernel<64><<<dim3(L.Npad / 128, B), 128, 0, st>>>(cm, L.Npad, G, K, thr0);
             PCD_CUDA_CHECK(cudaGetLastError());
         }
         const float *thr_arg = prepass ? thr0 : nullptr;
-#define PCD_LAUNCH_KNN3(F)                                                                                        \
+#define PCD_LAUNCH_KNN3(F, OC, OR)                                                                                        \
     do {                                                                                                          \
-        if (NL == 1) knn3_kernel<F, 1><<<grid, kKnnThreads, 0, st>>>(rowq, colq, thr_arg, N, M, L.Npad, L.Mpad, K, dists, idx); \
-        else knn3_kernel<F, 2><<<grid, kKnnThreads, 0, st>>>(rowq, colq, thr_arg, N, M, L.Npad, L.Mpad, K, dists, idx);    \
+        if (NL == 1) knn3_kernel<F, 1><<<grid, kKnnThreads, 0, st>>>(rowq, colq, thr_arg, N, M, L.Npad, L.Mpad, K, dists, idx, OC, OR); \
+        else knn3_kernel<F, 2><<<grid, kKnnThreads, 0, st>>>(rowq, colq, thr_arg, N, M, L.Npad, L.Mpad, K, dists, idx, OC, OR);    \
     } while (0)
-        if (form == PCD_FORM_ROW_COL) PCD_LAUNCH_KNN3(PCD_FORM_ROW_COL);
-        else if (form == PCD_FORM_COL_ROW) PCD_LAUNCH_KNN3(PCD_FORM_COL_ROW);
-        else PCD_LAUNCH_KNN3(PCD_FORM_SUM_FIRST);
+        if (collect) {
+            unsigned long long *cand = (unsigned long long *)(ws + L.cand);
+            unsigned int *cnt_g = (unsigned int *)(ws + L.cnt);
+            PCD_CUDA_CHECK(cudaMemsetAsync(ovf_cnt, 0, (size_t)B * 4, st));
+            const dim3 cg((L.Npad / (128 * kPreR)) * L.nsplit, B);
+            if (form == PCD_FORM_ROW_COL) knn3_collect_kernel<PCD_FORM_ROW_COL><<<cg, 128, 0, st>>>(rowq, (const float4 *)colpk, thr0, B, L.Npad, L.Mpad, M, L.nsplit, L.tps, L.caps, cand, cnt_g);
+            else if (form == PCD_FORM_COL_ROW) knn3_collect_kernel<PCD_FORM_COL_ROW><<<cg, 128, 0, st>>>(rowq, (const float4 *)colpk, thr0, B, L.Npad, L.Mpad, M, L.nsplit, L.tps, L.caps, cand, cnt_g);
+            else knn3_collect_kernel<PCD_FORM_SUM_FIRST><<<cg, 128, 0, st>>>(rowq, (const float4 *)colpk, thr0, B, L.Npad, L.Mpad, M, L.nsplit, L.tps, L.caps, cand, cnt_g);
+            PCD_CUDA_CHECK(cudaGetLastError());
+            const dim3 fg((N + 127) / 128, B);
+#define PCD_LAUNCH_FINAL(KT) knn3_final_kernel<KT><<<fg, 128, 0, st>>>(cand, cnt_g, B, N, L.Npad, L.nsplit, L.caps, K, dists, idx, ovf_cnt, ovf_rows)
+            if (K <= 8) PCD_LAUNCH_FINAL(8);
+            else if (K <= 16) PCD_LAUNCH_FINAL(16);
+            else if (K <= 24) PCD_LAUNCH_FINAL(24);
+            else if (K <= 32) PCD_LAUNCH_FINAL(32);
+            else PCD_LAUNCH_FINAL(64);
+#undef PCD_LAUNCH_FINAL
+            PCD_CUDA_CHECK(cudaGetLastError());
+            // rows whose candidate lists overflowed (none for randomly ordered clouds): warp-per-row select
+            if (form == PCD_FORM_ROW_COL) PCD_LAUNCH_KNN3(PCD_FORM_ROW_COL, ovf_cnt, ovf_rows);
+            else if (form == PCD_FORM_COL_ROW) PCD_LAUNCH_KNN3(PCD_FORM_COL_ROW, ovf_cnt, ovf_rows);
+            else PCD_LAUNCH_KNN3(PCD_FORM_SUM_FIRST, ovf_cnt, ovf_rows);
+        } else {
+            if (form == PCD_FORM_ROW_COL) PCD_LAUNCH_KNN3(PCD_FORM_ROW_COL, nullptr, nullptr);
+            else if (form == PCD_FORM_COL_ROW) PCD_LAUNCH_KNN3(PCD_FORM_COL_ROW, nullptr, nullptr);
+            else PCD_LAUNCH_KNN3(PCD_FORM_SUM_FIRST, nullptr, nullptr);
+        }
 #undef PCD_LAUNCH_KNN3
         PCD_CUDA_CHECK(cudaGetLastError());
     } else {

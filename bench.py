@@ -41,6 +41,7 @@ UNIT = "Gpair/s"
 B_PER_GPU, NPTS, SIGMA = 32, 4096, 0.01
 FLOP_PER_PAIR = 8.0
 BWD_BYTES_PER_POINT_DIR = 68.0
+SWEEP_DRAM_BYTES_PER_LAUNCH = 6324992   # ncu capture of nn1_sweep_kernel<2,16> at B=32 N=M=4096 (read 6.32 MB, write 0)
 
 
 def load_peaks():
@@ -373,7 +374,7 @@ def run_ours(args):
         bwd_avg_ms = sum(bwd_ms) / len(bwd_ms)
         bwd_bytes = 2.0 * B * NPTS * BWD_BYTES_PER_POINT_DIR
         cpu = None
-        if world == 1 or True:
+        if world == 1:                                        # reported baseline: rank 0 at N=1 only
             gps, ms, cores, b_chunk = cpu_reference_run(steps=3, warmup=1)
             cpu = {"value": gps, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"{b_chunk} of {B} samples x 3 steps (N=M={NPTS}); torch CPU op-for-op port of "
@@ -397,7 +398,9 @@ def run_ours(args):
             "gpu_launches": launches,
             "clocks": sampler.summary(),
             "roofline": {"bound": "fp32", "kernel": "nn1_sweep_kernel", "achieved": achieved, "peak": fp32_peak / 1e12,
-                         "unit": "TFLOP/s", "frac": achieved / (fp32_peak / 1e12), "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved / (fp32_peak / 1e12), "traffic": SWEEP_DRAM_BYTES_PER_LAUNCH,
+                         "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one launch at this "
+                                           "workload (profiles/r1_sweep_full_summary.txt); algorithmic input bytes = 6.29 MB",
                          "peak_source": "FFMA/FFMA2 micro-kernel measured in this run (pcd_measure_fp32_peak)",
                          "ms_per_launch": sweep_avg_ms, "flop_per_pair": FLOP_PER_PAIR},
             "roofline_backward": {"bound": "hbm", "kernel": "nn1_bwd_kernel x2", "achieved": bwd_bytes / (bwd_avg_ms * 1e-3) / 1e9,
@@ -409,7 +412,7 @@ def run_ours(args):
                           "sample_iters_per_s_graph": float(cw_t[1]) * B * world,
                           "config": f"PointNet(106) random init, B={B}/GPU N={NPTS}, w*(Chamfer+Hausdorff avg) + logits loss kappa=30, "
                                     f"Adam 1e-2, ClipPointsLinf 0.18, {CW_ITERS} iters; slowest rank; every rank attacks its own {B} samples",
-                          "cpu_reference_iters_per_s_B1": cw_cpu_baseline(),
+                          "cpu_reference_iters_per_s_B1": cw_cpu_baseline() if world == 1 else None,
                           "note": "iters_per_s = loop iterations per second with B samples per GPU advancing together; "
                                   "sample_iters_per_s = iterations x samples over all GPUs; CPU figure is the reference-shaped "
                                   "loop at B=1 (its only supported batch size) on the host cores"},

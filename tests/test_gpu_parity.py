@@ -303,6 +303,50 @@ def test_knn_bit_exact_random(K, form_key):
     assert np.array_equal(npy(d), od) and np.array_equal(npy(i), oi)
 
 
+@pytest.mark.parametrize("case", ["random4096", "sorted_overflow", "duplicates", "ragged", "k64", "sum_first", "swap"])
+def test_knn_collect_pipeline(case):
+    """xyz k-NN through pre-pass + collect + final select (and its overflow hand-over to the
+    warp-per-row kernel), bit-exact against the oracle."""
+    rs = np.random.RandomState(len(case))
+    form, norm, oform, onorm = FORMS["col_row_mulsum"]
+    K, swap = 17, False
+    rows = rs.rand(2, 2048, 3).astype(np.float32); cols = rows
+    if case == "random4096":
+        rows = cols = rs.randn(1, 4096, 3).astype(np.float32)
+    elif case == "sorted_overflow":
+        # points sorted along x: a row's neighbours share one or two chunks, the chunk-minima bound is loose
+        # and the candidate lists overflow -> exercised fallback
+        rows = cols = np.sort(rs.rand(2, 2048, 3).astype(np.float32), axis=1)
+        rows = cols = np.ascontiguousarray(rows[:, np.argsort(rows[0, :, 0])])
+    elif case == "duplicates":
+        cols = rows.copy(); cols[:, 1024:] = cols[:, :1024]; cols[:, 100:140] = cols[:, 7:8]
+    elif case == "ragged":
+        rows = rs.rand(3, 700, 3).astype(np.float32); cols = rs.rand(3, 1500, 3).astype(np.float32)
+    elif case == "k64":
+        K = 64
+    elif case == "sum_first":
+        form, norm, oform, onorm = FORMS["sum_first_fma"]
+    elif case == "swap":
+        cols = (rows + 0.01 * rs.randn(*rows.shape)).astype(np.float32); swap = True
+    d, i = F.knn(cu(rows), cu(cols), K, form=form, norm=norm, swap_norms=swap)
+    nr, nc = O.norms(onorm, rows), O.norms(onorm, cols)
+    if swap:
+        nr, nc = nc, nr
+    od, oi = O.knn(oform, rows, cols, nr, nc, K)
+    assert np.array_equal(npy(i), oi) and np.array_equal(npy(d), od)
+
+
+def test_knn_collect_matches_select_only(monkeypatch):
+    rs = np.random.RandomState(5)
+    x = cu(rs.rand(4, 3000, 3).astype(np.float32))
+    d1, i1 = F.knn(x, x, 20)
+    monkeypatch.setenv("PCD_KNN_NO_COLLECT", "1")
+    d2, i2 = F.knn(x, x, 20)
+    monkeypatch.setenv("PCD_KNN_NO_PREPASS", "1")
+    d3, i3 = F.knn(x, x, 20)
+    assert torch.equal(i1, i2) and torch.equal(d1, d2) and torch.equal(i1, i3) and torch.equal(d1, d3)
+
+
 @pytest.mark.parametrize("C", [1, 2, 5, 64, 128])
 def test_knn_feature_channels(C):
     rs = np.random.RandomState(C)
