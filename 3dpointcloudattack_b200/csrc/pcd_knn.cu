@@ -290,15 +290,24 @@ struct PreSmem {
 
 template <int FORM>
 __global__ void __launch_bounds__(128)
-knn3_chunkmin_kernel(const float4 *__restrict__ rowq, const float4 *__restrict__ colpk, int Npad, int Mpad, int M,
-                     int W /* columns per chunk, even */, int G, float *__restrict__ cm /* [B][G][Npad] */) {
+knn3_chunkmin_kernel(const float4 *__restrict__ rowq, const float4 *__restrict__ colpk, int Npad, int Mpad, int M_all,
+                     int W /* columns per chunk, even */, int G, int cps /* chunks per column split */,
+                     float *__restrict__ cm /* [B][G][Npad] */) {
     constexpr int R = kPreR;
     __shared__ __align__(128) PreSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y;
     const int row0 = blockIdx.x * (128 * R) + warp * (32 * R) + lane;       // rows row0 + 32 r
+    // column split blockIdx.z owns the chunks [c0, c1): columns [c0 W, min(M, c1 W)); stages are counted
+    // from its first column (W is even, so pair records stay aligned; the workspace has one stage of slack)
+    const int c0 = blockIdx.z * cps;
+    const int c1 = (c0 + cps < G) ? c0 + cps : G;
+    const int col_begin = c0 * W;
+    const int col_end = (c1 * W < M_all) ? c1 * W : M_all;
+    const int M = col_end - col_begin;                                       // columns of this split
+    if (M <= 0) return;
     const int ntiles = (M + kPreTile - 1) / kPreTile;
-    const float4 *src = colpk + (size_t)b * Mpad;
+    const float4 *src = colpk + (size_t)b * Mpad + col_begin;
     const uint32_t tile_bytes = kPreTile * 16u;
     if (tid == 0) {
         mbar_init(&sm.full[0], 1);
@@ -323,7 +332,7 @@ knn3_chunkmin_kernel(const float4 *__restrict__ rowq, const float4 *__restrict__
         m[r] = __int_as_float(0x7f800000);
     }
     float *out = cm + (size_t)b * G * Npad + row0;
-    int chunk = 0, left = W / 2;                       // packed steps left in the current chunk
+    int chunk = c0, left = W / 2;                      // packed steps left in the current chunk
     const int total_steps = (M + 1) / 2;
     int done = 0;
     for (int t = 0; t < ntiles; ++t) {
@@ -372,7 +381,7 @@ knn3_chunkmin_kernel(const float4 *__restrict__ rowq, const float4 *__restrict__
             tma_load_1d(sm.tile[buf], src + (size_t)(t + 2) * kPreTile, tile_bytes, &sm.full[buf]);
         }
     }
-    if (chunk < G) {       // last, partial chunk
+    if (chunk < c1) {      // last, partial chunk
 #pragma unroll
         for (int r = 0; r < R; ++r)
             out[(size_t)chunk * Npad + 32 * r] = (FORM == PCD_FORM_COL_ROW) ? __fadd_rn(m[r], qn[r]) : m[r];
@@ -620,15 +629,15 @@ knn3_final_kernel(const unsigned long long *__restrict__ cand, const unsigned in
             const size_t split_stride = (size_t)B * caps * Npad;
             const unsigned long long *src = cand + (size_t)b * caps * Npad + i;
             int sp = 0;
-            unsigned int s = 0, n_cur = s_n[0][threadIdx.x];
-            while (s >= n_cur && sp + 1 < nsplit) { ++sp; s = 0; n_cur = s_n[sp][threadIdx.x]; src += split_stride; }
-            unsigned long long next = total ? src[0] : kEmptyKey;
-#pragma unroll 1
-            for (unsigned int t = 0; t < total; ++t) {
-                const unsigned long long c = next;
-                ++s;
+            unsigned int s = 0, n_cur = s_n[0][threadIdx.x], fetched = 0;
+            auto fetch = [&]() -> unsigned long long {       // next key of the flat walk (kEmptyKey past the end)
+                if (fetched >= total) return kEmptyKey;
                 while (s >= n_cur && sp + 1 < nsplit) { ++sp; s = 0; n_cur = s_n[sp][threadIdx.x]; src += split_stride; }
-                next = (t + 1 < total) ? src[(size_t)s * Npad] : kEmptyKey;
+                const unsigned long long v = src[(size_t)s * Npad];
+                ++s; ++fetched;
+                return v;
+            };
+            auto insert = [&](unsigned long long c) {
                 if (c < L[KT - 1]) {
 #pragma unroll
                     for (int k = KT - 1; k >= 0; --k) {
@@ -637,6 +646,15 @@ knn3_final_kernel(const unsigned long long *__restrict__ cand, const unsigned in
                         L[k] = pk ? (pk1 ? L[k > 0 ? k - 1 : 0] : c) : L[k];
                     }
                 }
+            };
+            // four keys in flight: a key is loaded four insertions (~1 us of ALU work) before it is needed
+            unsigned long long k0 = fetch(), k1 = fetch(), k2 = fetch(), k3 = fetch();
+#pragma unroll 1
+            for (unsigned int t = 0; t < total; t += 4) {
+                insert(k0); k0 = fetch();
+                insert(k1); k1 = fetch();
+                insert(k2); k2 = fetch();
+                insert(k3); k3 = fetch();
             }
         }
     }
@@ -1066,7 +1084,7 @@ static KnnLayout knn_layout(int B, int N, int M, int C, int K) {
         L.Mpad = (int)align_up_k((size_t)M, kKnnTile);
         L.a = off; off = align_up_k(off + (size_t)B * L.Npad * 16, 256);
         L.b = off; off = align_up_k(off + (size_t)B * L.Mpad * 16, 256);
-        L.c = off; off = align_up_k(off + (size_t)B * L.Mpad * 16, 256);
+        L.c = off; off = align_up_k(off + (size_t)B * L.Mpad * 16 + kPreTile * 16, 256);   // + one stage of slack (chunk-aligned stages)
         L.d = off; off = align_up_k(off + (size_t)B * kPreMaxChunks * L.Npad * 4, 256);
         L.e = off; off = align_up_k(off + (size_t)B * L.Npad * 4, 256);
         // pre-pass: chunk width W so that 3K <= G <= 64 chunks where possible; skipped when M is too small
@@ -1159,10 +1177,18 @@ extern "C" int pcd_knn_forward(const float *rows, int64_t r_sb, int64_t r_sp, in
         int *ovf_cnt = (int *)(ws + L.ovf_cnt), *ovf_rows = (int *)(ws + L.ovf_rows);
         if (prepass) {
             const int W = L.W, G = L.G;
-            const dim3 pg(L.Npad / (128 * kPreR), B);
-            if (form == PCD_FORM_ROW_COL) knn3_chunkmin_kernel<PCD_FORM_ROW_COL><<<pg, 128, 0, st>>>(rowq, (const float4 *)colpk, L.Npad, L.Mpad, M, W, G, cm);
-            else if (form == PCD_FORM_COL_ROW) knn3_chunkmin_kernel<PCD_FORM_COL_ROW><<<pg, 128, 0, st>>>(rowq, (const float4 *)colpk, L.Npad, L.Mpad, M, W, G, cm);
-            else knn3_chunkmin_kernel<PCD_FORM_SUM_FIRST><<<pg, 128, 0, st>>>(rowq, (const float4 *)colpk, L.Npad, L.Mpad, M, W, G, cm);
+            // column splits at chunk granularity until the grid holds >= 4 waves of 8 CTAs per SM
+            const long long base = (long long)B * (L.Npad / (128 * kPreR));
+            long long csplit = ((long long)sms * 32 + base - 1) / base;
+            const int max_split = (M + 2 * kPreTile - 1) / (2 * kPreTile);        // at least two stages per split
+            if (csplit > max_split) csplit = max_split;
+            if (csplit > G) csplit = G;
+            if (csplit < 1) csplit = 1;
+            const int cps = (G + (int)csplit - 1) / (int)csplit;
+            const dim3 pg(L.Npad / (128 * kPreR), B, (G + cps - 1) / cps);
+            if (form == PCD_FORM_ROW_COL) knn3_chunkmin_kernel<PCD_FORM_ROW_COL><<<pg, 128, 0, st>>>(rowq, (const float4 *)colpk, L.Npad, L.Mpad, M, W, G, cps, cm);
+            else if (form == PCD_FORM_COL_ROW) knn3_chunkmin_kernel<PCD_FORM_COL_ROW><<<pg, 128, 0, st>>>(rowq, (const float4 *)colpk, L.Npad, L.Mpad, M, W, G, cps, cm);
+            else knn3_chunkmin_kernel<PCD_FORM_SUM_FIRST><<<pg, 128, 0, st>>>(rowq, (const float4 *)colpk, L.Npad, L.Mpad, M, W, G, cps, cm);
             PCD_CUDA_CHECK(cudaGetLastError());
             if (G <= 32) knn_threshold_kernel<32><<<dim3(L.Npad / 128, B), 128, 0, st>>>(cm, L.Npad, G, K, thr0);
             else knn_threshold_kernel<64><<<dim3(L.Npad / 128, B), 128, 0, st>>>(cm, L.Npad, G, K, thr0);
@@ -1185,11 +1211,17 @@ extern "C" int pcd_knn_forward(const float *rows, int64_t r_sb, int64_t r_sp, in
             PCD_CUDA_CHECK(cudaGetLastError());
             const dim3 fg((N + 127) / 128, B);
 #define PCD_LAUNCH_FINAL(KT) knn3_final_kernel<KT><<<fg, 128, 0, st>>>(cand, cnt_g, B, N, L.Npad, L.nsplit, L.caps, K, dists, idx, ovf_cnt, ovf_rows)
-            if (K <= 8) PCD_LAUNCH_FINAL(8);
-            else if (K <= 16) PCD_LAUNCH_FINAL(16);
-            else if (K <= 24) PCD_LAUNCH_FINAL(24);
-            else if (K <= 32) PCD_LAUNCH_FINAL(32);
-            else PCD_LAUNCH_FINAL(64);
+            switch ((K + 3) / 4) {                           // KT = K rounded up to a multiple of 4 (48 / 64 beyond 32)
+                case 1: PCD_LAUNCH_FINAL(4); break;
+                case 2: PCD_LAUNCH_FINAL(8); break;
+                case 3: PCD_LAUNCH_FINAL(12); break;
+                case 4: PCD_LAUNCH_FINAL(16); break;
+                case 5: PCD_LAUNCH_FINAL(20); break;
+                case 6: PCD_LAUNCH_FINAL(24); break;
+                case 7: PCD_LAUNCH_FINAL(28); break;
+                case 8: PCD_LAUNCH_FINAL(32); break;
+                default: if (K <= 48) PCD_LAUNCH_FINAL(48); else PCD_LAUNCH_FINAL(64); break;
+            }
 #undef PCD_LAUNCH_FINAL
             PCD_CUDA_CHECK(cudaGetLastError());
             // rows whose candidate lists overflowed (none for randomly ordered clouds): warp-per-row select
