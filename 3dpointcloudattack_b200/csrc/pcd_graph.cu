@@ -15,52 +15,61 @@ namespace pcd {
 // ------------------------------------------------------------------------- edge features
 // out[b, q*C + c, n, j] = op_q( x[b,c,n] (centre), x[b,c,idx[b,n,j]] (neighbour) ),  q < nblocks
 //   CENTER   -> centre            NEIGHBOR -> neighbour            DIFF -> neighbour - centre
-// ops are packed two bits per block.  One thread owns VEC consecutive (n,j) slots (the same n
-// when VEC = 4 divides k) and walks a group of CG channels with the indices in registers; the
-// x rows of the group (N floats each) are re-read through L1, the output -- the only large
-// stream: B * nblocks*C * N*k floats, 5.4 GB for DGCNN's last layer at BASELINE config 4 -- is
-// written once with streaming stores.
+// ops are packed two bits per block.  The output -- the only large stream: B * nblocks*C * N*k
+// floats, 5.4 GB for DGCNN's last layer at BASELINE config 4 -- is written once with streaming
+// float4 stores.  A CTA stages the x rows of its CG channels in shared memory (N floats each):
+// the neighbour gathers are random 4-byte reads, and from L1 they cost one tag lookup per
+// lane (ncu: lg_throttle, 4.0 TB/s of stores); from shared memory they are bank accesses.
 constexpr int kEdgeThreads = 256;
+constexpr int kEdgeSmemFloats = 16384;       // 64 KB of staged channel rows per CTA
 
 __device__ __forceinline__ float edge_value(int op, float ctr, float nb) {
     return op == PCD_EDGE_CENTER ? ctr : (op == PCD_EDGE_NEIGHBOR ? nb : __fadd_rn(nb, -ctr));
 }
 
+// grid (slices, channel groups, B); a slice = spt consecutive VEC-wide slots per thread-stride
 template <int VEC>
 __global__ void __launch_bounds__(kEdgeThreads)
 edge_feature_fwd_kernel(const float *__restrict__ x, const int32_t *__restrict__ idx, int C, int N, int k, int nblocks,
-                        int ops, int CG, float *__restrict__ out) {
+                        int ops, int CG, long long slots_per_slice, float *__restrict__ out) {
+    extern __shared__ float xs[];                                  // [CG][N]
     const long long NK = (long long)N * k;
-    const long long e0 = ((long long)blockIdx.x * kEdgeThreads + threadIdx.x) * VEC;
-    if (e0 >= NK) return;
     const int b = blockIdx.z;
     const int c0 = blockIdx.y * CG;
-    const int c1 = c0 + CG < C ? c0 + CG : C;
-    int m[VEC], n[VEC];
-    if (VEC == 4) {
-        const int4 v = *reinterpret_cast<const int4 *>(idx + (size_t)b * NK + e0);
-        m[0] = v.x; m[1 % VEC] = v.y; m[2 % VEC] = v.z; m[3 % VEC] = v.w;
-        const int nn = (int)(e0 / k);                       // k % 4 == 0: the four slots share n
+    const int ncg = (c0 + CG < C ? c0 + CG : C) - c0;
+    const float *xb = x + ((size_t)b * C + c0) * N;
+    for (int i = threadIdx.x; i < ncg * N; i += kEdgeThreads) xs[i] = __ldg(xb + i);
+    __syncthreads();
+    const long long nslots = (NK + VEC - 1) / VEC;
+    const long long s_begin = (long long)blockIdx.x * slots_per_slice;
+    const long long s_end = s_begin + slots_per_slice < nslots ? s_begin + slots_per_slice : nslots;
+    const int32_t *ib = idx + (size_t)b * NK;
+    for (long long sl = s_begin + threadIdx.x; sl < s_end; sl += kEdgeThreads) {
+        const long long e0 = sl * VEC;
+        int m[VEC];
+        if (VEC == 4) {
+            const int4 v = __ldcs(reinterpret_cast<const int4 *>(ib + e0));
+            m[0] = v.x; m[1 % VEC] = v.y; m[2 % VEC] = v.z; m[3 % VEC] = v.w;
+        } else {
+            m[0] = __ldcs(ib + e0);
+        }
+        const int n = (int)(e0 / k);                               // VEC = 4 only when 4 | k: the four slots share n
+        for (int c = 0; c < ncg; ++c) {
+            const float *xr = xs + c * N;
+            const float ctr = xr[n];
+            float nb[VEC];
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) n[i] = nn;
-    } else {
-        m[0] = idx[(size_t)b * NK + e0];
-        n[0] = (int)(e0 / k);
-    }
-    for (int c = c0; c < c1; ++c) {
-        const float *xr = x + ((size_t)b * C + c) * N;
-        float ctr[VEC], nb[VEC];
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) { ctr[i] = __ldg(xr + n[i]); nb[i] = __ldg(xr + m[i]); }
-        for (int q = 0; q < nblocks; ++q) {
-            const int op = (ops >> (2 * q)) & 3;
-            float *dst = out + (((size_t)b * nblocks + q) * C + c) * NK + e0;
-            if (VEC == 4) {
-                __stcs(reinterpret_cast<float4 *>(dst),
-                       make_float4(edge_value(op, ctr[0], nb[0]), edge_value(op, ctr[1 % VEC], nb[1 % VEC]),
-                                   edge_value(op, ctr[2 % VEC], nb[2 % VEC]), edge_value(op, ctr[3 % VEC], nb[3 % VEC])));
-            } else {
-                __stcs(dst, edge_value(op, ctr[0], nb[0]));
+            for (int i = 0; i < VEC; ++i) nb[i] = xr[m[i]];
+            for (int q = 0; q < nblocks; ++q) {
+                const int op = (ops >> (2 * q)) & 3;
+                float *dst = out + (((size_t)b * nblocks + q) * C + c0 + c) * NK + e0;
+                if (VEC == 4) {
+                    __stcs(reinterpret_cast<float4 *>(dst),
+                           make_float4(edge_value(op, ctr, nb[0]), edge_value(op, ctr, nb[1 % VEC]),
+                                       edge_value(op, ctr, nb[2 % VEC]), edge_value(op, ctr, nb[3 % VEC])));
+                } else {
+                    __stcs(dst, edge_value(op, ctr, nb[0]));
+                }
             }
         }
     }
@@ -68,11 +77,12 @@ edge_feature_fwd_kernel(const float *__restrict__ x, const int32_t *__restrict__
 
 // Backward: gx[b,c,n] = sum_j s_ctr(n,j) + sum_{(n',j): idx[b,n',j] = n} s_nbr(n',j) with
 //   s_nbr = sum of g over NEIGHBOR and DIFF blocks,  s_ctr = sum over CENTER blocks - sum over DIFF blocks.
-// One CTA per (sample, channel): the N accumulators live in shared memory, a thread owns a
-// centre n, sums its own term over j and scatters the neighbour terms with shared-memory
-// atomics (random targets: few conflicts); the upstream gradient -- again the only large
-// stream -- is read once.  Summation order of the scatter is not fixed (as in the reference's
-// index backward), the result differs run to run only in the last bits.
+// One CTA per (sample, channel): the N accumulators live in shared memory.  Threads walk the
+// (n, j) slots in lane-linear order, so the upstream gradient -- again the only large stream,
+// read once -- and the indices arrive as fully coalesced 16-byte loads; own terms and
+// neighbour terms both go through shared-memory atomics.  Summation order of the scatter is
+// not fixed (as in the reference's index backward): results differ run to run in the last bits.
+template <int VEC>
 __global__ void __launch_bounds__(kEdgeThreads)
 edge_feature_bwd_kernel(const float *__restrict__ g, const int32_t *__restrict__ idx, int C, int N, int k, int nblocks,
                         int ops, float *__restrict__ gx) {
@@ -82,43 +92,39 @@ edge_feature_bwd_kernel(const float *__restrict__ g, const int32_t *__restrict__
     for (int i = threadIdx.x; i < N; i += kEdgeThreads) acc[i] = 0.f;
     __syncthreads();
     const int32_t *ib = idx + (size_t)b * NK;
-    const bool vec = (k & 3) == 0;
-    for (int n = threadIdx.x; n < N; n += kEdgeThreads) {
-        float own = 0.f;
-        if (vec) {
-            for (int j = 0; j < k; j += 4) {
-                const int4 mv = *reinterpret_cast<const int4 *>(ib + (size_t)n * k + j);
-                float sn[4] = {0.f, 0.f, 0.f, 0.f};
-                for (int q = 0; q < nblocks; ++q) {
-                    const int op = (ops >> (2 * q)) & 3;
-                    const float4 gv = __ldcs(reinterpret_cast<const float4 *>(
-                        g + (((size_t)b * nblocks + q) * C + c) * NK + (size_t)n * k + j));
-                    const float ga[4] = {gv.x, gv.y, gv.z, gv.w};
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        if (op != PCD_EDGE_CENTER) sn[i] += ga[i];
-                        if (op == PCD_EDGE_CENTER) own += ga[i];
-                        if (op == PCD_EDGE_DIFF) own -= ga[i];
-                    }
-                }
-                atomicAdd(&acc[mv.x], sn[0]); atomicAdd(&acc[mv.y], sn[1]);
-                atomicAdd(&acc[mv.z], sn[2]); atomicAdd(&acc[mv.w], sn[3]);
-            }
+    const long long nslots = NK / VEC;
+    for (long long sl = threadIdx.x; sl < nslots; sl += kEdgeThreads) {
+        const long long e0 = sl * VEC;
+        int m[VEC];
+        if (VEC == 4) {
+            const int4 v = *reinterpret_cast<const int4 *>(ib + e0);
+            m[0] = v.x; m[1 % VEC] = v.y; m[2 % VEC] = v.z; m[3 % VEC] = v.w;
         } else {
-            for (int j = 0; j < k; ++j) {
-                const int m = ib[(size_t)n * k + j];
-                float sn = 0.f;
-                for (int q = 0; q < nblocks; ++q) {
-                    const int op = (ops >> (2 * q)) & 3;
-                    const float gv = __ldcs(g + (((size_t)b * nblocks + q) * C + c) * NK + (size_t)n * k + j);
-                    if (op != PCD_EDGE_CENTER) sn += gv;
-                    if (op == PCD_EDGE_CENTER) own += gv;
-                    if (op == PCD_EDGE_DIFF) own -= gv;
-                }
-                atomicAdd(&acc[m], sn);
+            m[0] = ib[e0];
+        }
+        float sn[VEC], own = 0.f;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) sn[i] = 0.f;
+        for (int q = 0; q < nblocks; ++q) {
+            const int op = (ops >> (2 * q)) & 3;
+            const float *gp = g + (((size_t)b * nblocks + q) * C + c) * NK + e0;
+            float ga[VEC];
+            if (VEC == 4) {
+                const float4 gv = __ldcs(reinterpret_cast<const float4 *>(gp));
+                ga[0] = gv.x; ga[1 % VEC] = gv.y; ga[2 % VEC] = gv.z; ga[3 % VEC] = gv.w;
+            } else {
+                ga[0] = __ldcs(gp);
+            }
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                if (op != PCD_EDGE_CENTER) sn[i] += ga[i];
+                if (op == PCD_EDGE_CENTER) own += ga[i];
+                if (op == PCD_EDGE_DIFF) own -= ga[i];
             }
         }
-        atomicAdd(&acc[n], own);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) atomicAdd(&acc[m[i]], sn[i]);
+        atomicAdd(&acc[(int)(e0 / k)], own);
     }
     __syncthreads();
     float *dst = gx + ((size_t)b * C + c) * N;
@@ -248,20 +254,38 @@ extern "C" int pcd_edge_feature_forward(const float *x, const int32_t *idx, int 
     }
     cudaStream_t st = (cudaStream_t)stream;
     const long long NK = (long long)N * k;
-    const int CG = C < 8 ? C : 8;
+    if ((size_t)N * sizeof(float) > 200 * 1024) {
+        set_error("pcd_edge_feature_forward: N=%d exceeds the shared-memory row staging (N <= 51200)", N);
+        return PCD_ERR_UNSUPPORTED;
+    }
+    // channel group: as many rows of N floats as fit 64 KB of shared memory (at least one, at most 16)
+    int CG = kEdgeSmemFloats / N;
+    if (CG < 1) CG = 1;
+    if (CG > 16) CG = 16;
+    if (CG > C) CG = C;
     const int cgroups = (C + CG - 1) / CG;
     if (cgroups > 65535) {
         set_error("pcd_edge_feature_forward: C=%d too large", C);
         return PCD_ERR_UNSUPPORTED;
     }
+    const size_t smem = (size_t)CG * N * sizeof(float);
     const bool vec = (k & 3) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)idx & 15) == 0;
-    if (vec) {
-        const dim3 grid((unsigned)((NK / 4 + kEdgeThreads - 1) / kEdgeThreads), cgroups, B);
-        edge_feature_fwd_kernel<4><<<grid, kEdgeThreads, 0, st>>>(x, idx, C, N, k, nblocks, packed, CG, out);
-    } else {
-        const dim3 grid((unsigned)((NK + kEdgeThreads - 1) / kEdgeThreads), cgroups, B);
-        edge_feature_fwd_kernel<1><<<grid, kEdgeThreads, 0, st>>>(x, idx, C, N, k, nblocks, packed, CG, out);
+    const long long nslots = vec ? NK / 4 : NK;
+    // slices: enough CTAs for ~6 waves of 3 resident CTAs per SM, at least 4 slots per thread
+    long long slices = (148LL * 3 * 6 + (long long)B * cgroups - 1) / ((long long)B * cgroups);
+    const long long max_slices = (nslots + 4 * kEdgeThreads - 1) / (4 * kEdgeThreads);
+    if (slices > max_slices) slices = max_slices;
+    if (slices < 1) slices = 1;
+    const long long sps = (nslots + slices - 1) / slices;
+    const dim3 grid((unsigned)((nslots + sps - 1) / sps), cgroups, B);
+    static size_t smem_set[2] = {0, 0};
+    if (smem > 48 * 1024 && smem > smem_set[vec]) {
+        if (vec) PCD_CUDA_CHECK(cudaFuncSetAttribute(edge_feature_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else PCD_CUDA_CHECK(cudaFuncSetAttribute(edge_feature_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set[vec] = smem;
     }
+    if (vec) edge_feature_fwd_kernel<4><<<grid, kEdgeThreads, smem, st>>>(x, idx, C, N, k, nblocks, packed, CG, sps, out);
+    else edge_feature_fwd_kernel<1><<<grid, kEdgeThreads, smem, st>>>(x, idx, C, N, k, nblocks, packed, CG, sps, out);
     PCD_CUDA_CHECK(cudaGetLastError());
     return PCD_OK;
 }
@@ -283,12 +307,15 @@ extern "C" int pcd_edge_feature_backward(const float *g, const int32_t *idx, int
         return PCD_ERR_ARG;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
-        PCD_CUDA_CHECK(cudaFuncSetAttribute(edge_feature_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
+    const bool vec = (k & 3) == 0;
+    static size_t smem_set[2] = {0, 0};
+    if (smem > 48 * 1024 && smem > smem_set[vec]) {
+        if (vec) PCD_CUDA_CHECK(cudaFuncSetAttribute(edge_feature_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else PCD_CUDA_CHECK(cudaFuncSetAttribute(edge_feature_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set[vec] = smem;
     }
-    edge_feature_bwd_kernel<<<dim3(C, B), kEdgeThreads, smem, st>>>(g, idx, C, N, k, nblocks, packed, gx);
+    if (vec) edge_feature_bwd_kernel<4><<<dim3(C, B), kEdgeThreads, smem, st>>>(g, idx, C, N, k, nblocks, packed, gx);
+    else edge_feature_bwd_kernel<1><<<dim3(C, B), kEdgeThreads, smem, st>>>(g, idx, C, N, k, nblocks, packed, gx);
     PCD_CUDA_CHECK(cudaGetLastError());
     return PCD_OK;
 }
