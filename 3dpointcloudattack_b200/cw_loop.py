@@ -51,6 +51,32 @@ class ClipPointsLinf(nn.Module):
         return pc
 
 
+class ProjectInnerClipLinf(nn.Module):
+    """attack/CW/CW_utils/clip_utils.py:59-136: points pushed inside the surface (negative offset
+    along the normal) are projected back onto it, then the per-point L2 clip; in place, batch safe
+    (the reference's dim-less torch.cross picks the wrong axis for B == 3)."""
+
+    def __init__(self, budget):
+        super().__init__()
+        self.clip_linf = ClipPointsLinf(budget)
+
+    @torch.no_grad()
+    def forward(self, pc, ori_pc, normal=None):
+        if normal is not None:
+            diff = pc - ori_pc
+            inner = torch.sum(diff * normal, dim=1) < 0.                      # [B, K]
+            vng = torch.cross(normal, diff, dim=1)
+            vng_norm = torch.sum(vng ** 2, dim=1) ** 0.5
+            vref = torch.cross(vng, normal, dim=1)
+            vref_norm = torch.sum(vref ** 2, dim=1) ** 0.5
+            diff_proj = diff * vref / (vref_norm[:, None, :] + 1e-9)
+            opposite = inner & (vng_norm < 1e-6)
+            diff_proj = torch.where(opposite[:, None, :], torch.zeros_like(diff_proj), diff_proj)
+            diff = torch.where(inner[:, None, :], diff_proj, diff)
+            pc.copy_(ori_pc + diff)
+        return self.clip_linf(pc, ori_pc)
+
+
 class CWAttack:
     def __init__(self, model, adv_func, dist_func, attack_lr=1e-2, init_weight=10., max_weight=80.,
                  binary_step=10, num_iter=500, clip_func=None, global_batch=None, use_graph=False):
@@ -91,8 +117,10 @@ class CWAttack:
             self.clip_func(adv.data, ori)
         st["loss"].copy_(loss.detach())
 
-    def attack(self, data, target, seed=0, first_sample=0):
-        """data [B, K, 3], target [B] -> (o_bestdist[B], o_bestattack[B,K,3], success mask[B])."""
+    def attack(self, data, target, seed=0, first_sample=0, init_noise=None):
+        """data [B, K, 3], target [B] -> (o_bestdist[B], o_bestattack[B,K,3], success mask[B]).
+        init_noise [binary_step, B, 3, K] replaces the per-sample generator draws (parity tests
+        replay the reference's own torch.randn draws, CW_attack.py:94)."""
         from .sharding import per_sample_noise
         dev = data.device
         if dev.type != "cuda":
@@ -116,7 +144,10 @@ class CWAttack:
         graph = None
         spans = []
         for step in range(self.binary_step):
-            noise = per_sample_noise((3, K), first_sample, B, 1e-7, seed=seed + step, device=dev)
+            if init_noise is not None:
+                noise = init_noise[step].to(dev) * 1e-7
+            else:
+                noise = per_sample_noise((3, K), first_sample, B, 1e-7, seed=seed + step, device=dev)
             with torch.no_grad():
                 st["adv"].copy_(ori + noise)
                 st["bestdist"].fill_(1e10); st["bestscore"].fill_(-1)
@@ -148,6 +179,10 @@ class CWAttack:
         return st["o_bestdist"], st["o_bestattack"].transpose(1, 2).contiguous(), ~fail
 
     def _capture(self, st, warmup=3):
+        """Capture one iteration.  The warm-up iterations run on the real state tensors (the graph must
+        record their addresses), so the state -- cloud, trackers, Adam moments and step count -- is
+        saved before and restored after: replaying num_iter times is exactly num_iter iterations."""
+        saved = {k: v.detach().clone() for k, v in st.items() if isinstance(v, torch.Tensor)}
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
@@ -159,4 +194,80 @@ class CWAttack:
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=side):
             self._iteration(st)
+        with torch.no_grad():
+            for k, v in saved.items():
+                st[k].copy_(v)
+            for state in st["opt"].state.values():
+                for t in state.values():
+                    if isinstance(t, torch.Tensor):
+                        t.zero_()
+            if st["adv"].grad is not None:
+                st["adv"].grad.zero_()
         return g
+
+
+class KNNAttack:
+    """Device-resident, batch-safe restatement of the kNN attack loop (attack/KNN/KNN_attack.py:56-246):
+    one long Adam loop, loss = adv_func(logits).mean() + dist_func(adv, ori).mean() * K, then
+    clip_func(adv, ori, normal) after every step (normal = the cloud itself when the input has
+    only xyz, KNN_attack.py:70-74).  `dist_func(adv[B,K,3], ori[B,K,3], weights=None,
+    batch_avg=False) -> [B]` is this package's ChamferDist / ChamferkNNDist."""
+
+    def __init__(self, model, adv_func, dist_func, clip_func, attack_lr=1e-3, num_iter=2500, global_batch=None,
+                 use_graph=False):
+        self.model = model.eval()
+        for p in self.model.parameters():
+            p.requires_grad_(False)
+        self.adv_func, self.dist_func, self.clip_func = adv_func, dist_func, clip_func
+        self.attack_lr, self.num_iter = attack_lr, num_iter
+        self.global_batch, self.use_graph = global_batch, use_graph
+        self.loop_ms = 0.0
+
+    def _iteration(self, st):
+        adv, ori = st["adv"], st["ori"]
+        K = adv.shape[2]
+        out = self.model(adv)
+        logits = out[0] if isinstance(out, tuple) else out
+        denom = float(self.global_batch or adv.shape[0])
+        adv_loss = self.adv_func(logits, st["target"], reduce=False).sum() / denom
+        dist_loss = self.dist_func(adv.transpose(1, 2), ori.transpose(1, 2), None, batch_avg=False).sum() / denom * K
+        loss = adv_loss + dist_loss
+        st["opt"].zero_grad(set_to_none=False)
+        loss.backward()
+        st["opt"].step()
+        self.clip_func(adv.data, ori, st["normal"])
+        st["loss"].copy_(loss.detach())
+
+    def attack(self, data, target, seed=0, first_sample=0, init_noise=None):
+        """data [B, K, 3] (or [B, K, 6] with normals), target [B] -> (adv[B,K,3], success mask[B])."""
+        from .sharding import per_sample_noise
+        dev = data.device
+        if dev.type != "cuda":
+            raise RuntimeError("KNNAttack runs on CUDA only")
+        B, K = data.shape[:2]
+        full = data.float().transpose(1, 2).contiguous().detach()
+        ori = full[:, :3].contiguous()
+        normal = ori if full.shape[1] == 3 else full[:, 3:].contiguous()
+        target = target.long().to(dev)
+        noise = init_noise.to(dev) * 1e-7 if init_noise is not None else \
+            per_sample_noise((3, K), first_sample, B, 1e-7, seed=seed, device=dev)
+        st = {"ori": ori, "normal": normal, "target": target, "loss": torch.zeros((), device=dev),
+              "adv": (ori + noise).requires_grad_(True)}
+        st["opt"] = torch.optim.Adam([st["adv"]], lr=self.attack_lr, weight_decay=0., capturable=self.use_graph, foreach=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if self.use_graph:
+            graph = CWAttack._capture(self, st)
+            e0.record()
+            for _ in range(self.num_iter):
+                graph.replay()
+        else:
+            e0.record()
+            for _ in range(self.num_iter):
+                self._iteration(st)
+        e1.record()
+        with torch.no_grad():
+            out = self.model(st["adv"])
+            pred = torch.argmax(out[0] if isinstance(out, tuple) else out, dim=-1)
+        torch.cuda.synchronize(dev)
+        self.loop_ms = e0.elapsed_time(e1)
+        return st["adv"].detach().transpose(1, 2).contiguous(), pred != target

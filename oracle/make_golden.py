@@ -141,9 +141,66 @@ def graph_and_sampling():
     save("f_graph_sampling", adv=adv, adv_cf=adv_cf, **out)
 
 
+def attack_loops():
+    """L4: the reference's own CW and kNN attack loops, unmodified, on CPU at B=1
+    (their only supported batch size) against tests/tiny_victim.TinyVictim."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
+    import tiny_victim
+    from attack.CW.CW_attack import CW
+    from attack.KNN.KNN_attack import CWKNN
+    from attack.CW.CW_utils import dist_utils as DU, adv_utils as AU, clip_utils as CU
+    victim = tiny_victim.make(seed=3)
+    data = face_fixture(256, 5)[None]                                   # [1,256,3]
+    with torch.no_grad():
+        label = victim(t(data).transpose(1, 2))[0].argmax(1)
+    out = dict(tiny_victim.state_to_npz(victim), data=data, label=n(label))
+    noises = []
+    real_randn = torch.randn
+
+    def recording_randn(*a, **k):
+        # The loops start from ori + 1e-7 * randn (CW_attack.py:94): the first Adam steps (update ~ lr * g/|g|)
+        # are then decided by gradients at fp32 rounding level, and ANY two correct implementations (the
+        # reference on CPU vs. on GPU included) part ways by +-lr per point.  The draws handed to the
+        # reference are scaled by 1e4 (start = ori + 1e-3 * randn) so that the comparison is well conditioned;
+        # the loop code itself runs unmodified.
+        v = real_randn(*a, **k) * 1e4
+        noises.append(n(v))
+        return v
+
+    tr = lambda f: (lambda a, o, w: f(a.transpose(1, 2).contiguous(), o.transpose(1, 2).contiguous(), w))
+    cases = {
+        "cw_chamfer": DU.ChamferDist(method="adv2ori"),
+        "cw_hausdorff": DU.HausdorffDist(method="ori2adv"),
+    }
+    torch.randn = recording_randn
+    try:
+        for tag, df in cases.items():
+            noises.clear()
+            torch.manual_seed(11)
+            atk = CW(victim, victim, AU.UntargetedLogitsAdvLoss(kappa=5.), CU.ClipPointsLinf(budget=0.18), tr(df),
+                     attack_lr=1e-2, init_weight=10., max_weight=80., binary_step=3, num_iter=12)
+            bestdist, bestattack, _ = atk.attack(t(data), label.clone())
+            out.update({tag + "_bestdist": np.asarray(bestdist), tag + "_bestattack": np.asarray(bestattack, np.float32),
+                        tag + "_noise": np.stack(noises)})
+        # kNN attack (attack/KNN/KNN_attack.py): one long loop, ChamferkNNDist, ProjectInnerClipLinf
+        noises.clear()
+        torch.manual_seed(12)
+        katk = CWKNN(victim, victim, victim, victim, victim, victim, AU.UntargetedLogitsAdvLoss(kappa=15.),
+                     DU.ChamferkNNDist(chamfer_method="adv2ori", knn_k=5, knn_alpha=1.05, chamfer_weight=5., knn_weight=3.),
+                     CU.ProjectInnerClipLinf(budget=0.1), attack_lr=1e-3, num_iter=20)
+        adv, _ = katk.attack(t(data), label.clone())
+        out.update(knn_adv=np.asarray(adv, np.float32), knn_noise=np.stack(noises))
+    finally:
+        torch.randn = real_randn
+    save("l4_attack_loops", **out)
+
+
 def main():
     torch.set_num_threads(1)
     _prepare_reference()
+    if "--loops" in sys.argv:
+        attack_loops()
+        return
     if "--graph" in sys.argv:          # only the section added after the first fixtures were committed
         graph_and_sampling()
         return
