@@ -54,6 +54,8 @@ def install(modules=None, strict=False):
         for n in names:
             if hasattr(ours, n):
                 setattr(ref, n, getattr(ours, n))
+        if name in ("model.pointnet2_utils", "pointnet.pointnet2_utils") and hasattr(ref, "PointNetFeaturePropagation"):
+            ref.PointNetFeaturePropagation.forward = pointnet2_utils.feature_propagation_forward    # 3-NN interpolation :273-311
         if name == "model.curvenet_util":
             ref.query_ball_point = pointnet2_utils.query_ball_point          # copy at curvenet_util.py:93-113
             ref.LPFA.group_feature = curvenet_util.group_feature             # method :206-236

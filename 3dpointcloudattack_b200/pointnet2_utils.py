@@ -58,3 +58,38 @@ def sample_and_group(npoint, radius, nsample, xyz, points, returnfps=False):
     if returnfps:
         return new_xyz, new_points, grouped_xyz, fps_idx
     return new_xyz, new_points
+
+
+def three_nn_interpolate(xyz1, xyz2, points2):
+    """The 3-NN inverse-distance interpolation inside PointNetFeaturePropagation.forward (:289-300):
+    xyz1 [B,N,3] (targets), xyz2 [B,S,3] (sources), points2 [B,S,D] -> [B,N,D].  The reference builds
+    the [B,N,S] matrix with square_distance and fully sorts every row to take three columns; here the
+    k-NN select kernel returns the three smallest (same arithmetic: FORM_ROW_COL, ascending,
+    lowest index on ties) and their gradient w.r.t. both clouds."""
+    B, N, _ = xyz1.shape
+    S = xyz2.shape[1]
+    if S == 1:
+        return points2.repeat(1, N, 1)
+    dists, idx = F.knn(xyz1, xyz2, 3, form=F.FORM_ROW_COL, norm=F.NORM_MULSUM)
+    dist_recip = 1.0 / (dists + 1e-8)
+    norm = torch.sum(dist_recip, dim=2, keepdim=True)
+    weight = dist_recip / norm
+    return torch.sum(index_points(points2, idx) * weight.view(B, N, 3, 1), dim=2)
+
+
+def feature_propagation_forward(self, xyz1, xyz2, points1, points2):
+    """Replacement body for PointNetFeaturePropagation.forward (:273-311); `self` is the reference's
+    module (mlp_convs / mlp_bns are read from it)."""
+    import torch.nn.functional as nnF
+    xyz1 = xyz1.permute(0, 2, 1)
+    xyz2 = xyz2.permute(0, 2, 1)
+    points2 = points2.permute(0, 2, 1)
+    interpolated = three_nn_interpolate(xyz1, xyz2, points2)
+    if points1 is not None:
+        new_points = torch.cat([points1.permute(0, 2, 1), interpolated], dim=-1)
+    else:
+        new_points = interpolated
+    new_points = new_points.permute(0, 2, 1)
+    for i, conv in enumerate(self.mlp_convs):
+        new_points = nnF.relu(self.mlp_bns[i](conv(new_points)))
+    return new_points

@@ -138,6 +138,15 @@ def graph_and_sampling():
     bq = P2.query_ball_point(0.2, 32, t(adv), P2.index_points(t(adv), fidx))
     out["ball_idx"] = n(bq)
     out["index_points_3d"] = n(P2.index_points(t(adv), bq[:, :64]))
+    # 3-NN inverse-distance interpolation (PointNetFeaturePropagation.forward :289-300), no MLP
+    fp = P2.PointNetFeaturePropagation(in_channel=8, mlp=[])
+    src = ori[:, ::4][:, :200].copy()                                    # [2,200,3] sources (the unperturbed cloud: no coincident pairs)
+    feat = rs.randn(2, 8, 200).astype(np.float32)
+    x1, x2, f2 = t(np.ascontiguousarray(adv[:, :600].transpose(0, 2, 1)), True), t(np.ascontiguousarray(src.transpose(0, 2, 1)), True), t(feat, True)
+    o = fp(x1, x2, None, f2)                                             # [2,8,600]
+    gw = rs.randn(*o.shape).astype(np.float32)
+    (o * t(gw)).sum().backward()
+    out.update(fp_xyz1=n(x1), fp_xyz2=n(x2), fp_feat=feat, fp_out=n(o), fp_gw=gw, fp_g1=n(x1.grad), fp_g2=n(x2.grad), fp_gf=n(f2.grad))
     save("f_graph_sampling", adv=adv, adv_cf=adv_cf, **out)
 
 

@@ -397,3 +397,13 @@ def index_points(points, idx):
     B = points.shape[0]
     bi = np.arange(B).reshape((B,) + (1,) * (idx.ndim - 1))
     return points[bi, idx]
+
+
+def three_nn_interpolate(xyz1, xyz2, points2):
+    """model/pointnet2_utils.py:289-300: xyz1[B,N,3], xyz2[B,S,3], points2[B,S,D] -> [B,N,D]
+    (square_distance = FORM_ROW_COL, three smallest ascending, 1/(d+1e-8) weights)."""
+    xyz1, xyz2, points2 = _f32(xyz1), _f32(xyz2), _f32(points2)
+    d, i = knn(FORM_ROW_COL, xyz1, xyz2, norms(NORM_MULSUM, xyz1), norms(NORM_MULSUM, xyz2), 3)
+    recip = np.float32(1.0) / (d + np.float32(1e-8))
+    w = recip / recip.sum(2, keepdims=True, dtype=np.float32)
+    return (index_points(points2, i.astype(np.int64)) * w[..., None]).sum(2, dtype=np.float32), d, i

@@ -521,6 +521,16 @@ def test_f_farthest_point_sample_vs_reference():
     assert np.array_equal(npy(pcd.pointnet2_utils.index_points(adv, bq[:, :64])), g["index_points_3d"])
 
 
+def test_f_three_nn_interpolation_vs_reference():
+    g = load_golden("f_graph_sampling")
+    x1, x2, f2 = cu(g["fp_xyz1"], True), cu(g["fp_xyz2"], True), cu(g["fp_feat"], True)
+    out = pcd.pointnet2_utils.three_nn_interpolate(x1.permute(0, 2, 1), x2.permute(0, 2, 1), f2.permute(0, 2, 1)).permute(0, 2, 1)
+    np.testing.assert_allclose(npy(out), g["fp_out"], rtol=1e-5, atol=1e-6)
+    (out * cu(g["fp_gw"])).sum().backward()
+    assert rel_inf(g["fp_gf"], npy(f2.grad)) < RTOL
+    assert rel_inf(g["fp_g1"], npy(x1.grad)) < 1e-4 and rel_inf(g["fp_g2"], npy(x2.grad)) < 1e-4     # d/dd of 1/(d+1e-8): cancellation-limited in fp32
+
+
 @pytest.mark.parametrize("N,npoint", [(100, 100), (257, 64), (513, 128), (1500, 512), (3000, 256), (4096, 1024),
                                       (6000, 128), (10000, 64)])
 def test_f_farthest_point_sample_every_variant(N, npoint):

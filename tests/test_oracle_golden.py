@@ -194,3 +194,11 @@ def test_f_farthest_point_sample_bit_exact():
     assert np.array_equal(O.farthest_point_sample(g["adv"][:, :300], 300), g["fps0_all"])
     assert np.array_equal(O.index_points(g["adv"], g["fps_512"]), g["index_points_2d"])
     assert np.array_equal(O.index_points(g["adv"], g["ball_idx"][:, :64]), g["index_points_3d"])
+
+
+def test_f_three_nn_interpolation():
+    g = load_golden("f_graph_sampling")
+    x1, x2 = g["fp_xyz1"].transpose(0, 2, 1), g["fp_xyz2"].transpose(0, 2, 1)
+    out, d, i = O.three_nn_interpolate(x1, x2, g["fp_feat"].transpose(0, 2, 1))
+    assert d.min() > 1e-6                                           # well conditioned: no coincident pairs
+    np.testing.assert_allclose(out.transpose(0, 2, 1), g["fp_out"], rtol=1e-5, atol=1e-6)
