@@ -344,7 +344,8 @@ __device__ __forceinline__ float apply_transform(int transform, float v) {
     return transform == PCD_VALUE_SQRT_CLAMP ? sqrtf(fmaxf(v, 0.0f)) : v;
 }
 
-// Eight lanes per point (coalesced 128-byte reads of the winning chunk).  A row point
+// Four lanes per point (eight independent 16-byte loads per lane; 2x the points in flight of the
+// eight-lane version, which was bound by the key -> chunk load round trips).  A row point
 // re-evaluates the 32 columns of its winning chunk, a column point the R rows of its winning
 // lane -- with the sweep's exact arithmetic -- and takes the lowest index whose distance equals
 // the minimum.  The block then reduces its 128 values (sum, max, first argmax) in a fixed
@@ -368,8 +369,8 @@ nn1_fixup_kernel(const float4 *__restrict__ rowpk, const float4 *__restrict__ co
                  float *__restrict__ row_min, int32_t *__restrict__ row_arg,
                  float *__restrict__ col_min, int32_t *__restrict__ col_arg) {
     const int b = blockIdx.y;
-    const int l8 = threadIdx.x & 7;
-    int p = blockIdx.x * 32 + (threadIdx.x >> 3);           // 32 points per block, rows first then columns
+    const int l4 = threadIdx.x & 3;
+    int p = blockIdx.x * 64 + (threadIdx.x >> 2);           // 64 points per block, rows first then columns
     const bool is_col = p >= N;
     if (is_col) p -= N;
     const bool live = p < (is_col ? M : N);
@@ -382,13 +383,17 @@ nn1_fixup_kernel(const float4 *__restrict__ rowpk, const float4 *__restrict__ co
             const int j0 = (int)(uint32_t)key * kColChunk;
             const float4 q = __ldg(&rowpk[(size_t)b * Npad + p]);
             const float4 *rec = colpk + (size_t)b * Mpad + j0;
-            // lane l8 takes records l8 and l8+8 (columns 2*l8, 2*l8+1, 16+2*l8, 17+2*l8)
-            const float4 a0 = __ldg(&rec[2 * l8]), c0 = __ldg(&rec[2 * l8 + 1]);
-            const float4 a1 = __ldg(&rec[16 + 2 * l8]), c1 = __ldg(&rec[17 + 2 * l8]);
-            if (pair_dist_scalar<FORM>(q.x, q.y, q.z, q.w, a1.y, a1.w, c1.y, c1.w) == v) arg = j0 + 17 + 2 * l8;
-            if (pair_dist_scalar<FORM>(q.x, q.y, q.z, q.w, a1.x, a1.z, c1.x, c1.z) == v) arg = j0 + 16 + 2 * l8;
-            if (pair_dist_scalar<FORM>(q.x, q.y, q.z, q.w, a0.y, a0.w, c0.y, c0.w) == v) arg = j0 + 1 + 2 * l8;
-            if (pair_dist_scalar<FORM>(q.x, q.y, q.z, q.w, a0.x, a0.z, c0.x, c0.z) == v) arg = j0 + 2 * l8;
+            // lane l4 takes the pair records l4, l4+4, l4+8, l4+12 (columns 2 rec, 2 rec + 1): eight
+            // independent 16-byte loads in flight per lane, highest column first so the lowest match wins
+            float4 a[4], c[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { a[t] = __ldg(&rec[2 * (l4 + 4 * t)]); c[t] = __ldg(&rec[2 * (l4 + 4 * t) + 1]); }
+#pragma unroll
+            for (int t = 3; t >= 0; --t) {
+                const int j = j0 + 2 * (l4 + 4 * t);
+                if (pair_dist_scalar<FORM>(q.x, q.y, q.z, q.w, a[t].y, a[t].w, c[t].y, c[t].w) == v) arg = j + 1;
+                if (pair_dist_scalar<FORM>(q.x, q.y, q.z, q.w, a[t].x, a[t].z, c[t].x, c[t].z) == v) arg = j;
+            }
         } else {
             const unsigned long long key = colkey[(size_t)b * Mpad + p];
             v = ordered_to_f32((uint32_t)(key >> 32));
@@ -397,20 +402,18 @@ nn1_fixup_kernel(const float4 *__restrict__ rowpk, const float4 *__restrict__ co
             const float *rec = reinterpret_cast<const float *>(colpk) + ((size_t)b * Mpad + (p & ~1)) * 4 + (p & 1);
             const float cx = rec[0], cy = rec[2], cz = rec[4], cn = rec[6];
             const float4 *rq = rowpk + (size_t)b * Npad + i0;
-            // lane l8 takes rows l8 and l8+8 of the winning lane's R rows (R = 2, 4, 8 or 16)
-            if (l8 + 8 < R) {
-                const float4 q = __ldg(&rq[l8 + 8]);
-                if (pair_dist_scalar<FORM>(q.x, q.y, q.z, q.w, cx, cy, cz, cn) == v) arg = i0 + l8 + 8;
-            }
-            if (l8 < R) {
-                const float4 q = __ldg(&rq[l8]);
-                if (pair_dist_scalar<FORM>(q.x, q.y, q.z, q.w, cx, cy, cz, cn) == v) arg = i0 + l8;
-            }
+            // lane l4 takes rows l4, l4+4, l4+8, l4+12 of the winning lane's R rows (R = 2, 4, 8 or 16)
+            float4 q[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) q[t] = (l4 + 4 * t < R) ? __ldg(&rq[l4 + 4 * t]) : make_float4(0.f, 0.f, 0.f, __int_as_float(0x7fc00000));
+#pragma unroll
+            for (int t = 3; t >= 0; --t)
+                if (l4 + 4 * t < R && pair_dist_scalar<FORM>(q[t].x, q[t].y, q[t].z, q[t].w, cx, cy, cz, cn) == v) arg = i0 + l4 + 4 * t;
         }
     }
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) arg = min(arg, __shfl_xor_sync(0xffffffffu, arg, o, 8));   // all lanes take part
-    if (live && l8 == 0) {
+    for (int o = 2; o > 0; o >>= 1) arg = min(arg, __shfl_xor_sync(0xffffffffu, arg, o, 4));   // all lanes take part
+    if (live && l4 == 0) {
         if (arg == 0x7fffffff) arg = 0;        // cannot happen: the tagged chunk holds the minimum
         const float val = apply_transform(transform, v);
         if (!is_col) { row_min[(size_t)b * N + p] = val; row_arg[(size_t)b * N + p] = arg; }
@@ -727,7 +730,7 @@ extern "C" int pcd_nn1_forward(const float *rows, int64_t r_sb, int64_t r_sp, in
         if (g_sweep_ev1) PCD_CUDA_CHECK(cudaEventRecord(g_sweep_ev1, st));
     }
     {
-        const dim3 grid((N + M + 31) / 32 + 1, B);
+        const dim3 grid((N + M + 63) / 64 + 1, B);
         const float4 *colpk4 = (const float4 *)colpk;
 #define PCD_LAUNCH_FIXUP(F)                                                                                    \
     nn1_fixup_kernel<F><<<grid, 256, 0, st>>>(rowpk, colpk4, rowkey, colkey, N, M, L.Npad, L.Mpad, R, transform, \
