@@ -44,28 +44,22 @@ constexpr int kSweepThreads = kSweepWarps * 32;
 constexpr int kColChunk = 32;     // columns per row-direction tag
 constexpr int kMaxColTile = 256;  // columns per TMA stage (16 B each)
 constexpr int kRowPadUnit = 2048; // rows are padded to a multiple of 128*R, R <= 16
-constexpr int kFixThreads = 128;  // points per fix-up block (8 lanes each)
-constexpr int kMaxFixBlocks = 4096;
 
 struct Nn1Layout {
-    int Npad, Mpad, nblk_r, nblk_c;
-    size_t rowpk, rowpp, colpk, rowkey, colkey, partial, counter, total;
+    int Npad, Mpad;
+    size_t rowpk, rowpp, colpk, rowkey, colkey, total;
 };
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static Nn1Layout nn1_layout(int B, int N, int M) {
     Nn1Layout L;
     L.Npad = (int)align_up((size_t)N, kRowPadUnit);
     L.Mpad = (int)align_up((size_t)M, kMaxColTile);
-    L.nblk_r = (N + kFixThreads - 1) / kFixThreads;
-    L.nblk_c = (M + kFixThreads - 1) / kFixThreads;
     size_t off = 0;
     L.rowpk = off; off = align_up(off + (size_t)B * L.Npad * 16, 256);
     L.rowpp = off; off = align_up(off + (size_t)B * L.Npad * 16, 256);   // the same records in sweep (slot) order
     L.colpk = off; off = align_up(off + (size_t)B * L.Mpad * 16 + 64, 256);   // +64: the sweep prefetches one record past a tile
     L.rowkey = off; off = align_up(off + (size_t)B * L.Npad * 8, 256);
     L.colkey = off; off = align_up(off + (size_t)B * L.Mpad * 8, 256);
-    L.partial = off; off = align_up(off + (size_t)B * (L.nblk_r + L.nblk_c) * 16, 256);
-    L.counter = off; off = align_up(off + (size_t)B * 2 * 4, 256);
     L.total = off;
     return L;
 }
@@ -89,13 +83,11 @@ __global__ void nn1_prep_kernel(const float *__restrict__ rows, int64_t r_sb, in
                                 const float *__restrict__ cols, int64_t c_sb, int64_t c_sp, int64_t c_sc,
                                 int B, int N, int M, int Npad, int Mpad, int R, int norm_kind, int swap_norms,
                                 float4 *__restrict__ rowpk, float4 *__restrict__ rowpp, float *__restrict__ colpk,
-                                unsigned long long *__restrict__ rowkey, unsigned long long *__restrict__ colkey,
-                                unsigned int *__restrict__ counter) {
+                                unsigned long long *__restrict__ rowkey, unsigned long long *__restrict__ colkey) {
     const long long per_b = (long long)Npad + Mpad;
     const long long total = per_b * B;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
          t += (long long)gridDim.x * blockDim.x) {
-        if (t < 2 * B) counter[t] = 0u;
         const int b = (int)(t / per_b);
         const int p = (int)(t - (long long)b * per_b);
         if (p < Npad) {
@@ -348,9 +340,8 @@ __device__ __forceinline__ float apply_transform(int transform, float v) {
 // eight-lane version, which was bound by the key -> chunk load round trips).  A row point
 // re-evaluates the 32 columns of its winning chunk, a column point the R rows of its winning
 // lane -- with the sweep's exact arithmetic -- and takes the lowest index whose distance equals
-// the minimum.  The block then reduces its 128 values (sum, max, first argmax) in a fixed
-// order; the last block of each (sample, side) folds the block partials in a fixed order too,
-// so the statistics are run-to-run deterministic.
+// the minimum.  The per-sample statistics (sum, max, first argmax) are reduced by
+// nn1_reduce_kernel in a fixed order, so they are run-to-run deterministic.
 __device__ __forceinline__ void reduce_smf(float &s, float &mx, int &am) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -704,8 +695,6 @@ extern "C" int pcd_nn1_forward(const float *rows, int64_t r_sb, int64_t r_sp, in
     float *colpk = (float *)(ws + L.colpk);
     unsigned long long *rowkey = (unsigned long long *)(ws + L.rowkey);
     unsigned long long *colkey = (unsigned long long *)(ws + L.colkey);
-    float4 *partial = (float4 *)(ws + L.partial);
-    unsigned int *counter = (unsigned int *)(ws + L.counter);
 
     int R, mt;
     choose_tiling(B, N, M, sms, &R, &mt);
@@ -714,7 +703,7 @@ extern "C" int pcd_nn1_forward(const float *rows, int64_t r_sb, int64_t r_sp, in
         const long long total = (long long)B * (L.Npad + L.Mpad);
         const int grid = (int)((total + 255) / 256 < (long long)sms * 8 ? (total + 255) / 256 : (long long)sms * 8);
         nn1_prep_kernel<<<grid, 256, 0, st>>>(rows, r_sb, r_sp, r_sc, cols, c_sb, c_sp, c_sc, B, N, M, L.Npad,
-                                              L.Mpad, R, norm_kind, swap_norms, rowpk, rowpp, colpk, rowkey, colkey, counter);
+                                              L.Mpad, R, norm_kind, swap_norms, rowpk, rowpp, colpk, rowkey, colkey);
         PCD_CUDA_CHECK(cudaGetLastError());
     }
     {

@@ -43,3 +43,52 @@ class PointNetVictim(nn.Module):
         x = torch.max(x, 2)[0]
         x = F.relu(self.b4(self.f1(x))); x = F.relu(self.b5(self.drop(self.f2(x))))
         return F.log_softmax(self.f3(x), dim=1), trans, None
+
+
+class DGCNNVictim(nn.Module):
+    """DGCNN classifier with the layer shapes of the reference's model/dgcnn.py:262-328 (four edge
+    convolutions 6->64, 128->64, 128->128, 256->256 with BN + LeakyReLU(0.2) and max over k, 512->emb
+    point-wise layer, max+avg pooling, 2 emb->512->256->classes head), written from the public
+    architecture.  `graph_feature(x[B,C,N], k) -> [B,2C,N,k]` is injected: this package's
+    dgcnn.get_graph_feature or the reference's torch formulation (torch_graph_feature below)."""
+
+    def __init__(self, graph_feature, k=20, emb_dims=1024, num_classes=106, dropout=0.5):
+        super().__init__()
+        self.gf, self.k = graph_feature, k
+        act = lambda: nn.LeakyReLU(negative_slope=0.2)
+        self.conv1 = nn.Sequential(nn.Conv2d(6, 64, 1, bias=False), nn.BatchNorm2d(64), act())
+        self.conv2 = nn.Sequential(nn.Conv2d(128, 64, 1, bias=False), nn.BatchNorm2d(64), act())
+        self.conv3 = nn.Sequential(nn.Conv2d(128, 128, 1, bias=False), nn.BatchNorm2d(128), act())
+        self.conv4 = nn.Sequential(nn.Conv2d(256, 256, 1, bias=False), nn.BatchNorm2d(256), act())
+        self.conv5 = nn.Sequential(nn.Conv1d(512, emb_dims, 1, bias=False), nn.BatchNorm1d(emb_dims), act())
+        self.linear1 = nn.Linear(emb_dims * 2, 512, bias=False)
+        self.bn6, self.dp1 = nn.BatchNorm1d(512), nn.Dropout(dropout)
+        self.linear2 = nn.Linear(512, 256)
+        self.bn7, self.dp2 = nn.BatchNorm1d(256), nn.Dropout(dropout)
+        self.linear3 = nn.Linear(256, num_classes)
+
+    def forward(self, x):
+        B = x.size(0)
+        x1 = self.conv1(self.gf(x, self.k)).max(dim=-1)[0]
+        x2 = self.conv2(self.gf(x1, self.k)).max(dim=-1)[0]
+        x3 = self.conv3(self.gf(x2, self.k)).max(dim=-1)[0]
+        x4 = self.conv4(self.gf(x3, self.k)).max(dim=-1)[0]
+        x = self.conv5(torch.cat((x1, x2, x3, x4), dim=1))
+        x = torch.cat((F.adaptive_max_pool1d(x, 1).view(B, -1), F.adaptive_avg_pool1d(x, 1).view(B, -1)), 1)
+        x = self.dp1(F.leaky_relu(self.bn6(self.linear1(x)), negative_slope=0.2))
+        x = self.dp2(F.leaky_relu(self.bn7(self.linear2(x)), negative_slope=0.2))
+        x = F.log_softmax(self.linear3(x), -1)
+        return x, x, x
+
+
+def torch_graph_feature(x, k):
+    """The reference's formulation (model/dgcnn.py:194-227) with x.device instead of the hard-coded cuda:0."""
+    B, C, N = x.shape
+    inner = -2 * torch.matmul(x.transpose(2, 1), x)
+    xx = torch.sum(x ** 2, dim=1, keepdim=True)
+    idx = (-xx - inner - xx.transpose(2, 1)).topk(k=k, dim=-1)[1]
+    idx = (idx + torch.arange(0, B, device=x.device).view(-1, 1, 1) * N).view(-1)
+    xt = x.transpose(2, 1).contiguous()
+    feature = xt.view(B * N, -1)[idx, :].view(B, N, k, C)
+    xr = xt.view(B, N, 1, C).repeat(1, 1, k, 1)
+    return torch.cat((feature - xr, xr), dim=3).permute(0, 3, 1, 2).contiguous()
