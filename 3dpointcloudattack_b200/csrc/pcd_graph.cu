@@ -124,7 +124,23 @@ edge_feature_bwd_kernel(const float *__restrict__ g, const int32_t *__restrict__
         }
 #pragma unroll
         for (int i = 0; i < VEC; ++i) atomicAdd(&acc[m[i]], sn[i]);
-        atomicAdd(&acc[(int)(e0 / k)], own);
+        // own term: consecutive lanes share the centre n (k / VEC slots each).  Shared-memory float
+        // atomics are compare-and-swap loops, and same-address lanes serialise them, so the lanes of
+        // a run first add up with a segmented shuffle scan and only the run's last lane touches acc[n].
+        // (Batching the loads of several slots per thread ahead of the atomics was measured slower:
+        // the CAS loops are latency bound and want occupancy -- 64 warps/SM -- more than load ILP.)
+        const int n = (int)(e0 / k);
+        const unsigned active = __activemask();
+        const int lane = threadIdx.x & 31;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float up = __shfl_up_sync(active, own, o);
+            const int nup = __shfl_up_sync(active, n, o);
+            if (lane >= o && nup == n) own += up;
+        }
+        const int ndown = __shfl_down_sync(active, n, 1);
+        const bool last = lane == 31 || ndown != n || !((active >> (lane + 1)) & 1u);
+        if (last) atomicAdd(&acc[n], own);
     }
     __syncthreads();
     float *dst = gx + ((size_t)b * C + c) * N;
