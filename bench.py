@@ -342,6 +342,32 @@ def run_ours(args):
     h2d = adv_h.numel() * 4 + ori_h.numel() * 4
     d2h = loss_h.numel() * 4 + grad_h.numel() * 4
 
+    # ---------------- secondary: the per-GPU shard of BASELINE configs[4] (B=512 N=M=16384 over 8 GPUs = 64 per GPU) ----
+    def large_cloud(Bl=64, Nl=16384, reps=3):
+        synth = importlib.import_module("3dpointcloudattack_b200.synth")
+        o_l = synth.face_clouds(4, Nl, seed=4321).to(dev).repeat(Bl // 4, 1, 1).contiguous()
+        a_l = (o_l + SIGMA * torch.randn(o_l.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(7))).requires_grad_(True)
+        ts, sw = [], []
+        for k in range(reps + 1):
+            a_l.grad = None
+            s0, s1, e0, e1 = ev(), ev(), ev(), ev()
+            s0.record(); s1.record()                       # materialise the cudaEvent handles
+            lib.pcd_nn1_set_sweep_events(s0.cuda_event, s1.cuda_event)
+            e0.record()
+            step(a_l, o_l)
+            e1.record()
+            lib.pcd_nn1_set_sweep_events(None, None)
+            torch.cuda.synchronize()
+            if k:
+                ts.append(e0.elapsed_time(e1)); sw.append(s0.elapsed_time(s1))
+        pairs = float(Bl) * Nl * Nl
+        t, w = sum(ts) / len(ts), sum(sw) / len(sw)
+        return {"workload": f"chamfer+hausdorff fwd+bwd B={Bl}/GPU N=M={Nl} (per-GPU shard of BASELINE configs[4])",
+                "ms_per_step": t, "value": pairs / (t * 1e-3) / 1e9, "unit": UNIT,
+                "sweep_ms": w, "sweep_tflops": FLOP_PER_PAIR * pairs / (w * 1e-3) / 1e12}
+
+    large = large_cloud()
+
     # ---------------- secondary metric: CW attack iterations/s (device-resident loop, section 8f-1) ----
     cw = run_cw(pcd, dev, rank, world, B)
 
@@ -408,6 +434,7 @@ def run_ours(args):
                                   "peak_source": hbm_src, "ms": bwd_avg_ms,
                                   "note": "includes autograd glue; launch-latency bound at this size (17.8 MB)"},
             "cpu_baseline": cpu,
+            "large_cloud": dict(large, sweep_frac=large["sweep_tflops"] / (fp32_peak / 1e12)),
             "cw_attack": {"metric": "CW attack iters/s", "iters_per_s_graph": float(cw_t[1]), "iters_per_s_eager": float(cw_t[0]),
                           "sample_iters_per_s_graph": float(cw_t[1]) * B * world,
                           "config": f"PointNet(106) random init, B={B}/GPU N={NPTS}, w*(Chamfer+Hausdorff avg) + logits loss kappa=30, "
