@@ -619,3 +619,63 @@ def test_l4_loops_are_batch_safe():
         d1, a1, _ = mk().attack(data[b:b + 1], label[b:b + 1], init_noise=noise[:, b:b + 1])
         np.testing.assert_allclose(npy(d2[b:b + 1]), npy(d1), rtol=1e-3)
         assert _agree(npy(a2[b:b + 1]), npy(a1)) > 0.98
+
+
+# ------------------------------------------------------------- randomized shapes / layouts / edge cases
+def _layout(a, kind):
+    """the same [B,N,C] cloud as contiguous, channel-first view, or a strided slice of a larger buffer"""
+    t = cu(a)
+    if kind == 1:
+        return cu(np.ascontiguousarray(a.transpose(0, 2, 1))).transpose(1, 2)
+    if kind == 2:
+        big = torch.zeros(a.shape[0], a.shape[1], a.shape[2] + 2, device="cuda")
+        big[:, :, 1:1 + a.shape[2]] = t
+        return big[:, :, 1:1 + a.shape[2]]
+    return t
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_nn1_shapes(seed):
+    rs = np.random.RandomState(1000 + seed)
+    B = int(rs.randint(1, 5)); N = int(rs.choice([1, 2, 31, 33, 127, 500, 1025, 2500])); M = int(rs.choice([1, 3, 32, 64, 129, 700, 2049]))
+    form_key = ["row_col_mulsum", "col_row_mulsum", "sum_first_fma"][seed % 3]
+    form, norm, oform, onorm = FORMS[form_key]
+    rows = rs.randn(B, N, 3).astype(np.float32); cols = rs.randn(B, M, 3).astype(np.float32)
+    if seed % 4 == 0 and M > 2:
+        cols[:, M // 2:] = cols[:, :M - M // 2]                   # duplicates: lowest-index ties
+    if seed % 5 == 0:
+        rows *= 1e-3; cols *= 1e-3                                 # tiny coordinates (denormal-free, cancellation heavy)
+    r = F.nn1(_layout(rows, seed % 3), _layout(cols, (seed // 3) % 3), form, norm, cache=False)
+    o = oracle_nn1(rows, cols, oform, onorm)
+    assert np.array_equal(npy(r.row_arg), o.row_arg) and np.array_equal(npy(r.col_arg), o.col_arg)
+    assert np.array_equal(npy(r.row_min), o.row_min) and np.array_equal(npy(r.col_min), o.col_min)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_knn_shapes(seed):
+    rs = np.random.RandomState(2000 + seed)
+    B = int(rs.randint(1, 4)); C = int(rs.choice([1, 2, 3, 3, 3, 5, 16, 64])); N = int(rs.choice([1, 7, 64, 300, 1100]))
+    M = int(rs.choice([1, 5, 33, 256, 257, 900, 2100]))
+    K = int(min(M, rs.choice([1, 2, 3, 8, 17, 20, 33, 64])))
+    form_key = ["col_row_mulsum", "row_col_mulsum"][seed % 2]
+    form, norm, oform, onorm = FORMS[form_key]
+    rows = rs.randn(B, N, C).astype(np.float32); cols = rs.randn(B, M, C).astype(np.float32)
+    if seed % 3 == 0 and M > 4:
+        cols[:, M // 2:] = cols[:, :M - M // 2]
+    d, i = F.knn(_layout(rows, seed % 3), _layout(cols, (seed // 3) % 3), K, form=form, norm=norm)
+    od, oi = O.knn(oform, rows, cols, O.norms(onorm, rows), O.norms(onorm, cols), K)
+    assert np.array_equal(npy(i), oi) and np.array_equal(npy(d), od)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_ball_query_and_fps(seed):
+    rs = np.random.RandomState(3000 + seed)
+    B = int(rs.randint(1, 4)); N = int(rs.choice([5, 64, 333, 1500])); S = int(rs.choice([1, 17, 128]))
+    ns = int(rs.choice([1, 8, 32, 64])); radius = float(rs.choice([0.05, 0.2, 0.6, 3.0]))
+    xyz = rs.rand(B, N, 3).astype(np.float32); q = rs.rand(B, S, 3).astype(np.float32)
+    got = pcd.pointnet2_utils.query_ball_point(radius, ns, _layout(xyz, seed % 3), _layout(q, (seed + 1) % 3))
+    assert np.array_equal(npy(got), O.query_ball_point(radius, ns, xyz, q))
+    npoint = int(min(N, rs.choice([1, 4, 60])))
+    start = rs.randint(0, N, size=B)
+    fps = F.farthest_point_sample(_layout(xyz, (seed + 2) % 3), npoint, cu(start))
+    assert np.array_equal(npy(fps), O.farthest_point_sample(xyz, npoint, start))
