@@ -27,6 +27,7 @@ SIGNATURES = {
     "pcd_nn1_workspace_bytes": (_Z, [_I, _I, _I]),
     "pcd_nn1_forward": (_I, _CLOUD + _CLOUD + [_I, _I, _I, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
     "pcd_nn1_set_sweep_events": (_I, [_P, _P]),
+    "pcd_nn1_set_backward_events": (_I, [_P, _P]),
     "pcd_nn1_backward": (_I, _CLOUD + _CLOUD + [_I, _I, _I, _I, _I] + [_P] * 12 + [_c.POINTER(_L), _F, _F] + _CLOUD + _CLOUD + [_P]),
     "pcd_knn_workspace_bytes": (_Z, [_I, _I, _I, _I, _I]),
     "pcd_knn_forward": (_I, _CLOUD + _CLOUD + [_I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),

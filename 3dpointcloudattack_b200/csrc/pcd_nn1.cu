@@ -637,6 +637,12 @@ extern "C" const char *pcd_last_error(void) { return g_err; }
 
 // optional profiling hook: events recorded around the sweep launch of the next forward calls
 static thread_local cudaEvent_t g_sweep_ev0 = nullptr, g_sweep_ev1 = nullptr;
+static thread_local cudaEvent_t g_bwd_ev0 = nullptr, g_bwd_ev1 = nullptr;
+extern "C" int pcd_nn1_set_backward_events(void *start_event, void *stop_event) {
+    g_bwd_ev0 = (cudaEvent_t)start_event;
+    g_bwd_ev1 = (cudaEvent_t)stop_event;
+    return PCD_OK;
+}
 extern "C" int pcd_nn1_set_sweep_events(void *start_event, void *stop_event) {
     g_sweep_ev0 = (cudaEvent_t)start_event;
     g_sweep_ev1 = (cudaEvent_t)stop_event;
@@ -778,6 +784,7 @@ extern "C" int pcd_nn1_backward(const float *rows, int64_t r_sb, int64_t r_sp, i
     cudaStream_t st = (cudaStream_t)stream;
     const bool dense_r = !grad_rows || (gr_sc == 1 && gr_sp == 3 && gr_sb == (int64_t)N * 3);
     const bool dense_c = !grad_cols || (gc_sc == 1 && gc_sp == 3 && gc_sb == (int64_t)M * 3);
+    if (g_bwd_ev0) PCD_CUDA_CHECK(cudaEventRecord(g_bwd_ev0, st));
     if (dense_r && dense_c) {
         if (grad_rows) PCD_CUDA_CHECK(cudaMemsetAsync(grad_rows, 0, (size_t)B * N * 3 * sizeof(float), st));
         if (grad_cols) PCD_CUDA_CHECK(cudaMemsetAsync(grad_cols, 0, (size_t)B * M * 3 * sizeof(float), st));
@@ -789,5 +796,6 @@ extern "C" int pcd_nn1_backward(const float *rows, int64_t r_sb, int64_t r_sp, i
         nn1_bwd_kernel<1><<<grid, 256, 0, st>>>(a);
         PCD_CUDA_CHECK(cudaGetLastError());
     }
+    if (g_bwd_ev1) PCD_CUDA_CHECK(cudaEventRecord(g_bwd_ev1, st));
     return PCD_OK;
 }

@@ -244,7 +244,8 @@ def run_ours(args):
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
     sweep_ev = [(ev(), ev()) for _ in range(args.steps)]
-    for a, b in sweep_ev:                                     # materialise the cudaEvent handles
+    bwdk_ev = [(ev(), ev()) for _ in range(args.steps)]
+    for a, b in sweep_ev + bwdk_ev:                           # materialise the cudaEvent handles
         a.record(); b.record()
     torch.cuda.synchronize()
 
@@ -264,18 +265,21 @@ def run_ours(args):
         adv.grad = None
         e0, e1, e2 = ev(), ev(), ev()
         lib.pcd_nn1_set_sweep_events(sweep_ev[k][0].cuda_event, sweep_ev[k][1].cuda_event)
+        lib.pcd_nn1_set_backward_events(bwdk_ev[k][0].cuda_event, bwdk_ev[k][1].cuda_event)
         e0.record()
         loss, _ = loss_fn(adv, ori)
         e1.record()
         loss.backward()
         e2.record()
         lib.pcd_nn1_set_sweep_events(None, None)
+        lib.pcd_nn1_set_backward_events(None, None)
         eager_ev.append((e0, e2)); bwd_ev.append((e1, e2))
     torch.cuda.synchronize()
     launches_per_step = (F.launches() - launches0) // args.steps
     eager_ms = [a.elapsed_time(b) for a, b in eager_ev]
     sweep_ms = [a.elapsed_time(b) for a, b in sweep_ev]
     bwd_ms = [a.elapsed_time(b) for a, b in bwd_ev]
+    bwdk_ms = [a.elapsed_time(b) for a, b in bwdk_ev]
 
     # ---------------- timed region: the same step captured once as a CUDA graph and replayed -----
     graphed = pcd.graph.GraphedLoss(loss_fn, adv, ori, warmup=3)
@@ -397,7 +401,8 @@ def run_ours(args):
         fp32_peak = F.fp32_peak_flops(2048)
         sweep_avg_ms = sum(sweep_ms) / len(sweep_ms)
         achieved = FLOP_PER_PAIR * pairs_step_rank / (sweep_avg_ms * 1e-3) / 1e12
-        bwd_avg_ms = sum(bwd_ms) / len(bwd_ms)
+        bwd_avg_ms = sum(bwdk_ms) / len(bwdk_ms)             # memset + nn1_bwd_kernel, events inside the C ABI
+        bwd_autograd_ms = sum(bwd_ms) / len(bwd_ms)
         bwd_bytes = 2.0 * B * NPTS * BWD_BYTES_PER_POINT_DIR
         cpu = None
         if world == 1:                                        # reported baseline: rank 0 at N=1 only
@@ -429,10 +434,12 @@ def run_ours(args):
                                            "workload (profiles/r1_sweep_full_summary.txt); algorithmic input bytes = 6.29 MB",
                          "peak_source": "FFMA/FFMA2 micro-kernel measured in this run (pcd_measure_fp32_peak)",
                          "ms_per_launch": sweep_avg_ms, "flop_per_pair": FLOP_PER_PAIR},
-            "roofline_backward": {"bound": "hbm", "kernel": "nn1_bwd_kernel x2", "achieved": bwd_bytes / (bwd_avg_ms * 1e-3) / 1e9,
+            "roofline_backward": {"bound": "hbm", "kernel": "memset + nn1_bwd_kernel<2>", "achieved": bwd_bytes / (bwd_avg_ms * 1e-3) / 1e9,
                                   "peak": hbm_gbs, "unit": "GB/s", "frac": bwd_bytes / (bwd_avg_ms * 1e-3) / 1e9 / hbm_gbs,
                                   "peak_source": hbm_src, "ms": bwd_avg_ms,
-                                  "note": "includes autograd glue; launch-latency bound at this size (17.8 MB)"},
+                                  "loss_backward_ms_with_autograd": bwd_autograd_ms,
+                                  "note": "algorithmic 68 B per (point, direction) = 17.8 MB: too small for the HBM roofline, "
+                                          "launch-latency bound; the eager loss.backward() around it is python/autograd glue"},
             "cpu_baseline": cpu,
             "large_cloud": dict(large, sweep_frac=large["sweep_tflops"] / (fp32_peak / 1e12)),
             "cw_attack": {"metric": "CW attack iters/s", "iters_per_s_graph": float(cw_t[1]), "iters_per_s_eager": float(cw_t[0]),
