@@ -1077,16 +1077,9 @@ static KnnLayout knn_layout(int B, int N, int M, int C, int K) {
     L.prepass = false;
     L.W = L.G = L.nsplit = L.tps = L.caps = 0;
     L.cand = L.cnt = L.ovf_cnt = L.ovf_rows = 0;
-    L.Npad = (int)align_up_k((size_t)N, C == 3 ? 128 * kPreR : kFcCtaRows);
     size_t off = 0;
     L.e = 0;
     if (C == 3) {
-        L.Mpad = (int)align_up_k((size_t)M, kKnnTile);
-        L.a = off; off = align_up_k(off + (size_t)B * L.Npad * 16, 256);
-        L.b = off; off = align_up_k(off + (size_t)B * L.Mpad * 16, 256);
-        L.c = off; off = align_up_k(off + (size_t)B * L.Mpad * 16 + kPreTile * 16, 256);   // + one stage of slack (chunk-aligned stages)
-        L.d = off; off = align_up_k(off + (size_t)B * kPreMaxChunks * L.Npad * 4, 256);
-        L.e = off; off = align_up_k(off + (size_t)B * L.Npad * 4, 256);
         // pre-pass: chunk width W so that 3K <= G <= 64 chunks where possible; skipped when M is too small
         int W = (M / (3 * (K > 0 ? K : 1))) & ~1;
         const int wmin = ((M + kPreMaxChunks - 1) / kPreMaxChunks + 1) & ~1;
@@ -1095,6 +1088,15 @@ static KnnLayout knn_layout(int B, int N, int M, int C, int K) {
         L.W = W;
         L.G = (M + W - 1) / W;
         L.prepass = K >= 1 && L.G >= K && L.G <= kPreMaxChunks && M >= 256;
+        // rows-in-lanes passes want 512-row tiles; the warp-per-row select alone only 32 (small clouds, big batches)
+        L.Npad = (int)align_up_k((size_t)N, L.prepass ? 128 * kPreR : kKnnWarps * kKnnRQ);
+        L.Mpad = (int)align_up_k((size_t)M, kKnnTile);
+        L.a = off; off = align_up_k(off + (size_t)B * L.Npad * 16, 256);
+        L.b = off; off = align_up_k(off + (size_t)B * L.Mpad * 16, 256);
+        L.c = off; off = align_up_k(off + (size_t)B * L.Mpad * 16 + kPreTile * 16, 256);   // + one stage of slack (chunk-aligned stages)
+        L.d = off;
+        if (L.prepass) off = align_up_k(off + (size_t)B * L.G * L.Npad * 4, 256);            // chunk minima [B][G][Npad]
+        L.e = off; off = align_up_k(off + (size_t)B * L.Npad * 4, 256);
         if (L.prepass) {
             // collect pass: split the column stages of a row tile over nsplit CTAs until the grid fills the GPU
             const int ntiles = (M + kPreTile - 1) / kPreTile;
@@ -1113,6 +1115,7 @@ static KnnLayout knn_layout(int B, int N, int M, int C, int K) {
             L.ovf_rows = off; off = align_up_k(off + (size_t)B * L.Npad * 4, 256);
         }
     } else {
+        L.Npad = (int)align_up_k((size_t)N, kFcCtaRows);
         L.Mpad = (int)align_up_k((size_t)M, kFcTile);
         L.a = off; off = align_up_k(off + (size_t)B * L.Npad * C * 4, 256);
         L.b = off; off = align_up_k(off + (size_t)B * L.Npad * 4, 256);
