@@ -31,6 +31,8 @@ PATCHES = {
     "attack.GeoA3.utility": (knn_utils, ["knn_points", "knn_gather"]),
     "model.dgcnn": (dgcnn, ["knn", "get_graph_feature"]),
     "pointnet.model": (dgcnn, ["knn", "get_graph_feature"]),
+    "attack.AOF.TAOF_attack": (dgcnn, ["knn"]),            # same formulation as dgcnn.knn (TAOF_attack.py:13-28)
+    "attack.AOF.Eval_AOF": (dgcnn, ["knn"]),
     "model.curvenet_util": (curvenet_util, ["knn", "normal_knn", "farthest_point_sample"]),
     "model.pointnet2_utils": (pointnet2_utils, ["query_ball_point", "farthest_point_sample"]),
     "pointnet.pointnet2_utils": (pointnet2_utils, ["query_ball_point", "farthest_point_sample"]),
