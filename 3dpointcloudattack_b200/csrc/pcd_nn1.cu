@@ -70,9 +70,10 @@ static Nn1Layout nn1_layout(int B, int N, int M) {
 // coalesced (one 256-B run per r instead of 32 scattered lines: the scattered flush cost 1.8 us
 // per row tile, 8 us of 131 at BASELINE config 2).  The records exist twice: rowpp in slot order
 // for the sweep's coalesced loads (another 4 us), rowpk in row order for the fix-up.
-__host__ __device__ __forceinline__ int row_slot(int i, int R) {
-    const int blk = i / (32 * R), w = i - blk * 32 * R;
-    return blk * 32 * R + (w % R) * 32 + w / R;
+__host__ __device__ __forceinline__ int row_slot(int i, int R) {      // R is 2, 4, 8 or 16: shifts, no divisions
+    const int rs = R == 16 ? 4 : (R == 8 ? 3 : (R == 4 ? 2 : 1));
+    const int w = i & ((32 << rs) - 1);
+    return (i - w) + ((w & (R - 1)) << 5) + (w >> rs);
 }
 
 // rowpk[b][i] = float4(-2x, -2y, -2z, nrow)           (AoS, one LDG.128 per query)
