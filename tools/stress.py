@@ -1,0 +1,66 @@
+"""Large-shape smoke / consistency run (development tool): sizes beyond the test-suite, checked through
+size-independent properties (role swap, idempotence, self-neighbour, agreement between code paths)."""
+import importlib, os, sys, time
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+pcd = importlib.import_module("3dpointcloudattack_b200")
+synth = importlib.import_module("3dpointcloudattack_b200.synth")
+F = pcd.functional
+
+def main():
+    t0 = time.time()
+    # NN-1 at the full BASELINE configs[4] per-GPU shard and at a large batch
+    for (B, N) in [(64, 16384), (512, 4096)]:
+        ori = synth.face_clouds(8, N, seed=7).cuda().repeat(B // 8, 1, 1).contiguous()
+        adv = (ori + 0.01 * torch.randn_like(ori))
+        a = F.nn1(ori, adv, F.FORM_SUM_FIRST, F.NORM_FMA, cache=False)
+        b = F.nn1(adv, ori, F.FORM_SUM_FIRST, F.NORM_FMA, cache=False)
+        assert torch.equal(a.row_min, b.col_min) and torch.equal(a.col_arg, b.row_arg) and torch.equal(a.row_arg, b.col_arg)
+        # brute-force check of 64 random rows against torch on the same device (fp64 distances, argmin must agree
+        # wherever the fp32 minimum is unique by a safe margin)
+        ii = torch.randint(0, N, (64,), device="cuda")
+        d64 = ((ori[0, ii].double()[:, None] - adv[0].double()[None]) ** 2).sum(-1)
+        top2 = d64.topk(2, largest=False)
+        safe = (top2.values[:, 1] - top2.values[:, 0]) > 1e-6
+        assert torch.equal(a.row_arg[0, ii][safe].long(), top2.indices[:, 0][safe])
+        print(f"nn1 B={B} N={N}: ok ({int(safe.sum())}/64 rows checked against fp64 brute force)", flush=True)
+    # k-NN xyz: collect pipeline vs warp-per-row select on a big batch
+    x = torch.rand(512, 2048, 3, device="cuda")
+    d1, i1 = F.knn(x, x, 20)
+    os.environ["PCD_KNN_NO_COLLECT"] = "1"
+    d2, i2 = F.knn(x, x, 20)
+    del os.environ["PCD_KNN_NO_COLLECT"]
+    assert torch.equal(i1, i2) and torch.equal(d1, d2)
+    # (expansion-form self distances are rounding noise, ~1e-7: a neighbour closer than ~6e-4 can legitimately win)
+    self_first = float((i1[:, :, 0].long() == torch.arange(2048, device="cuda").expand(512, -1)).float().mean())
+    assert self_first > 0.9999
+    print(f"knn xyz B=512 N=2048 K=20: collect pipeline == select kernel, self first on {self_first:.6f} of the rows", flush=True)
+    # feature k-NN: self first, distances ascending
+    f = torch.randn(64, 4096, 64, device="cuda")
+    d, i = F.knn(f, f, 20)
+    assert float((i[:, :, 0].long() == torch.arange(4096, device="cuda").expand(64, -1)).float().mean()) > 0.9999
+    assert bool((d[:, :, 1:] >= d[:, :, :-1]).all())
+    print("knn C=64 B=64 N=4096 K=20: ok", flush=True)
+    # edge features: forward == torch gather, backward == autograd of the torch formulation
+    xf = torch.randn(64, 64, 2048, device="cuda", requires_grad=True)
+    out = pcd.dgcnn.get_graph_feature(xf, k=20, idx=i1[:64].long())
+    xr = xf.detach().clone().requires_grad_(True)
+    idx = i1[:64].long()
+    nb = torch.gather(xr[:, :, None, :].expand(-1, -1, 2048, -1), 3, idx[:, None].expand(-1, 64, -1, -1))
+    ref = torch.cat((nb - xr[:, :, :, None], xr[:, :, :, None].expand(-1, -1, -1, 20)), 1)
+    assert torch.equal(out, ref)
+    g = torch.randn_like(out)
+    out.backward(g); ref.backward(g)
+    assert float((xf.grad - xr.grad).abs().max() / xr.grad.abs().max()) < 1e-5
+    print("edge features B=64 C=64 N=2048 k=20: forward bit-equal, backward 1e-5", flush=True)
+    # FPS against the torch loop on CPU-order arithmetic is covered by the tests; here: distinct indices, start kept
+    xyz = torch.rand(256, 4096, 3, device="cuda")
+    s = F.farthest_point_sample(xyz, 1024)
+    assert bool((s[:, 0] == 0).all()) and all(len(set(r.tolist())) == 1024 for r in s[:4])
+    print("fps B=256 N=4096 npoint=1024: ok", flush=True)
+    torch.cuda.synchronize()
+    print("stress ok in %.1f s, peak memory %.1f GB" % (time.time() - t0, torch.cuda.max_memory_allocated() / 1e9))
+
+if __name__ == "__main__":
+    main()
