@@ -160,6 +160,7 @@ fps_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sp, int64_t sc, in
            const int32_t *__restrict__ start, int32_t *__restrict__ out) {
     constexpr int W = T / 32;
     __shared__ unsigned long long wbest[2][W];
+    extern __shared__ float4 pts[];                         // [T * PPT] the cloud again: the chosen centroid is one broadcast LDS
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float *pb = xyz + b * sb;
     float px[PPT], py[PPT], pz[PPT], dist[PPT];
@@ -173,13 +174,16 @@ fps_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sp, int64_t sc, in
             px[s] = py[s] = pz[s] = 0.f;
             dist[s] = -1.f;                                 // never the maximum, never updated
         }
+        pts[i] = make_float4(px[s], py[s], pz[s], 0.f);
     }
+    __syncthreads();
     int far = start ? start[b] : 0;
     if (far < 0 || far >= N) far = 0;
     for (int it = 0; it < npoint; ++it) {
         if (tid == 0) out[(size_t)b * npoint + it] = far;
         if (it + 1 == npoint) break;
-        const float cx = __ldg(pb + far * sp), cy = __ldg(pb + far * sp + sc), cz = __ldg(pb + far * sp + 2 * sc);
+        const float4 c4 = pts[far];
+        const float cx = c4.x, cy = c4.y, cz = c4.z;
         uint32_t bd = 0u, bi = 0xffffffffu;                  // best (distance bits, index) of this thread
 #pragma unroll
         for (int s = 0; s < PPT; ++s) {
@@ -195,13 +199,11 @@ fps_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sp, int64_t sc, in
         const uint32_t wi = __reduce_min_sync(0xffffffffu, bd == wd ? bi : 0xffffffffu);
         if (lane == 0) wbest[it & 1][warp] = ((unsigned long long)wd << 32) | (0xffffffffu - wi);
         __syncthreads();
-        unsigned long long kbest = lane < W ? wbest[it & 1][lane] : 0ull;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const unsigned long long other = __shfl_xor_sync(0xffffffffu, kbest, o);
-            kbest = other > kbest ? other : kbest;
-        }
-        far = (int)(0xffffffffu - (uint32_t)kbest);
+        // every warp folds the W per-warp results itself: max distance bits, then lowest index among the maxima
+        const unsigned long long kw = lane < W ? wbest[it & 1][lane] : 0ull;
+        const uint32_t kd = (uint32_t)(kw >> 32), ki = 0xffffffffu - (uint32_t)kw;
+        const uint32_t bd2 = __reduce_max_sync(0xffffffffu, kd);
+        far = (int)__reduce_min_sync(0xffffffffu, (lane < W && kd == bd2) ? ki : 0xffffffffu);
     }
 }
 
@@ -236,13 +238,11 @@ fps_large_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sp, int64_t 
         const uint32_t wi = __reduce_min_sync(0xffffffffu, bd == wd ? bi : 0xffffffffu);
         if (lane == 0) wbest[it & 1][warp] = ((unsigned long long)wd << 32) | (0xffffffffu - wi);
         __syncthreads();
-        unsigned long long kbest = lane < W ? wbest[it & 1][lane] : 0ull;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const unsigned long long other = __shfl_xor_sync(0xffffffffu, kbest, o);
-            kbest = other > kbest ? other : kbest;
-        }
-        far = (int)(0xffffffffu - (uint32_t)kbest);
+        // every warp folds the W per-warp results itself: max distance bits, then lowest index among the maxima
+        const unsigned long long kw = lane < W ? wbest[it & 1][lane] : 0ull;
+        const uint32_t kd = (uint32_t)(kw >> 32), ki = 0xffffffffu - (uint32_t)kw;
+        const uint32_t bd2 = __reduce_max_sync(0xffffffffu, kd);
+        far = (int)__reduce_min_sync(0xffffffffu, (lane < W && kd == bd2) ? ki : 0xffffffffu);
     }
 }
 
@@ -343,11 +343,21 @@ extern "C" int pcd_fps(const float *xyz, int64_t sb, int64_t sp, int64_t sc, int
         return PCD_ERR_ARG;
     }
     cudaStream_t st = (cudaStream_t)stream;
-#define PCD_FPS(T, PPT) fps_kernel<T, PPT><<<B, T, 0, st>>>(xyz, sb, sp, sc, N, npoint, start, out)
-    if (N <= 256) PCD_FPS(256, 1);
-    else if (N <= 512) PCD_FPS(512, 1);
-    else if (N <= 1024) PCD_FPS(512, 2);
-    else if (N <= 2048) PCD_FPS(512, 4);
+#define PCD_FPS(T, PPT)                                                                                          \
+    do {                                                                                                         \
+        constexpr size_t sm_bytes = (size_t)(T) * (PPT) * sizeof(float4);                                        \
+        static bool attr_set = false;                                                                            \
+        if (sm_bytes > 48 * 1024 && !attr_set) {                                                                 \
+            PCD_CUDA_CHECK(cudaFuncSetAttribute(fps_kernel<T, PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                                (int)sm_bytes));                                                 \
+            attr_set = true;                                                                                     \
+        }                                                                                                        \
+        fps_kernel<T, PPT><<<B, T, sm_bytes, st>>>(xyz, sb, sp, sc, N, npoint, start, out);                      \
+    } while (0)
+    if (N <= 256) PCD_FPS(128, 2);
+    else if (N <= 512) PCD_FPS(128, 4);
+    else if (N <= 1024) PCD_FPS(256, 4);
+    else if (N <= 2048) PCD_FPS(256, 8);
     else if (N <= 4096) PCD_FPS(512, 8);
     else if (N <= 8192) PCD_FPS(1024, 8);
     else {
