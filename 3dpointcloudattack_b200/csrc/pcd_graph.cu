@@ -54,6 +54,8 @@ edge_feature_fwd_kernel(const float *__restrict__ x, const int32_t *__restrict__
             m[0] = __ldcs(ib + e0);
         }
         const int n = (int)(e0 / k);                               // VEC = 4 only when 4 | k: the four slots share n
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) m[i] = min(max(m[i], 0), N - 1);      // never read outside the staged rows (the kernel is store bound)
         for (int c = 0; c < ncg; ++c) {
             const float *xr = xs + c * N;
             const float ctr = xr[n];
@@ -104,7 +106,7 @@ edge_feature_bwd_kernel(const float *__restrict__ g, const int32_t *__restrict__
         }
         float sn[VEC], own = 0.f;
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) sn[i] = 0.f;
+        for (int i = 0; i < VEC; ++i) { sn[i] = 0.f; m[i] = min(max(m[i], 0), N - 1); }
         for (int q = 0; q < nblocks; ++q) {
             const int op = (ops >> (2 * q)) & 3;
             const float *gp = g + (((size_t)b * nblocks + q) * C + c) * NK + e0;

@@ -189,7 +189,7 @@ int pcd_ball_query(const float *xyz, int64_t x_sb, int64_t x_sp, int64_t x_sc,
  *   model/curvenet_util.py:206-236  LPFA.group_feature  ops = {CENTER, NEIGHBOR, DIFF} (xyz, 9 ch)
  *                                                        ops = {DIFF}                   (features)
  * x [B,C,N] contiguous fp32 (channel-first, as the victims hold it), idx [B,N,k] int32 with
- * entries in [0,N), out [B, nblocks*C, N, k] contiguous:
+ * entries in [0,N) (others are clamped), out [B, nblocks*C, N, k] contiguous:
  *   out[b, q*C + c, n, j] = ops[q](centre = x[b,c,n], neighbour = x[b,c,idx[b,n,j]])
  * `ops` is a HOST array of nblocks (1..4) pcd_edge_op values.  The backward accumulates
  * gx[b,c,n] from g [B, nblocks*C, N, k] (own terms plus the scatter through idx); gx is
