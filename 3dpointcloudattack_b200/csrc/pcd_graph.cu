@@ -85,7 +85,7 @@ edge_feature_fwd_kernel(const float *__restrict__ x, const int32_t *__restrict__
 // neighbour terms both go through shared-memory atomics.  Summation order of the scatter is
 // not fixed (as in the reference's index backward): results differ run to run in the last bits.
 template <int VEC>
-__global__ void __launch_bounds__(kEdgeThreads)
+__global__ void __launch_bounds__(kEdgeThreads, 8)       // 8 CTAs = 64 warps per SM: the CAS loops are latency bound
 edge_feature_bwd_kernel(const float *__restrict__ g, const int32_t *__restrict__ idx, int C, int N, int k, int nblocks,
                         int ops, float *__restrict__ gx) {
     extern __shared__ float acc[];
