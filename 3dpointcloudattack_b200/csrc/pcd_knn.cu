@@ -597,11 +597,11 @@ knn3_collect_kernel(const float4 *__restrict__ rowq, const float4 *__restrict__ 
 // (knn3_kernel rewrites their outputs afterwards).  Results leave through shared memory so that
 // a warp writes its 32 x K outputs as one contiguous, coalesced block.
 template <int KT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, (KT <= 20) ? 8 : ((KT <= 24) ? 6 : ((KT <= 32) ? 5 : 3)))     // occupancy hides the candidate-load latency
 knn3_final_kernel(const unsigned long long *__restrict__ cand, const unsigned int *__restrict__ cnt_g, int B, int N,
                   int Npad, int nsplit, int caps, int K, float *__restrict__ dists, int32_t *__restrict__ idx,
                   int *__restrict__ ovf_cnt, int *__restrict__ ovf_rows) {
-    __shared__ uint32_t stage[4][32 * PCD_KNN_MAX_K];
+    extern __shared__ uint32_t stage_dyn[];                  // [4 warps][32 * K] output staging
     __shared__ unsigned short s_n[16][128];
     const int b = blockIdx.y, i = blockIdx.x * 128 + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -662,7 +662,7 @@ knn3_final_kernel(const unsigned long long *__restrict__ cand, const unsigned in
     const int nvalid = N - i0 < 32 ? N - i0 : 32;
     if (nvalid <= 0) return;
     const size_t base = ((size_t)b * N + i0) * K;
-    uint32_t *sg = stage[warp];
+    uint32_t *sg = stage_dyn + (size_t)warp * 32 * K;
     if (dists) {
 #pragma unroll
         for (int k = 0; k < KT; ++k)
@@ -1213,7 +1213,7 @@ extern "C" int pcd_knn_forward(const float *rows, int64_t r_sb, int64_t r_sp, in
             else knn3_collect_kernel<PCD_FORM_SUM_FIRST><<<cg, 128, 0, st>>>(rowq, (const float4 *)colpk, thr0, B, L.Npad, L.Mpad, M, L.nsplit, L.tps, L.caps, cand, cnt_g);
             PCD_CUDA_CHECK(cudaGetLastError());
             const dim3 fg((N + 127) / 128, B);
-#define PCD_LAUNCH_FINAL(KT) knn3_final_kernel<KT><<<fg, 128, 0, st>>>(cand, cnt_g, B, N, L.Npad, L.nsplit, L.caps, K, dists, idx, ovf_cnt, ovf_rows)
+#define PCD_LAUNCH_FINAL(KT) knn3_final_kernel<KT><<<fg, 128, (size_t)128 * K * sizeof(uint32_t), st>>>(cand, cnt_g, B, N, L.Npad, L.nsplit, L.caps, K, dists, idx, ovf_cnt, ovf_rows)
             switch ((K + 3) / 4) {                           // KT = K rounded up to a multiple of 4 (48 / 64 beyond 32)
                 case 1: PCD_LAUNCH_FINAL(4); break;
                 case 2: PCD_LAUNCH_FINAL(8); break;

@@ -354,7 +354,7 @@ __device__ __forceinline__ void reduce_smf(float &s, float &mx, int &am) {
 }
 
 template <int FORM>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)        // 64 warps per SM: the key -> chunk load round trips are the bound
 nn1_fixup_kernel(const float4 *__restrict__ rowpk, const float4 *__restrict__ colpk,
                  const unsigned long long *__restrict__ rowkey, const unsigned long long *__restrict__ colkey,
                  int N, int M, int Npad, int Mpad, int R, int transform,
