@@ -460,7 +460,7 @@ def run_ours(args):
             "roofline": {"bound": "fp32", "kernel": "nn1_sweep_kernel", "achieved": achieved, "peak": fp32_peak / 1e12,
                          "unit": "TFLOP/s", "frac": achieved / (fp32_peak / 1e12), "traffic": SWEEP_DRAM_BYTES_PER_LAUNCH,
                          "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one launch at this "
-                                           "workload (profiles/r1_sweep_full_summary.txt); algorithmic input bytes = 6.29 MB",
+                                           "workload (profiles/r1_v6_ncu_summary.txt); algorithmic input bytes = 6.29 MB",
                          "peak_source": "FFMA/FFMA2 micro-kernel measured in this run (pcd_measure_fp32_peak)",
                          "ms_per_launch": sweep_avg_ms, "flop_per_pair": FLOP_PER_PAIR},
             "roofline_backward": {"bound": "hbm", "kernel": "memset + nn1_bwd_kernel<2>", "achieved": bwd_bytes / (bwd_avg_ms * 1e-3) / 1e9,
