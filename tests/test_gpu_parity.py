@@ -712,3 +712,64 @@ def test_pipelined_loss_matches_eager():
     loss2, (l2,) = loss_fn(a2, ori_h.cuda())
     loss2.backward()
     assert torch.equal(torch.cat([x[0] for x in aux], 1), l2.detach().cpu()) and rel_inf(npy(a2.grad), grad.numpy()) < 1e-6
+
+
+# ------------------------------------------------------------- model-level: the callers either side of the path
+def test_dgcnn_victim_with_kernels_matches_torch_formulation():
+    """A DGCNN-shaped victim (tools/victims.py) forward + backward w.r.t. the cloud with this package's
+    k-NN + edge-feature kernels vs. the reference's torch formulation (model/dgcnn.py:194-227), same weights."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import victims
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(0)
+    ours = victims.DGCNNVictim(lambda x, k: pcd.dgcnn.get_graph_feature(x, k=k), k=8, emb_dims=64, num_classes=5).cuda().eval()
+    ref = victims.DGCNNVictim(victims.torch_graph_feature, k=8, emb_dims=64, num_classes=5).cuda().eval()
+    ref.load_state_dict(ours.state_dict())
+    synth = importlib.import_module("3dpointcloudattack_b200.synth")
+    x0 = synth.face_clouds(2, 512, seed=9).cuda().transpose(1, 2).contiguous()
+    outs, grads = [], []
+    for m in (ours, ref):
+        x = x0.clone().requires_grad_(True)
+        o = m(x)[0]
+        o[:, 1].sum().backward()
+        outs.append(npy(o)); grads.append(npy(x.grad))
+    np.testing.assert_allclose(outs[0], outs[1], rtol=1e-4, atol=1e-5)
+    assert rel_inf(grads[1], grads[0]) < 1e-3          # feature-space graphs can differ at near-ties (cuBLAS order)
+
+
+def test_sample_and_group_matches_reference_formulation_on_cpu():
+    """PointNet++ set-abstraction grouping (model/pointnet2_utils.py:107-135): FPS + ball query + gathers on the
+    GPU kernels vs. the reference's formulation restated with torch on the CPU (same torch.randint start draw)."""
+    rs = np.random.RandomState(4)
+    xyz = rs.rand(3, 700, 3).astype(np.float32)
+    pts = rs.randn(3, 700, 5).astype(np.float32)
+    npoint, radius, nsample = 64, 0.25, 16
+    torch.manual_seed(123)
+    new_xyz, new_points = pcd.pointnet2_utils.sample_and_group(npoint, radius, nsample, cu(xyz), cu(pts))
+    torch.manual_seed(123)
+    x, p = torch.from_numpy(xyz), torch.from_numpy(pts)
+    B, N, _ = x.shape
+    cent = torch.zeros(B, npoint, dtype=torch.long)
+    dist = torch.ones(B, N) * 1e10
+    far = torch.randint(0, N, (B,), dtype=torch.long)
+    bi = torch.arange(B)
+    for i in range(npoint):                                        # :59-81
+        cent[:, i] = far
+        c = x[bi, far, :].view(B, 1, 3)
+        d = torch.sum((x - c) ** 2, -1)
+        m = d < dist
+        dist[m] = d[m]
+        far = torch.max(dist, -1)[1]
+    nx = x[bi[:, None], cent]
+    sq = -2 * torch.matmul(nx, x.permute(0, 2, 1)) + torch.sum(nx ** 2, -1).view(B, npoint, 1) + torch.sum(x ** 2, -1).view(B, 1, N)
+    gi = torch.arange(N).view(1, 1, N).repeat(B, npoint, 1)        # :84-104
+    gi[sq > radius ** 2] = N
+    gi = gi.sort(dim=-1)[0][:, :, :nsample]
+    first = gi[:, :, 0].view(B, npoint, 1).repeat(1, 1, nsample)
+    gi[gi == N] = first[gi == N]
+    gx = x[bi[:, None, None], gi] - nx.view(B, npoint, 1, 3)
+    ref_points = torch.cat([gx, p[bi[:, None, None], gi]], dim=-1)
+    assert np.array_equal(npy(new_xyz), nx.numpy())
+    assert np.array_equal(npy(new_points), ref_points.numpy())
