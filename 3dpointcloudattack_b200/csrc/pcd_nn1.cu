@@ -584,10 +584,13 @@ static cudaError_t launch_sweep(const float4 *rowpk, const float4 *colpk, unsign
     const int nq = (M + kQuad - 1) / kQuad;                  // ... and fully inert column quads
     const long long units = (long long)B * nqt * nq;
     if (units >= (1LL << 31)) return cudaErrorInvalidValue;
-    int occ = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nn1_sweep_kernel<FORM, R>, kSweepThreads, 0);
-    if (e != cudaSuccess) return e;
-    if (occ < 1) occ = 1;
+    static int occ = 0;                                      // per instantiation; queried once (the query costs microseconds)
+    if (occ == 0) {
+        int o = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, nn1_sweep_kernel<FORM, R>, kSweepThreads, 0);
+        if (e != cudaSuccess) return e;
+        occ = o < 1 ? 1 : o;
+    }
     long long grid = (long long)sms * occ;
     if (grid > units) grid = units;
     nn1_sweep_kernel<FORM, R><<<(unsigned)grid, kSweepThreads, 0, st>>>(rowpk, colpk, rowkey, colkey, Npad, Mpad,

@@ -6,6 +6,7 @@ module computes a distance with torch ops and nothing falls back to CPU.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 from collections import namedtuple
 
@@ -42,8 +43,20 @@ def _cloud_args(t):
     return [t.data_ptr(), t.stride(0), t.stride(1), t.stride(2)]
 
 
-def _stream():
-    return torch.cuda.current_stream().cuda_stream
+def _stream(dev=None):
+    """raw cudaStream_t of the current stream (torch.cuda.current_stream() builds a Stream object: ~20 us per call)"""
+    idx = torch.cuda.current_device() if dev is None or dev.index is None else dev.index
+    return torch._C._cuda_getCurrentRawStream(idx)
+
+
+_NULLCTX = contextlib.nullcontext()
+
+
+def _on(dev):
+    """device guard only when the tensor's device is not the current one (the guard costs ~10 us)"""
+    if dev.index is None or torch.cuda.current_device() == dev.index:
+        return _NULLCTX
+    return torch.cuda.device(dev)
 
 
 def _ptr(t):
@@ -73,7 +86,7 @@ class _NN1(torch.autograd.Function):
         B, N, _ = rows.shape
         M = cols.shape[1]
         dev = rows.device
-        with torch.cuda.device(dev):
+        with _on(dev):
             row_min = torch.empty((B, N), dtype=torch.float32, device=dev)
             col_min = torch.empty((B, M), dtype=torch.float32, device=dev)
             row_arg = torch.empty((B, N), dtype=torch.int32, device=dev)
@@ -86,7 +99,7 @@ class _NN1(torch.autograd.Function):
                                      form, norm, int(swap_norms), transform, row_scale, col_scale,
                                      row_min.data_ptr(), row_arg.data_ptr(), col_min.data_ptr(), col_arg.data_ptr(),
                                      stats.data_ptr(), stats_i.data_ptr(),
-                                     ws.data_ptr(), ws_bytes, _stream())
+                                     ws.data_ptr(), ws_bytes, _stream(dev))
             _lib.check(st, "pcd_nn1_forward")
         _launch_count += 4
         ctx.save_for_backward(rows, cols, row_arg, col_arg, row_min, col_min, stats_i)
@@ -109,7 +122,7 @@ class _NN1(torch.autograd.Function):
         B, N, _ = rows.shape
         M = cols.shape[1]
         dev = rows.device
-        with torch.cuda.device(dev):
+        with _on(dev):
             c = lambda t: None if t is None else t.contiguous()
             g_row, g_col = c(g_row_min), c(g_col_min)
             # [B] upstream gradients are read through their stride: autograd hands out expanded
@@ -125,7 +138,7 @@ class _NN1(torch.autograd.Function):
                                       _ptr(g_row), _ptr(g_col),
                                       _ptr(w[0]), _ptr(w[1]), stats_i[0].data_ptr(),
                                       _ptr(w[2]), _ptr(w[3]), stats_i[1].data_ptr(),
-                                      w_strides, row_scale, col_scale, *gr, *gc, _stream())
+                                      w_strides, row_scale, col_scale, *gr, *gc, _stream(dev))
             _lib.check(st, "pcd_nn1_backward")
         _launch_count += 1
         return grad_rows, grad_cols, None, None, None, None, None, None, None
@@ -193,14 +206,14 @@ class _KNN(torch.autograd.Function):
         B, N, C = rows.shape
         M = cols.shape[1]
         dev = rows.device
-        with torch.cuda.device(dev):
+        with _on(dev):
             dists = torch.empty((B, N, K), dtype=torch.float32, device=dev)
             idx = torch.empty((B, N, K), dtype=torch.int32, device=dev)
             ws_bytes = lib.pcd_knn_workspace_bytes(B, N, M, C, K)
             ws = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=dev)
             st = lib.pcd_knn_forward(*_cloud_args(rows), *_cloud_args(cols), B, N, M, C, K,
                                      form, norm, int(swap_norms), dists.data_ptr(), idx.data_ptr(),
-                                     ws.data_ptr(), ws_bytes, _stream())
+                                     ws.data_ptr(), ws_bytes, _stream(dev))
             _lib.check(st, "pcd_knn_forward")
         _launch_count += 2
         ctx.save_for_backward(rows, cols, idx)
@@ -223,14 +236,14 @@ class _KNN(torch.autograd.Function):
                                       "(the reference differentiates kNN distances on xyz only)")
         lib = _lib.load()
         dev = rows.device
-        with torch.cuda.device(dev):
+        with _on(dev):
             g = g_dists.contiguous()
             grad_rows = torch.empty((B, N, 3), dtype=torch.float32, device=dev) if need_r else None
             grad_cols = torch.empty((B, M, 3), dtype=torch.float32, device=dev) if need_c else None
             gr = _cloud_args(grad_rows) if need_r else [None, 0, 0, 0]
             gc = _cloud_args(grad_cols) if need_c else [None, 0, 0, 0]
             st = lib.pcd_knn_backward(*_cloud_args(rows), *_cloud_args(cols), B, N, M, K, swap_norms,
-                                      idx.data_ptr(), g.data_ptr(), *gr, *gc, _stream())
+                                      idx.data_ptr(), g.data_ptr(), *gr, *gc, _stream(dev))
             _lib.check(st, "pcd_knn_backward")
         _launch_count += 2
         return grad_rows, grad_cols, None, None, None, None, None
@@ -261,11 +274,11 @@ def ball_query(radius, nsample, xyz, new_xyz):
     B, N, _ = xyz.shape
     S = new_xyz.shape[1]
     dev = xyz.device
-    with torch.cuda.device(dev):
+    with _on(dev):
         idx = torch.empty((B, S, int(nsample)), dtype=torch.int32, device=dev)
         r2 = torch.tensor(float(radius) ** 2, dtype=torch.float32).item()   # fp32(radius**2), as the reference compares
         st = lib.pcd_ball_query(*_cloud_args(xyz.detach()), *_cloud_args(new_xyz.detach()), B, N, S, r2,
-                                int(nsample), idx.data_ptr(), _stream())
+                                int(nsample), idx.data_ptr(), _stream(dev))
         _lib.check(st, "pcd_ball_query")
     _launch_count += 1
     return idx
@@ -281,10 +294,10 @@ class _EdgeFeature(torch.autograd.Function):
         k = idx.shape[2]
         dev = x.device
         c_ops = (ctypes.c_int * len(ops))(*ops)
-        with torch.cuda.device(dev):
+        with _on(dev):
             out = torch.empty((B, len(ops) * C, N, k), dtype=torch.float32, device=dev)
             st = lib.pcd_edge_feature_forward(x.data_ptr(), idx.data_ptr(), B, C, N, k, len(ops), c_ops,
-                                              out.data_ptr(), _stream())
+                                              out.data_ptr(), _stream(dev))
             _lib.check(st, "pcd_edge_feature_forward")
         _launch_count += 1
         ctx.save_for_backward(idx)
@@ -302,11 +315,11 @@ class _EdgeFeature(torch.autograd.Function):
         B, _, N, k = g.shape
         dev = g.device
         c_ops = (ctypes.c_int * len(ops))(*ops)
-        with torch.cuda.device(dev):
+        with _on(dev):
             g = g.contiguous()
             gx = torch.empty((B, C, N), dtype=torch.float32, device=dev)
             st = lib.pcd_edge_feature_backward(g.data_ptr(), idx.data_ptr(), B, C, N, k, len(ops), c_ops,
-                                               gx.data_ptr(), _stream())
+                                               gx.data_ptr(), _stream(dev))
             _lib.check(st, "pcd_edge_feature_backward")
         _launch_count += 1
         return gx, None, None
@@ -343,12 +356,12 @@ def farthest_point_sample(xyz, npoint, start=None):
     if npoint < 1:
         raise ValueError("npoint must be >= 1")
     dev = xyz.device
-    with torch.cuda.device(dev):
+    with _on(dev):
         st32 = None if start is None else start.detach().to(device=dev, dtype=torch.int32).contiguous()
         out = torch.empty((B, npoint), dtype=torch.int32, device=dev)
         x = xyz.detach()
         st = lib.pcd_fps(x.data_ptr(), x.stride(0), x.stride(1), x.stride(2), B, N, npoint, _ptr(st32),
-                         out.data_ptr(), _stream())
+                         out.data_ptr(), _stream(dev))
         _lib.check(st, "pcd_fps")
     _launch_count += 1
     return out
