@@ -13,6 +13,16 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # a fresh checkout has no built artefacts (they are git-ignored): build the CUDA library (nvcc
+    # cross-compiles without a GPU) and the CPU oracle once, exactly as __graft_entry__.build() does
+    lib = os.path.join(ROOT, "3dpointcloudattack_b200", "libpcdist.so")
+    orc = os.path.join(ROOT, "oracle", "libpcd_oracle.so")
+    if not (os.path.exists(lib) and os.path.exists(orc)):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("_graft_entry", os.path.join(ROOT, "__graft_entry__.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.build()
 
 
 def load_golden(name):
