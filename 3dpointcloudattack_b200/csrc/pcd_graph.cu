@@ -296,11 +296,9 @@ extern "C" int pcd_edge_feature_forward(const float *x, const int32_t *idx, int 
     if (slices < 1) slices = 1;
     const long long sps = (nslots + slices - 1) / slices;
     const dim3 grid((unsigned)((nslots + sps - 1) / sps), cgroups, B);
-    static size_t smem_set[2] = {0, 0};
-    if (smem > 48 * 1024 && smem > smem_set[vec]) {
+    if (smem > 48 * 1024) {      // per device and function: requested on every call (~1 us), no process-wide memo
         if (vec) PCD_CUDA_CHECK(cudaFuncSetAttribute(edge_feature_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         else PCD_CUDA_CHECK(cudaFuncSetAttribute(edge_feature_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set[vec] = smem;
     }
     if (vec) edge_feature_fwd_kernel<4><<<grid, kEdgeThreads, smem, st>>>(x, idx, C, N, k, nblocks, packed, CG, sps, out);
     else edge_feature_fwd_kernel<1><<<grid, kEdgeThreads, smem, st>>>(x, idx, C, N, k, nblocks, packed, CG, sps, out);
@@ -326,11 +324,9 @@ extern "C" int pcd_edge_feature_backward(const float *g, const int32_t *idx, int
     }
     cudaStream_t st = (cudaStream_t)stream;
     const bool vec = (k & 3) == 0;
-    static size_t smem_set[2] = {0, 0};
-    if (smem > 48 * 1024 && smem > smem_set[vec]) {
+    if (smem > 48 * 1024) {
         if (vec) PCD_CUDA_CHECK(cudaFuncSetAttribute(edge_feature_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         else PCD_CUDA_CHECK(cudaFuncSetAttribute(edge_feature_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set[vec] = smem;
     }
     if (vec) edge_feature_bwd_kernel<4><<<dim3(C, B), kEdgeThreads, smem, st>>>(g, idx, C, N, k, nblocks, packed, gx);
     else edge_feature_bwd_kernel<1><<<dim3(C, B), kEdgeThreads, smem, st>>>(g, idx, C, N, k, nblocks, packed, gx);
@@ -348,12 +344,9 @@ extern "C" int pcd_fps(const float *xyz, int64_t sb, int64_t sp, int64_t sc, int
 #define PCD_FPS(T, PPT)                                                                                          \
     do {                                                                                                         \
         constexpr size_t sm_bytes = (size_t)(T) * (PPT) * sizeof(float4);                                        \
-        static bool attr_set = false;                                                                            \
-        if (sm_bytes > 48 * 1024 && !attr_set) {                                                                 \
+        if (sm_bytes > 48 * 1024)                                                                                \
             PCD_CUDA_CHECK(cudaFuncSetAttribute(fps_kernel<T, PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                                (int)sm_bytes));                                                 \
-            attr_set = true;                                                                                     \
-        }                                                                                                        \
+                                                (int)sm_bytes));                                                                                                        \
         fps_kernel<T, PPT><<<B, T, sm_bytes, st>>>(xyz, sb, sp, sc, N, npoint, start, out);                      \
     } while (0)
     if (N <= 256) PCD_FPS(128, 2);
@@ -368,11 +361,8 @@ extern "C" int pcd_fps(const float *xyz, int64_t sb, int64_t sp, int64_t sc, int
             set_error("pcd_fps: N=%d exceeds the shared-memory distance array (N <= 51200)", N);
             return PCD_ERR_UNSUPPORTED;
         }
-        static size_t smem_set = 0;
-        if (smem > 48 * 1024 && smem > smem_set) {
+        if (smem > 48 * 1024)
             PCD_CUDA_CHECK(cudaFuncSetAttribute(fps_large_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            smem_set = smem;
-        }
         fps_large_kernel<1024><<<B, 1024, smem, st>>>(xyz, sb, sp, sc, N, npoint, start, out);
     }
 #undef PCD_FPS
