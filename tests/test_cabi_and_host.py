@@ -59,6 +59,16 @@ def test_no_cpu_fallback():
         pcd.pointnet2_utils.query_ball_point(0.2, 4, a, a)
     with pytest.raises(RuntimeError, match="CUDA only"):
         pcd.dgcnn.knn(a.transpose(1, 2), 2)
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        pcd.dgcnn.get_graph_feature(a.transpose(1, 2).contiguous(), k=2, idx=torch.zeros(1, 8, 2, dtype=torch.long))
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        pcd.pointnet2_utils.farthest_point_sample(a, 4)
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        pcd.curvenet_util.farthest_point_sample(a, 4)
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        pcd.cw_loop.CWAttack(torch.nn.Identity(), None, None).attack(a, torch.zeros(1))
+    with pytest.raises(ValueError, match="pinned"):
+        pcd.graph.PipelinedLoss(lambda x, y: (x.sum(), ()), a, a)
 
 
 def test_product_never_imports_the_oracle():
