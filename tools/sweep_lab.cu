@@ -133,6 +133,7 @@ int main() {
     run<16, 2, 0, 0, 2>("row min2", sms, d);
     run<16, 3, 3, 0, 2>("row min3 + col min3 tree (no warp red)", sms, d);
     run<16, 3, 3, 1, 2>("row min3 + col min3 tree + CREDUX (current)", sms, d);
+    run<16, 3, 3, 1, 1>("current, ONE CTA per SM (1 warp per scheduler)", sms, d);
     run<16, 2, 2, 1, 2>("row min2 + col min2 chain + CREDUX", sms, d);
     run<16, 2, 4, 1, 2>("row min2 + col min2 tree + CREDUX", sms, d);
     run<16, 3, 2, 1, 2>("row min3 + col min2 chain + CREDUX", sms, d);
