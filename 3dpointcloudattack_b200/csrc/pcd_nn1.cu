@@ -641,7 +641,8 @@ extern "C" const char *pcd_last_error(void) { return g_err; }
 
 // optional profiling hook: events recorded around the sweep launch of the next forward calls
 static thread_local cudaEvent_t g_sweep_ev0 = nullptr, g_sweep_ev1 = nullptr;
-static thread_local cudaEvent_t g_bwd_ev0 = nullptr, g_bwd_ev1 = nullptr;
+// process-wide, not thread-local: autograd runs backward functions on its own worker thread
+static cudaEvent_t g_bwd_ev0 = nullptr, g_bwd_ev1 = nullptr;
 extern "C" int pcd_nn1_set_backward_events(void *start_event, void *stop_event) {
     g_bwd_ev0 = (cudaEvent_t)start_event;
     g_bwd_ev1 = (cudaEvent_t)stop_event;

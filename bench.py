@@ -376,24 +376,29 @@ def run_ours(args):
         synth = importlib.import_module("3dpointcloudattack_b200.synth")
         o_l = synth.face_clouds(4, Nl, seed=4321).to(dev).repeat(Bl // 4, 1, 1).contiguous()
         a_l = (o_l + SIGMA * torch.randn(o_l.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(7))).requires_grad_(True)
-        ts, sw = [], []
+        ts, sw, bw = [], [], []
         for k in range(reps + 1):
             a_l.grad = None
-            s0, s1, e0, e1 = ev(), ev(), ev(), ev()
-            s0.record(); s1.record()                       # materialise the cudaEvent handles
+            s0, s1, b0, b1, e0, e1 = ev(), ev(), ev(), ev(), ev(), ev()
+            for x in (s0, s1, b0, b1):
+                x.record()                                 # materialise the cudaEvent handles
             lib.pcd_nn1_set_sweep_events(s0.cuda_event, s1.cuda_event)
+            lib.pcd_nn1_set_backward_events(b0.cuda_event, b1.cuda_event)
             e0.record()
             step(a_l, o_l)
             e1.record()
             lib.pcd_nn1_set_sweep_events(None, None)
+            lib.pcd_nn1_set_backward_events(None, None)
             torch.cuda.synchronize()
             if k:
-                ts.append(e0.elapsed_time(e1)); sw.append(s0.elapsed_time(s1))
+                ts.append(e0.elapsed_time(e1)); sw.append(s0.elapsed_time(s1)); bw.append(b0.elapsed_time(b1))
         pairs = float(Bl) * Nl * Nl
-        t, w = sum(ts) / len(ts), sum(sw) / len(sw)
+        t, w, bk = sum(ts) / len(ts), sum(sw) / len(sw), sum(bw) / len(bw)
+        bwd_gbs = 2.0 * Bl * Nl * BWD_BYTES_PER_POINT_DIR / (bk * 1e-3) / 1e9
         return {"workload": f"chamfer+hausdorff fwd+bwd B={Bl}/GPU N=M={Nl} (per-GPU shard of BASELINE configs[4])",
                 "ms_per_step": t, "value": pairs / (t * 1e-3) / 1e9, "unit": UNIT,
-                "sweep_ms": w, "sweep_tflops": FLOP_PER_PAIR * pairs / (w * 1e-3) / 1e12}
+                "sweep_ms": w, "sweep_tflops": FLOP_PER_PAIR * pairs / (w * 1e-3) / 1e12,
+                "backward_ms": bk, "backward_gbs": bwd_gbs, "backward_hbm_frac": bwd_gbs / load_peaks()[0]}
 
     large = large_cloud()
 
@@ -467,8 +472,9 @@ def run_ours(args):
                                   "peak": hbm_gbs, "unit": "GB/s", "frac": bwd_bytes / (bwd_avg_ms * 1e-3) / 1e9 / hbm_gbs,
                                   "peak_source": hbm_src, "ms": bwd_avg_ms,
                                   "loss_backward_ms_with_autograd": bwd_autograd_ms,
-                                  "note": "algorithmic 68 B per (point, direction) = 17.8 MB: too small for the HBM roofline, "
-                                          "launch-latency bound; the eager loss.backward() around it is python/autograd glue"},
+                                  "note": "algorithmic 68 B per (point, direction) = 17.8 MB: too small for the HBM roofline; timed between "
+                                          "events around the two memsets and the kernel as launched EAGERLY (host launch gaps included; "
+                                          "7.6 us inside the replayed graph); large_cloud.backward_* is the same kernel at 143 MB"},
             "cpu_baseline": cpu,
             "large_cloud": dict(large, sweep_frac=large["sweep_tflops"] / (fp32_peak / 1e12)),
             "cw_attack": {"metric": "CW attack iters/s", "iters_per_s_graph": float(cw_t[1]), "iters_per_s_eager": float(cw_t[0]),

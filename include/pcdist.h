@@ -107,7 +107,8 @@ int pcd_nn1_forward(const float *rows, int64_t r_sb, int64_t r_sp, int64_t r_sc,
  * launch on the caller's stream, so the dominant kernel can be timed live with CUDA events
  * without a profiler.  Pass NULL, NULL to switch it off. */
 int pcd_nn1_set_sweep_events(void *start_event, void *stop_event);
-/* Same for pcd_nn1_backward: recorded before its memsets / after its last kernel launch. */
+/* Same for pcd_nn1_backward: recorded before its memsets / after its last kernel launch.  Process-wide
+ * (PyTorch calls backward functions from its autograd worker thread), so set it around ONE backward at a time. */
 int pcd_nn1_set_backward_events(void *start_event, void *stop_event);
 
 /* Backward of everything derived from the NN-1 minima, through the saved argmins
