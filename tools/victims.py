@@ -92,3 +92,86 @@ def torch_graph_feature(x, k):
     feature = xt.view(B * N, -1)[idx, :].view(B, N, k, C)
     xr = xt.view(B, N, 1, C).repeat(1, 1, k, 1)
     return torch.cat((feature - xr, xr), dim=3).permute(0, 3, 1, 2).contiguous()
+
+
+def torch_sample_and_group(npoint, radius, nsample, xyz, points):
+    """The reference's formulation of model/pointnet2_utils.py:59-135 (FPS Python loop, square_distance + full sort
+    ball query, advanced-indexing gathers) on xyz.device -- the baseline the FPS / ball-query kernels replace."""
+    B, N, C = xyz.shape
+    dev = xyz.device
+    cent = torch.zeros(B, npoint, dtype=torch.long, device=dev)
+    dist = torch.ones(B, N, device=dev) * 1e10
+    far = torch.randint(0, N, (B,), dtype=torch.long).to(dev)
+    bi = torch.arange(B, dtype=torch.long, device=dev)
+    for i in range(npoint):
+        cent[:, i] = far
+        c = xyz[bi, far, :].view(B, 1, 3)
+        d = torch.sum((xyz - c) ** 2, -1)
+        m = d < dist
+        dist[m] = d[m]
+        far = torch.max(dist, -1)[1]
+    new_xyz = xyz[bi[:, None], cent]
+    sq = -2 * torch.matmul(new_xyz, xyz.permute(0, 2, 1))
+    sq += torch.sum(new_xyz ** 2, -1).view(B, npoint, 1)
+    sq += torch.sum(xyz ** 2, -1).view(B, 1, N)
+    gi = torch.arange(N, dtype=torch.long, device=dev).view(1, 1, N).repeat([B, npoint, 1])
+    gi[sq > radius ** 2] = N
+    gi = gi.sort(dim=-1)[0][:, :, :nsample]
+    first = gi[:, :, 0].view(B, npoint, 1).repeat([1, 1, nsample])
+    mask = gi == N
+    gi[mask] = first[mask]
+    grouped = xyz[bi[:, None, None], gi] - new_xyz.view(B, npoint, 1, C)
+    if points is not None:
+        grouped = torch.cat([grouped, points[bi[:, None, None], gi]], dim=-1)
+    return new_xyz, grouped
+
+
+class _SetAbstraction(nn.Module):
+    def __init__(self, npoint, radius, nsample, in_channel, mlp, group_all, sample_and_group):
+        super().__init__()
+        self.npoint, self.radius, self.nsample, self.group_all, self.sag = npoint, radius, nsample, group_all, sample_and_group
+        self.convs, self.bns = nn.ModuleList(), nn.ModuleList()
+        last = in_channel
+        for out in mlp:
+            self.convs.append(nn.Conv2d(last, out, 1)); self.bns.append(nn.BatchNorm2d(out)); last = out
+
+    def forward(self, xyz, points):
+        xyz = xyz.permute(0, 2, 1)
+        if points is not None:
+            points = points.permute(0, 2, 1)
+        if self.group_all:
+            B, N, C = xyz.shape
+            new_xyz = torch.zeros(B, 1, C, device=xyz.device)
+            new_points = xyz.view(B, 1, N, C) if points is None else torch.cat([xyz.view(B, 1, N, C), points.view(B, 1, N, -1)], dim=-1)
+        else:
+            new_xyz, new_points = self.sag(self.npoint, self.radius, self.nsample, xyz, points)
+        new_points = new_points.permute(0, 3, 2, 1)
+        for conv, bn in zip(self.convs, self.bns):
+            new_points = F.relu(bn(conv(new_points)))
+        return new_xyz.permute(0, 2, 1), torch.max(new_points, 2)[0]
+
+
+class PointNet2SSGVictim(nn.Module):
+    """PointNet++ SSG classifier with the layer shapes of the reference's model/pointnet2_SSG.py:230-254
+    (SA 512/0.2/32 [64,64,128], SA 128/0.4/64 [128,128,256], global SA [256,512,1024], 1024-512-256-classes),
+    written from the public architecture; `sample_and_group(npoint, radius, nsample, xyz, points)` is injected."""
+
+    def __init__(self, sample_and_group, num_classes=106):
+        super().__init__()
+        self.sa1 = _SetAbstraction(512, 0.2, 32, 3, [64, 64, 128], False, sample_and_group)
+        self.sa2 = _SetAbstraction(128, 0.4, 64, 128 + 3, [128, 128, 256], False, sample_and_group)
+        self.sa3 = _SetAbstraction(None, None, None, 256 + 3, [256, 512, 1024], True, sample_and_group)
+        self.fc1, self.bn1, self.drop1 = nn.Linear(1024, 512), nn.BatchNorm1d(512), nn.Dropout(0.4)
+        self.fc2, self.bn2, self.drop2 = nn.Linear(512, 256), nn.BatchNorm1d(256), nn.Dropout(0.4)
+        self.fc3 = nn.Linear(256, num_classes)
+
+    def forward(self, xyz):
+        B = xyz.shape[0]
+        l1_xyz, l1_points = self.sa1(xyz, None)
+        l2_xyz, l2_points = self.sa2(l1_xyz, l1_points)
+        _, l3_points = self.sa3(l2_xyz, l2_points)
+        x = l3_points.view(B, 1024)
+        x = self.drop1(F.relu(self.bn1(self.fc1(x))))
+        x = self.drop2(F.relu(self.bn2(self.fc2(x))))
+        x = F.log_softmax(self.fc3(x), -1)
+        return x, x, x
