@@ -25,10 +25,9 @@ SIGNATURES = {
     "pcd_version": (_I, []),
     "pcd_last_error": (_c.c_char_p, []),
     "pcd_nn1_workspace_bytes": (_Z, [_I, _I, _I]),
-    "pcd_nn1_forward": (_I, _CLOUD + _CLOUD + [_I, _I, _I, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
-    "pcd_nn1_set_sweep_events": (_I, [_P, _P]),
-    "pcd_nn1_set_backward_events": (_I, [_P, _P]),
-    "pcd_nn1_backward": (_I, _CLOUD + _CLOUD + [_I, _I, _I, _I, _I] + [_P] * 12 + [_c.POINTER(_L), _F, _F] + _CLOUD + _CLOUD + [_P]),
+    "pcd_nn1_forward": (_I, _CLOUD + _CLOUD + [_I, _I, _I, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P,
+                                               _P, _Z, _P, _Z, _P, _Z, _I, _I, _P, _P, _P]),
+    "pcd_nn1_backward": (_I, _CLOUD + _CLOUD + [_I, _I, _I, _I, _I] + [_P] * 12 + [_c.POINTER(_L), _F, _F] + _CLOUD + _CLOUD + [_I, _P]),
     "pcd_knn_workspace_bytes": (_Z, [_I, _I, _I, _I, _I]),
     "pcd_knn_forward": (_I, _CLOUD + _CLOUD + [_I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),
     "pcd_knn_backward": (_I, _CLOUD + _CLOUD + [_I, _I, _I, _I, _I, _P, _P] + _CLOUD + _CLOUD + [_P]),
@@ -36,7 +35,7 @@ SIGNATURES = {
     "pcd_edge_feature_forward": (_I, [_P, _P, _I, _I, _I, _I, _I, _c.POINTER(_I), _P, _P]),
     "pcd_edge_feature_backward": (_I, [_P, _P, _I, _I, _I, _I, _I, _c.POINTER(_I), _P, _P]),
     "pcd_fps": (_I, [_P, _L, _L, _L, _I, _I, _I, _P, _P, _P]),
-    "pcd_measure_fp32_peak": (_I, [_I, _c.POINTER(_c.c_double), _P]),
+    "pcd_fp32_probe_launch": (_I, [_I, _I, _P, _c.POINTER(_c.c_double), _P]),
 }
 
 _lib = None

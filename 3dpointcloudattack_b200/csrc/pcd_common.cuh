@@ -174,4 +174,49 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src
         : "memory");
 }
 
+// ------------------------------------------------- programmatic dependent launch (sm_90+)
+// A kernel launched with the programmatic-stream-serialization attribute may become resident
+// while its predecessor in the stream is still running; it must execute pdl_wait() before it
+// touches anything the predecessor writes.  pdl_launch_dependents() in the predecessor allows the
+// successor's CTAs to be scheduled from that point on.  Both are no-ops in a normal launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                        bool programmatic, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = programmatic ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// Per-device cache of a small integer property (SM count, occupancy of one kernel): the queries cost
+// microseconds and the answer differs between the devices of one process.
+struct PerDeviceInt {
+    int v[64];
+};
+static inline int current_device() {
+    int dev = 0;
+    return cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 ? dev : -1;
+}
+static inline int num_sms() {
+    static PerDeviceInt cache = {};
+    const int dev = current_device();
+    if (dev < 0) return 0;
+    if (cache.v[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+        cache.v[dev] = n;
+    }
+    return cache.v[dev];
+}
+
 }  // namespace pcd

@@ -3,7 +3,9 @@
 // MEASURED_PEAKS.json carries HBM and bf16 tensor peaks only; the NN-1 / k-NN sweeps are bound
 // by the CUDA-core fp32 pipe, so bench.py measures that denominator in the same run: an
 // FFMA-only kernel (16 independent accumulator chains per thread, scalar FFMA and packed
-// FFMA2 variants; the larger of the two is reported).
+// FFMA2 variants; the larger of the two is reported).  The entry point only LAUNCHES the probe
+// (stream-ordered, allocation-free, like every other call of the ABI); the caller brackets it
+// with its own CUDA events.
 #include "pcd_common.cuh"
 
 namespace pcd {
@@ -48,41 +50,20 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(float *out, int iters, fl
 
 using namespace pcd;
 
-extern "C" int pcd_measure_fp32_peak(int iters, double *flops_per_s, void *stream) {
-    if (!flops_per_s || iters <= 0) {
-        set_error("pcd_measure_fp32_peak: bad argument");
+extern "C" int pcd_fp32_probe_launch(int variant, int iters, float *scratch, double *flop_count, void *stream) {
+    if (!flop_count || !scratch || iters <= 0 || variant < 0 || variant > 1) {
+        set_error("pcd_fp32_probe_launch: bad argument");
         return PCD_ERR_ARG;
     }
-    int dev = 0, sms = 0;
-    PCD_CUDA_CHECK(cudaGetDevice(&dev));
-    PCD_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int sms = num_sms();
+    if (sms <= 0) return cuda_fail(cudaGetLastError(), "no CUDA device");
     cudaStream_t st = (cudaStream_t)stream;
-    float *scratch = nullptr;
-    PCD_CUDA_CHECK(cudaMalloc(&scratch, 256));
-    cudaEvent_t e0, e1;
-    PCD_CUDA_CHECK(cudaEventCreate(&e0));
-    PCD_CUDA_CHECK(cudaEventCreate(&e1));
     const int grid = sms * 8;
-    double best = 0.0;
-    for (int variant = 0; variant < 2; ++variant) {
-        for (int rep = 0; rep < 4; ++rep) {   // first rep = warm-up
-            PCD_CUDA_CHECK(cudaEventRecord(e0, st));
-            if (variant == 0) fma_peak_kernel<false><<<grid, 256, 0, st>>>(scratch, iters, 1.0001f, 0.5f);
-            else fma_peak_kernel<true><<<grid, 256, 0, st>>>(scratch, iters, 1.0001f, 0.5f);
-            PCD_CUDA_CHECK(cudaGetLastError());
-            PCD_CUDA_CHECK(cudaEventRecord(e1, st));
-            PCD_CUDA_CHECK(cudaEventSynchronize(e1));
-            float ms = 0.f;
-            PCD_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
-            // 64 FMA per thread per iteration in both variants (16*4 scalar, 8*8 packed x 2 / 2 .. see below)
-            const double fma_per_thread = (variant == 0) ? 64.0 * iters : 128.0 * iters;
-            const double flops = 2.0 * fma_per_thread * 256.0 * grid / (ms * 1e-3);
-            if (rep > 0 && flops > best) best = flops;
-        }
-    }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaFree(scratch);
-    *flops_per_s = best;
+    if (variant == 0) fma_peak_kernel<false><<<grid, 256, 0, st>>>(scratch, iters, 1.0001f, 0.5f);
+    else fma_peak_kernel<true><<<grid, 256, 0, st>>>(scratch, iters, 1.0001f, 0.5f);
+    PCD_CUDA_CHECK(cudaGetLastError());
+    // scalar: 16 chains x 4 repeats = 64 FMA per thread and iteration; packed: 8 x 8 FFMA2 = 128 FMA
+    const double fma_per_thread = (variant == 0) ? 64.0 * iters : 128.0 * iters;
+    *flop_count = 2.0 * fma_per_thread * 256.0 * grid;
     return PCD_OK;
 }

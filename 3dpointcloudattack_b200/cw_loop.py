@@ -79,7 +79,11 @@ class ProjectInnerClipLinf(nn.Module):
 
 class CWAttack:
     def __init__(self, model, adv_func, dist_func, attack_lr=1e-2, init_weight=10., max_weight=80.,
-                 binary_step=10, num_iter=500, clip_func=None, global_batch=None, use_graph=False):
+                 binary_step=10, num_iter=500, clip_func=None, global_batch=None, use_graph=False,
+                 attack_method="untarget"):
+        if attack_method not in ("untarget", "target"):
+            raise ValueError("attack_method must be 'untarget' or 'target' (CW_attack.py:28)")
+        self.attack_method = attack_method
         self.model = model.eval()
         for p in self.model.parameters():
             p.requires_grad_(False)
@@ -97,7 +101,8 @@ class CWAttack:
         pred = torch.argmax(logits, dim=1)
         with torch.no_grad():
             dist_val = torch.sqrt(torch.sum((adv - ori) ** 2, dim=[1, 2]))
-            ok = pred != target                                                   # untargeted success
+            st["last_input"].copy_(adv)          # `input_val`: the iterate this iteration STARTS from (CW_attack.py:132)
+            ok = (pred != target) if self.attack_method == "untarget" else (pred == target)   # CW_attack.py:136-153
             better = ok & (dist_val < st["bestdist"])
             st["bestdist"].copy_(torch.where(better, dist_val, st["bestdist"]))
             st["bestscore"].copy_(torch.where(better, pred, st["bestscore"]))
@@ -139,6 +144,7 @@ class CWAttack:
             "bestdist": torch.full((B,), 1e10, device=dev),
             "bestscore": torch.full((B,), -1, dtype=torch.long, device=dev),
             "loss": torch.zeros((), device=dev),
+            "last_input": ori.clone(),
             "adv": ori.clone().requires_grad_(True),
         }
         graph = None
@@ -167,13 +173,14 @@ class CWAttack:
             e1.record()
             spans.append((e0, e1))
             with torch.no_grad():                     # binary search of the distance weight (CW_attack.py:182-200)
-                succ = (st["bestscore"] != target) & (st["bestscore"] != -1) & (st["bestdist"] <= st["o_bestdist"])
+                hit = (st["bestscore"] != target) if self.attack_method == "untarget" else (st["bestscore"] == target)
+                succ = hit & (st["bestscore"] != -1) & (st["bestdist"] <= st["o_bestdist"])
                 lower = torch.where(succ, torch.maximum(lower, st["weight"]), lower)
                 upper = torch.where(succ, upper, torch.minimum(upper, st["weight"]))
                 st["weight"].copy_((lower + upper) / 2.)
-        with torch.no_grad():                         # samples never attacked successfully keep the last iterate
-            fail = lower == 0.
-            st["o_bestattack"].copy_(torch.where(fail[:, None, None], st["adv"].detach(), st["o_bestattack"]))
+        with torch.no_grad():        # samples never attacked successfully get `input_val` of the last iteration, i.e. the
+            fail = lower == 0.       # iterate BEFORE the final Adam step and clip (CW_attack.py:203-206)
+            st["o_bestattack"].copy_(torch.where(fail[:, None, None], st["last_input"], st["o_bestattack"]))
         torch.cuda.synchronize(dev)
         self.loop_ms = sum(a.elapsed_time(b) for a, b in spans)
         return st["o_bestdist"], st["o_bestattack"].transpose(1, 2).contiguous(), ~fail

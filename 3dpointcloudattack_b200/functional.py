@@ -16,7 +16,7 @@ from . import _lib
 from ._lib import (EDGE_CENTER, EDGE_DIFF, EDGE_NEIGHBOR, FORM_COL_ROW, FORM_ROW_COL, FORM_SUM_FIRST, NORM_FMA, NORM_MULSUM,
                    VALUE_SQRT_CLAMP, VALUE_SQUARED)
 
-__all__ = ["nn1", "NN1Result", "knn", "ball_query", "edge_feature", "farthest_point_sample", "fp32_peak_flops",
+__all__ = ["nn1", "NN1Result", "time_next_sweep", "clear_cache", "knn", "ball_query", "edge_feature", "farthest_point_sample", "fp32_peak_flops",
            "EDGE_CENTER", "EDGE_NEIGHBOR", "EDGE_DIFF",
            "FORM_ROW_COL", "FORM_COL_ROW", "FORM_SUM_FIRST", "NORM_MULSUM", "NORM_FMA",
            "VALUE_SQUARED", "VALUE_SQRT_CLAMP"]
@@ -78,14 +78,35 @@ class _Token:
         self.consumed = False
 
 
+_tiling = (0, 0)          # (rows per lane, column tile) override for the next calls; (0, 0) = heuristic (tests / tuning)
+_sweep_events = None     # (start, stop) torch.cuda.Event pair consumed by the next _NN1.forward (bench.py's roofline)
+
+
+def time_next_sweep(start_event, stop_event):
+    """Measurement helper: the next nn1() call on this thread records the two torch.cuda.Event
+    objects immediately before / after its sweep kernel launch (passed per call through the C ABI;
+    the library itself keeps no state).  The event between the kernels costs that call the
+    programmatic overlap of the chain, nothing else."""
+    global _sweep_events
+    _sweep_events = None if start_event is None else (start_event, stop_event)
+
+
+def force_tiling(rows_per_lane=0, col_tile=0):
+    """Tests / tuning sweeps: force the sweep's tile shape for the following nn1() calls (0, 0 = heuristic)."""
+    global _tiling
+    _tiling = (int(rows_per_lane), int(col_tile))
+
+
 class _NN1(torch.autograd.Function):
     @staticmethod
     def forward(ctx, rows, cols, form, norm, swap_norms, transform, row_scale, col_scale, token):
-        global _launch_count
+        global _launch_count, _sweep_events
         lib = _lib.load()
         B, N, _ = rows.shape
         M = cols.shape[1]
         dev = rows.device
+        need_r, need_c = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        ev, _sweep_events = _sweep_events, None
         with _on(dev):
             row_min = torch.empty((B, N), dtype=torch.float32, device=dev)
             col_min = torch.empty((B, M), dtype=torch.float32, device=dev)
@@ -95,16 +116,25 @@ class _NN1(torch.autograd.Function):
             stats_i = torch.empty((2, B), dtype=torch.int32, device=dev)
             ws_bytes = lib.pcd_nn1_workspace_bytes(B, N, M)
             ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+            # gradient buffers of the coming backward: the forward's last kernel clears them on the way, so the
+            # backward is ONE launch (atomics into zeroed memory) instead of memset + memset + kernel
+            grad_rows = torch.empty((B, N, 3), dtype=torch.float32, device=dev) if need_r and (B * N * 3) % 4 == 0 else None
+            grad_cols = torch.empty((B, M, 3), dtype=torch.float32, device=dev) if need_c and (B * M * 3) % 4 == 0 else None
             st = lib.pcd_nn1_forward(*_cloud_args(rows), *_cloud_args(cols), B, N, M,
                                      form, norm, int(swap_norms), transform, row_scale, col_scale,
                                      row_min.data_ptr(), row_arg.data_ptr(), col_min.data_ptr(), col_arg.data_ptr(),
                                      stats.data_ptr(), stats_i.data_ptr(),
-                                     ws.data_ptr(), ws_bytes, _stream(dev))
+                                     _ptr(grad_rows), 0 if grad_rows is None else grad_rows.numel(),
+                                     _ptr(grad_cols), 0 if grad_cols is None else grad_cols.numel(),
+                                     ws.data_ptr(), ws_bytes, _tiling[0], _tiling[1],
+                                     None if ev is None else ev[0].cuda_event, None if ev is None else ev[1].cuda_event,
+                                     _stream(dev))
             _lib.check(st, "pcd_nn1_forward")
-        _launch_count += 4
+        _launch_count += 3
         ctx.save_for_backward(rows, cols, row_arg, col_arg, row_min, col_min, stats_i)
         ctx.cfg = (int(swap_norms), transform, row_scale, col_scale)
         ctx.token = token
+        ctx.zeroed = [grad_rows, grad_cols]      # valid for ONE backward (retain_graph re-runs allocate afresh)
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(row_arg, col_arg, stats_i)
         return row_min, row_arg, col_min, col_arg, stats[0], stats[1], stats[2], stats[3], stats_i
@@ -129,8 +159,11 @@ class _NN1(torch.autograd.Function):
             # (stride 0) views for sum()/mean() and we do not want a copy kernel per gradient
             w = [g_row_sum, g_row_max, g_col_sum, g_col_max]
             w_strides = (ctypes.c_int64 * 4)(*[0 if t is None else t.stride(0) for t in w])
-            grad_rows = torch.empty((B, N, 3), dtype=torch.float32, device=dev) if need_r else None
-            grad_cols = torch.empty((B, M, 3), dtype=torch.float32, device=dev) if need_c else None
+            zr, zc = ctx.zeroed
+            ctx.zeroed = [None, None]
+            prezeroed = (not need_r or zr is not None) and (not need_c or zc is not None)
+            grad_rows = (zr if prezeroed else torch.empty((B, N, 3), dtype=torch.float32, device=dev)) if need_r else None
+            grad_cols = (zc if prezeroed else torch.empty((B, M, 3), dtype=torch.float32, device=dev)) if need_c else None
             gr = _cloud_args(grad_rows) if need_r else [None, 0, 0, 0]
             gc = _cloud_args(grad_cols) if need_c else [None, 0, 0, 0]
             st = lib.pcd_nn1_backward(*_cloud_args(rows), *_cloud_args(cols), B, N, M, swap_norms, transform,
@@ -138,7 +171,7 @@ class _NN1(torch.autograd.Function):
                                       _ptr(g_row), _ptr(g_col),
                                       _ptr(w[0]), _ptr(w[1]), stats_i[0].data_ptr(),
                                       _ptr(w[2]), _ptr(w[3]), stats_i[1].data_ptr(),
-                                      w_strides, row_scale, col_scale, *gr, *gc, _stream(dev))
+                                      w_strides, row_scale, col_scale, *gr, *gc, int(prezeroed), _stream(dev))
             _lib.check(st, "pcd_nn1_backward")
         _launch_count += 1
         return grad_rows, grad_cols, None, None, None, None, None, None, None
@@ -164,6 +197,13 @@ def nn1(rows, cols, form, norm, swap_norms=False, transform=VALUE_SQUARED, row_s
     again with the very same tensors (same storage, same version counter) and mode -- the
     reference's losses recompute the same adv->ori nearest neighbours up to six times per
     iteration (attack/GeoA3/GeoA3_attack.py:134-166, Chamfer then Hausdorff in CW).
+
+    The cache is only consulted while an autograd graph is being recorded (grad mode on and one
+    of the clouds requires grad) and its entry dies with the first backward() through it: one
+    entry = one forward pass of one iteration.  Under no_grad nothing is cached -- in-place
+    writes through `.data` (the clip / projection steps of the attack loops) do not bump the
+    version counter, so a cached no_grad result could be stale.  Code that mutates a cloud
+    through `.data` BETWEEN two calls inside the same recorded forward must call clear_cache().
     """
     _check_cloud(rows, "rows"); _check_cloud(cols, "cols")
     if rows.shape[0] != cols.shape[0]:
@@ -173,9 +213,10 @@ def nn1(rows, cols, form, norm, swap_norms=False, transform=VALUE_SQUARED, row_s
     if rows.shape[1] == 0 or cols.shape[1] == 0 or rows.shape[0] == 0:
         raise ValueError("empty clouds are not supported (the reference's min() raises as well)")
     key = None
+    cache = cache and torch.is_grad_enabled() and (rows.requires_grad or cols.requires_grad)
     if cache:
         key = (_tensor_key(rows), _tensor_key(cols), form, norm, bool(swap_norms), transform,
-               float(row_sum_scale), float(col_sum_scale), torch.is_grad_enabled())
+               float(row_sum_scale), float(col_sum_scale))
         if _nn1_cache["key"] == key and not _nn1_cache["token"].consumed:
             return _nn1_cache["val"]
     token = _Token()
@@ -368,10 +409,20 @@ def farthest_point_sample(xyz, npoint, start=None):
 
 
 def fp32_peak_flops(iters=2048):
-    """Measured fp32 FMA peak of the current device (FLOP/s) -- roofline denominator."""
-    import ctypes
+    """Measured fp32 FMA peak of the current device (FLOP/s) -- roofline denominator: the larger of
+    the scalar-FFMA and packed-FFMA2 probe kernels, best of three timed launches each (CUDA events)."""
     lib = _lib.load()
-    out = ctypes.c_double(0.0)
-    st = lib.pcd_measure_fp32_peak(int(iters), ctypes.byref(out), _stream())
-    _lib.check(st, "pcd_measure_fp32_peak")
-    return out.value
+    scratch = torch.empty(64, dtype=torch.float32, device="cuda")
+    flop = ctypes.c_double(0.0)
+    best = 0.0
+    for variant in (0, 1):
+        for rep in range(4):                                  # first = warm-up
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            st = lib.pcd_fp32_probe_launch(variant, int(iters), scratch.data_ptr(), ctypes.byref(flop), _stream())
+            _lib.check(st, "pcd_fp32_probe_launch")
+            e1.record()
+            e1.synchronize()
+            if rep:
+                best = max(best, flop.value / (e0.elapsed_time(e1) * 1e-3))
+    return best

@@ -23,6 +23,8 @@ class GraphedLoss:
         self.fn = fn
         self.adv = adv.detach().clone().requires_grad_(True)
         self.ori = ori.detach().clone()
+        # d(loss)/d(loss) = 1 as a static tensor: loss.backward() would launch a fill kernel on every replay
+        self._one = torch.ones((), dtype=torch.float32, device=adv.device)
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
@@ -30,14 +32,14 @@ class GraphedLoss:
             for _ in range(warmup):
                 self.adv.grad = None
                 loss, _ = fn(self.adv, self.ori)
-                loss.backward()
+                torch.autograd.backward(loss, grad_tensors=self._one.expand_as(loss))
         cur.wait_stream(side)
         torch.cuda.synchronize()
         self.adv.grad = None
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph, stream=side):      # same stream as the warm-up (AccumulateGrad node)
             self.loss, self.aux = fn(self.adv, self.ori)
-            self.loss.backward()
+            torch.autograd.backward(self.loss, grad_tensors=self._one.expand_as(self.loss))
         self.grad = self.adv.grad
 
     def replay(self, adv=None, ori=None):
@@ -94,6 +96,7 @@ class PipelinedLoss:
             cur.wait_stream(st)
         torch.cuda.synchronize(dev)
         self.aux_host = [[torch.empty(shape, dtype=dtype).pin_memory() for shape, dtype in per] for per in aux_shapes]
+        self._one = torch.ones((), dtype=torch.float32, device=dev)
         for a in self.adv_dev:
             a.grad = None
         self.graph = torch.cuda.CUDAGraph()
@@ -110,7 +113,7 @@ class PipelinedLoss:
                     prev_h2d = torch.cuda.Event()
                     prev_h2d.record(st)
                     loss, aux = fn(self.adv_dev[c], self.ori_dev[c])
-                    loss.backward()
+                    torch.autograd.backward(loss, grad_tensors=self._one.expand_as(loss))
                     for out, a in zip(self.aux_host[c], aux):
                         out.copy_(a.detach(), non_blocking=True)
                     self.grad_host[lo:hi].copy_(self.adv_dev[c].grad, non_blocking=True)

@@ -16,7 +16,7 @@ value      device-timed (CUDA events per step, L2 flushed between steps outside 
 e2e        same step from pinned HOST buffers: H2D of adv and ori, fwd+bwd, D2H of the four
            loss vectors and the gradient w.r.t. adv; host<->device copies inside the timed region.
 roofline   the sweep kernel alone, timed live with CUDA events recorded inside the C ABI around
-           its launch (pcd_nn1_set_sweep_events); peak = fp32 FMA rate measured in the same
+           its launch (event arguments of pcd_nn1_forward); peak = fp32 FMA rate measured in the same
            run by an FFMA micro-kernel (MEASURED_PEAKS.json has no CUDA-core fp32 figure).
 cpu_baseline  the reference's torch CPU path (oracle/ref_torch_port.py: op-for-op restatement)
            on the host cores, on a bounded sample (B_chunk samples of the same workload).
@@ -244,8 +244,7 @@ def run_ours(args):
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
     sweep_ev = [(ev(), ev()) for _ in range(args.steps)]
-    bwdk_ev = [(ev(), ev()) for _ in range(args.steps)]
-    for a, b in sweep_ev + bwdk_ev:                           # materialise the cudaEvent handles
+    for a, b in sweep_ev:                                     # materialise the cudaEvent handles
         a.record(); b.record()
     torch.cuda.synchronize()
 
@@ -267,22 +266,46 @@ def run_ours(args):
         flush.zero_()
         adv.grad = None
         e0, e1, e2 = ev(), ev(), ev()
-        lib.pcd_nn1_set_sweep_events(sweep_ev[k][0].cuda_event, sweep_ev[k][1].cuda_event)
-        lib.pcd_nn1_set_backward_events(bwdk_ev[k][0].cuda_event, bwdk_ev[k][1].cuda_event)
+        F.time_next_sweep(sweep_ev[k][0], sweep_ev[k][1])     # events passed per call through the C ABI
         e0.record()
         loss, _ = loss_fn(adv, ori)
         e1.record()
         loss.backward()
         e2.record()
-        lib.pcd_nn1_set_sweep_events(None, None)
-        lib.pcd_nn1_set_backward_events(None, None)
         eager_ev.append((e0, e2)); bwd_ev.append((e1, e2))
     torch.cuda.synchronize()
     launches_per_step = (F.launches() - launches0) // args.steps
     eager_ms = [a.elapsed_time(b) for a, b in eager_ev]
     sweep_ms = [a.elapsed_time(b) for a, b in sweep_ev]
     bwd_ms = [a.elapsed_time(b) for a, b in bwd_ev]
-    bwdk_ms = [a.elapsed_time(b) for a, b in bwdk_ev]
+
+    # the backward kernel alone: one pcd_nn1_backward launch (pre-zeroed gradient buffer) between two events
+    def time_backward_kernel(a_t, o_t, reps):
+        import ctypes
+        Bq, Nq = a_t.shape[0], a_t.shape[1]
+        r = F.nn1(o_t, a_t.detach(), F.FORM_SUM_FIRST, F.NORM_FMA, row_sum_scale=1.0 / Nq, col_sum_scale=1.0 / Nq, cache=False)
+        g = torch.zeros_like(a_t)
+        wv = torch.ones(Bq, device=dev)
+        ws_ = (ctypes.c_int64 * 4)(1, 1, 1, 1)
+        out = []
+        for _ in range(reps + 2):
+            g.zero_()
+            flush.zero_()
+            b0, b1 = ev(), ev()
+            b0.record()
+            st_ = lib.pcd_nn1_backward(o_t.data_ptr(), *o_t.stride(), a_t.data_ptr(), *a_t.stride(), Bq, Nq, Nq, 0, 0,
+                                       r.row_arg.data_ptr(), r.col_arg.data_ptr(), r.row_min.data_ptr(), r.col_min.data_ptr(),
+                                       None, None, wv.data_ptr(), wv.data_ptr(), r.row_argmax.data_ptr(),
+                                       wv.data_ptr(), wv.data_ptr(), r.col_argmax.data_ptr(), ws_, 1.0 / Nq, 1.0 / Nq,
+                                       None, 0, 0, 0, g.data_ptr(), *g.stride(), 1, torch.cuda.current_stream().cuda_stream)
+            pcd._lib.check(st_, "pcd_nn1_backward")
+            b1.record()
+            out.append((b0, b1))
+        torch.cuda.synchronize()
+        ms = sorted(x.elapsed_time(y) for x, y in out[2:])
+        return ms[len(ms) // 2]
+
+    bwdk_med_ms = time_backward_kernel(adv.detach(), ori, args.steps)
 
     # ---------------- timed region: the same step captured once as a CUDA graph and replayed -----
     graphed = pcd.graph.GraphedLoss(loss_fn, adv, ori, warmup=3)
@@ -372,28 +395,28 @@ def run_ours(args):
     d2h = loss_h.numel() * 4 + grad_h.numel() * 4
 
     # ---------------- secondary: the per-GPU shard of BASELINE configs[4] (B=512 N=M=16384 over 8 GPUs = 64 per GPU) ----
-    def large_cloud(Bl=64, Nl=16384, reps=3):
+    def large_cloud(Bl=64, Nl=16384, reps=10):
         synth = importlib.import_module("3dpointcloudattack_b200.synth")
         o_l = synth.face_clouds(4, Nl, seed=4321).to(dev).repeat(Bl // 4, 1, 1).contiguous()
         a_l = (o_l + SIGMA * torch.randn(o_l.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(7))).requires_grad_(True)
         ts, sw, bw = [], [], []
         for k in range(reps + 1):
             a_l.grad = None
-            s0, s1, b0, b1, e0, e1 = ev(), ev(), ev(), ev(), ev(), ev()
-            for x in (s0, s1, b0, b1):
+            s0, s1, e0, e1 = ev(), ev(), ev(), ev()
+            for x in (s0, s1):
                 x.record()                                 # materialise the cudaEvent handles
-            lib.pcd_nn1_set_sweep_events(s0.cuda_event, s1.cuda_event)
-            lib.pcd_nn1_set_backward_events(b0.cuda_event, b1.cuda_event)
+            flush.zero_()
+            F.time_next_sweep(s0, s1)
             e0.record()
             step(a_l, o_l)
             e1.record()
-            lib.pcd_nn1_set_sweep_events(None, None)
-            lib.pcd_nn1_set_backward_events(None, None)
             torch.cuda.synchronize()
             if k:
-                ts.append(e0.elapsed_time(e1)); sw.append(s0.elapsed_time(s1)); bw.append(b0.elapsed_time(b1))
+                ts.append(e0.elapsed_time(e1)); sw.append(s0.elapsed_time(s1))
+        bw = [time_backward_kernel(a_l.detach(), o_l, 5)]
         pairs = float(Bl) * Nl * Nl
-        t, w, bk = sum(ts) / len(ts), sum(sw) / len(sw), sum(bw) / len(bw)
+        med = lambda v: sorted(v)[len(v) // 2]
+        t, w, bk = med(ts), med(sw), med(bw)
         bwd_gbs = 2.0 * Bl * Nl * BWD_BYTES_PER_POINT_DIR / (bk * 1e-3) / 1e9
         return {"workload": f"chamfer+hausdorff fwd+bwd B={Bl}/GPU N=M={Nl} (per-GPU shard of BASELINE configs[4])",
                 "ms_per_step": t, "value": pairs / (t * 1e-3) / 1e9, "unit": UNIT,
@@ -431,7 +454,7 @@ def run_ours(args):
         fp32_peak = F.fp32_peak_flops(2048)
         sweep_avg_ms = sum(sweep_ms) / len(sweep_ms)
         achieved = FLOP_PER_PAIR * pairs_step_rank / (sweep_avg_ms * 1e-3) / 1e12
-        bwd_avg_ms = sum(bwdk_ms) / len(bwdk_ms)             # memset + nn1_bwd_kernel, events inside the C ABI
+        bwd_avg_ms = bwdk_med_ms                              # nn1_bwd_kernel<2> alone (gradient buffer pre-zeroed by the forward)
         bwd_autograd_ms = sum(bwd_ms) / len(bwd_ms)
         bwd_bytes = 2.0 * B * NPTS * BWD_BYTES_PER_POINT_DIR
         cpu = None
@@ -466,15 +489,15 @@ def run_ours(args):
                          "unit": "TFLOP/s", "frac": achieved / (fp32_peak / 1e12), "traffic": SWEEP_DRAM_BYTES_PER_LAUNCH,
                          "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one launch at this "
                                            "workload (profiles/r1_v6_ncu_summary.txt); algorithmic input bytes = 6.29 MB",
-                         "peak_source": "FFMA/FFMA2 micro-kernel measured in this run (pcd_measure_fp32_peak)",
+                         "peak_source": "FFMA/FFMA2 micro-kernel measured in this run (pcd_fp32_probe_launch between CUDA events)",
                          "ms_per_launch": sweep_avg_ms, "flop_per_pair": FLOP_PER_PAIR},
-            "roofline_backward": {"bound": "hbm", "kernel": "memset + nn1_bwd_kernel<2>", "achieved": bwd_bytes / (bwd_avg_ms * 1e-3) / 1e9,
+            "roofline_backward": {"bound": "hbm", "kernel": "nn1_bwd_kernel<2>", "achieved": bwd_bytes / (bwd_avg_ms * 1e-3) / 1e9,
                                   "peak": hbm_gbs, "unit": "GB/s", "frac": bwd_bytes / (bwd_avg_ms * 1e-3) / 1e9 / hbm_gbs,
                                   "peak_source": hbm_src, "ms": bwd_avg_ms,
                                   "loss_backward_ms_with_autograd": bwd_autograd_ms,
-                                  "note": "algorithmic 68 B per (point, direction) = 17.8 MB: too small for the HBM roofline; timed between "
-                                          "events around the two memsets and the kernel as launched EAGERLY (host launch gaps included; "
-                                          "7.6 us inside the replayed graph); large_cloud.backward_* is the same kernel at 143 MB"},
+                                  "note": "algorithmic 68 B per (point, direction) = 17.8 MB: too small for the HBM roofline (launch "
+                                          "latency); one pcd_nn1_backward launch between two events, L2 flushed, median; "
+                                          "large_cloud.backward_* is the same kernel at 143 MB"},
             "cpu_baseline": cpu,
             "large_cloud": dict(large, sweep_frac=large["sweep_tflops"] / (fp32_peak / 1e12)),
             "cw_attack": {"metric": "CW attack iters/s", "iters_per_s_graph": float(cw_t[1]), "iters_per_s_eager": float(cw_t[0]),

@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define PCD_VERSION 100
+#define PCD_VERSION 200
 
 enum pcd_status {
     PCD_OK = 0,
@@ -90,6 +90,24 @@ const char *pcd_last_error(void);
  * row_sum_scale / col_sum_scale fold the reference's divisors into the kernel (1/N2 and 1/N1
  * for distance.py's means, 1/3 for dis_utils_torch.chamfer's quirk, 1 for plain sums); the sums
  * are accumulated in a fixed order (run-to-run deterministic).
+ * NaN / inf coordinates never fault: a point without any finite distance gets arg 0 and the
+ * value NaN (columns) or +inf (rows); NaN distances are skipped by the minima (the reference
+ * propagates them).
+ *
+ * Launches: three kernels chained by programmatic dependent launch (reset of the workspace
+ * keys -> sweep -> exact argmin + per-sample statistics).  Dense clouds -- point-major [.,N,3]
+ * (sp = 3, sc = 1) or channel-major [.,3,N] (sp = 1), base 16-byte aligned, N % 4 == 0,
+ * sb % 4 == 0 -- are streamed where they lie; any other layout and swap_norms are packed into
+ * the workspace first (same results).
+ * zero0 / zero1 (optional, NULL or 16-byte aligned, float counts multiples of 4): buffers the
+ * last kernel clears on the way -- pass the gradient buffers of the coming pcd_nn1_backward
+ * and call it with grads_prezeroed = 1.
+ * rows_per_lane / col_tile: 0 = the built-in tile-shape heuristic; 2, 4, 8, 16 / a power of two in
+ * 32..256 force the sweep's register blocking / TMA stage width (tests, tuning sweeps; results
+ * are identical for every tiling).
+ * sweep_start_event / sweep_stop_event (optional cudaEvent_t): recorded on `stream` immediately
+ * before / after the sweep kernel launch so a caller can time the dominant kernel live with
+ * CUDA events (bench.py's roofline); per call, no global state.
  * ---------------------------------------------------------------------------------- */
 size_t pcd_nn1_workspace_bytes(int B, int N, int M);
 
@@ -100,16 +118,9 @@ int pcd_nn1_forward(const float *rows, int64_t r_sb, int64_t r_sp, int64_t r_sc,
                     float row_sum_scale, float col_sum_scale,
                     float *row_min, int32_t *row_arg, float *col_min, int32_t *col_arg,
                     float *stats_f, int32_t *stats_i,
-                    void *workspace, size_t workspace_bytes, void *stream);
-
-/* Profiling hook (bench.py): when both are non-NULL cudaEvent_t handles, every following
- * pcd_nn1_forward on this host thread records them immediately before / after the sweep kernel
- * launch on the caller's stream, so the dominant kernel can be timed live with CUDA events
- * without a profiler.  Pass NULL, NULL to switch it off. */
-int pcd_nn1_set_sweep_events(void *start_event, void *stop_event);
-/* Same for pcd_nn1_backward: recorded before its memsets / after its last kernel launch.  Process-wide
- * (PyTorch calls backward functions from its autograd worker thread), so set it around ONE backward at a time. */
-int pcd_nn1_set_backward_events(void *start_event, void *stop_event);
+                    float *zero0, size_t zero0_floats, float *zero1, size_t zero1_floats,
+                    void *workspace, size_t workspace_bytes, int rows_per_lane, int col_tile,
+                    void *sweep_start_event, void *sweep_stop_event, void *stream);
 
 /* Backward of everything derived from the NN-1 minima, through the saved argmins
  * (autograd of torch.min(dim) / torch.max / mean / cdist in the reference).
@@ -120,7 +131,8 @@ int pcd_nn1_set_backward_events(void *start_event, void *stop_event);
  * all one call.  For PCD_VALUE_SQRT_CLAMP row_min/col_min (the stored post-sqrt values) must
  * be given: d/dp sqrt(d2) = (p - q)/sqrt(d2), 0 where it is 0 (cdist backward).
  * grad_rows / grad_cols are written in full (no need to zero them) with the caller's strides;
- * either may be NULL when that cloud needs no gradient.
+ * either may be NULL when that cloud needs no gradient.  grads_prezeroed != 0: the caller
+ * guarantees both buffers are zero (pcd_nn1_forward's zero fill) -- one kernel launch, atomics only.
  * swap_norms: gradients of the swapped-norm surrogate exactly as autograd produces them
  * (norm terms land on the *other* index, attack/GeoA3/knn_utils.py:13-15).
  * ---------------------------------------------------------------------------------- */
@@ -137,7 +149,7 @@ int pcd_nn1_backward(const float *rows, int64_t r_sb, int64_t r_sp, int64_t r_sc
                      float row_sum_scale, float col_sum_scale,
                      float *grad_rows, int64_t gr_sb, int64_t gr_sp, int64_t gr_sc,
                      float *grad_cols, int64_t gc_sb, int64_t gc_sp, int64_t gc_sc,
-                     void *stream);
+                     int grads_prezeroed, void *stream);
 
 /* ------------------------------------------------------------------------------------
  * k-NN select sweep: the K smallest d(i,j) of every row, ascending by (distance, index).
@@ -215,11 +227,14 @@ int pcd_fps(const float *xyz, int64_t sb, int64_t sp, int64_t sc, int B, int N, 
             const int32_t *start, int32_t *out, void *stream);
 
 /* ------------------------------------------------------------------------------------
- * Measurement helper (bench.py): runs an FFMA-only micro-kernel and returns the achieved
- * fp32 FLOP/s in *flops_per_s (host pointer).  This is the measured roofline denominator for
- * the sweep kernels (the FP32 FMA peak is not in MEASURED_PEAKS.json).
+ * Measurement helper (bench.py): launches ONE FFMA-only probe kernel on `stream` (variant 0 =
+ * scalar FFMA, 1 = packed FFMA2) and stores the number of FLOPs that launch performs in
+ * *flop_count (HOST pointer).  The caller times it with its own CUDA events: achieved FLOP/s =
+ * *flop_count / elapsed.  This is the measured roofline denominator for the sweep kernels (the
+ * FP32 FMA peak is not in MEASURED_PEAKS.json).  scratch: >= 4 bytes of device memory (never
+ * written in practice).  Stream-ordered, allocation-free, no synchronisation.
  * ---------------------------------------------------------------------------------- */
-int pcd_measure_fp32_peak(int iters, double *flops_per_s, void *stream);
+int pcd_fp32_probe_launch(int variant, int iters, float *scratch, double *flop_count, void *stream);
 
 #ifdef __cplusplus
 }

@@ -204,9 +204,48 @@ def attack_loops():
     save("l4_attack_loops", **out)
 
 
+def feature_knn():
+    """a6 for the feature layers (C = 64, 64, 128): the UNMODIFIED reference DGCNN (model/dgcnn.py:270-311,
+    random init, eval mode) runs on two face clouds; every `knn(x, k)` call it makes (dgcnn.py:194-200 via
+    get_graph_feature :207) is recorded -- the feature tensor it was given and the index tensor it returned.
+    Fixture: N = 512 points, k = 20; the four calls have C = 3, 64, 64, 128 (dgcnn.py:299-311)."""
+    import argparse
+    from model import dgcnn
+    torch.manual_seed(20261020)
+    args = argparse.Namespace(k=20, emb_dims=1024, dropout=0.5)
+    net = dgcnn.DGCNN(args).eval()
+    x = np.stack([face_fixture(512, 3), face_fixture(512, 4)]).transpose(0, 2, 1)
+    calls = []
+    real_knn = dgcnn.knn
+
+    def recording_knn(x_, k):
+        idx = real_knn(x_, k)
+        calls.append((n(x_).copy(), n(idx).copy()))
+        return idx
+
+    saved = dgcnn.torch
+    dgcnn.torch = _TorchOnCPU()
+    dgcnn.knn = recording_knn
+    try:
+        with torch.no_grad():
+            net(t(np.ascontiguousarray(x)))
+    finally:
+        dgcnn.torch = saved
+        dgcnn.knn = real_knn
+    assert [c[0].shape[1] for c in calls] == [3, 64, 64, 128], [c[0].shape for c in calls]
+    out = {}
+    for li, (feat, idx) in enumerate(calls):
+        out[f"x{li}"] = feat.astype(np.float32)
+        out[f"idx{li}"] = idx.astype(np.int16)          # N = 512 fits; halves the fixture
+    save("a6_knn_graph_features", **out)
+
+
 def main():
     torch.set_num_threads(1)
     _prepare_reference()
+    if "--features" in sys.argv:       # a6 for C = 64 / 128 (added in round 2)
+        feature_knn()
+        return
     if "--loops" in sys.argv:
         attack_loops()
         return

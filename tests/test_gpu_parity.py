@@ -12,6 +12,7 @@ import pytest
 import torch
 
 from conftest import load_golden, rel_inf
+from knn_proof import assert_knn_near_tie_proof
 from oracle import pcd_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -109,13 +110,18 @@ def test_nn1_layouts(layout):
     assert np.array_equal(npy(r.row_min), o.row_min) and np.array_equal(npy(r.col_arg), o.col_arg)
 
 
-@pytest.mark.parametrize("env", [("2", "32"), ("4", "64"), ("8", "256"), ("8", "128")])
-def test_nn1_every_tiling(env, monkeypatch):
-    monkeypatch.setenv("PCD_SWEEP_R", env[0]); monkeypatch.setenv("PCD_SWEEP_MT", env[1])
-    g = load_golden("a2_distance_ragged")
-    check_nn1(g["gts"], g["preds"], "sum_first_fma")
-    rs = np.random.RandomState(1)
-    check_nn1(rs.randn(3, 1500, 3).astype(np.float32), rs.randn(3, 2100, 3).astype(np.float32), "row_col_mulsum")
+@pytest.mark.parametrize("tiling", [(2, 32), (4, 64), (8, 256), (8, 128), (16, 256), (16, 64)])
+def test_nn1_every_tiling(tiling):
+    F.force_tiling(*tiling)
+    try:
+        g = load_golden("a2_distance_ragged")
+        check_nn1(g["gts"], g["preds"], "sum_first_fma")
+        rs = np.random.RandomState(1)
+        # 1500 x 2100: dense, streamed raw; 1501 x 2102: not a multiple of 4 -> packed through the workspace
+        check_nn1(rs.randn(3, 1500, 3).astype(np.float32), rs.randn(3, 2100, 3).astype(np.float32), "row_col_mulsum")
+        check_nn1(rs.randn(2, 1501, 3).astype(np.float32), rs.randn(2, 2102, 3).astype(np.float32), "col_row_mulsum")
+    finally:
+        F.force_tiling(0, 0)
 
 
 def test_nn1_full_size_c2_against_oracle():
@@ -176,7 +182,7 @@ def test_fused_chamfer_hausdorff_shares_one_sweep():
     n0 = F.launches()
     c1, c2 = pcd.distance.chamfer(p, t)
     h1, h2 = pcd.distance.hausdorff(p, t)
-    assert F.launches() - n0 == 4          # second call is served by the one-entry cache
+    assert F.launches() - n0 == 3          # arm + sweep + fix-up; the second call is served by the one-entry cache
     (c1.sum() + c2.sum() + h1.sum() + h2.sum()).backward()
     with torch.no_grad():
         p.add_(0.001)                        # in-place update bumps the version -> no stale hit
@@ -397,13 +403,33 @@ def test_a6_knn_graph_vs_reference():
     assert np.array_equal(npy(pcd.curvenet_util.normal_knn(x3, 20)), i20)
     f64 = cu(g["f64"])
     assert np.array_equal(npy(pcd.dgcnn.knn(f64, 20)), O.dgcnn_knn(g["f64"], 20))
-    assert (npy(pcd.dgcnn.knn(f64, 20)) == g["dgcnn_f64_k20"]).mean() > 0.999
+    assert_knn_near_tie_proof(npy(pcd.dgcnn.knn(f64, 20)), g["dgcnn_f64_k20"], g["f64"], "gaussian C=64")
     # get_graph_feature: gather + concat, compared with a direct numpy restatement
     feat = npy(pcd.dgcnn.get_graph_feature(x3, k=20))
     xt = g["x3"].transpose(0, 2, 1)
     nb = xt[np.arange(2)[:, None, None], i20]
     ref = np.concatenate([nb - xt[:, :, None, :], np.broadcast_to(xt[:, :, None, :], nb.shape)], -1).transpose(0, 3, 1, 2)
     assert np.array_equal(feat, ref)
+
+
+def test_a6_knn_graph_feature_layers_vs_reference():
+    """The four knn() calls of the reference DGCNN forward (C = 3, 64, 64, 128): the kernel is bit-identical to the
+    oracle's sequential chain; against the reference's own indices (CPU BLAS order, committed golden) and against
+    the reference formulation run HERE on the GPU (cuBLAS order -- what a user of the reference actually gets)
+    every difference is a provable near tie (tests/knn_proof.py), no agreement fraction is assumed."""
+    g = load_golden("a6_knn_graph_features")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    for li, C in enumerate((3, 64, 64, 128)):
+        x = g[f"x{li}"]
+        ours = npy(pcd.dgcnn.knn(cu(x), 20))
+        assert np.array_equal(ours, O.dgcnn_knn(x, 20)), f"layer {li}"
+        st_cpu = assert_knn_near_tie_proof(ours, g[f"idx{li}"].astype(np.int64), x, f"layer {li} vs reference CPU")
+        xt = cu(x)                                            # model/dgcnn.py:194-200 verbatim arithmetic, on the GPU
+        inner = -2 * torch.matmul(xt.transpose(2, 1), xt)
+        xx = torch.sum(xt ** 2, dim=1, keepdim=True)
+        ref_gpu = npy((-xx - inner - xx.transpose(2, 1)).topk(k=20, dim=-1)[1])
+        st_gpu = assert_knn_near_tie_proof(ours, ref_gpu, x, f"layer {li} vs reference formulation on GPU")
+        print(f"a6 layer {li} C={C}: vs reference CPU {st_cpu}; vs reference-on-GPU {st_gpu}")
 
 
 def test_a7_pointnet2_utils_vs_reference():
@@ -420,6 +446,87 @@ def test_a7_pointnet2_utils_vs_reference():
     np.testing.assert_allclose(npy(P2.square_distance(new_xyz[:, :64], xyz[:, :96])), g["sqdist_block"], atol=1e-6)
 
 
+# ------------------------------------------------- robustness of the NN-1 chain
+@pytest.mark.parametrize("n", [1024, 1022])          # 1024: streamed raw, 1022: packed through the workspace
+def test_nn1_nan_and_inf_points_do_not_fault(n):
+    """A NaN / inf coordinate (a diverged adversarial cloud) must not fault: the untouched column key
+    used to decode to a negative row index (pcd_nn1.cu fix-up).  Finite points keep exact results."""
+    rs = np.random.RandomState(11)
+    rows = rs.randn(3, n, 3).astype(np.float32); cols = rs.randn(3, n, 3).astype(np.float32)
+    rows[0, 5] = np.nan; cols[0, 7, 1] = np.inf; cols[1, :, :] = np.nan; rows[2, :, 0] = np.inf
+    for form_key in FORMS:
+        form, norm, oform, onorm = FORMS[form_key]
+        r = F.nn1(cu(rows), cu(cols), form, norm, cache=False)
+        torch.cuda.synchronize()
+        ra, ca = npy(r.row_arg), npy(r.col_arg)
+        assert ra.min() >= 0 and ra.max() < n and ca.min() >= 0 and ca.max() < n
+        # sample 0: rows other than the NaN one against the finite columns are exact
+        ok_r = np.ones(n, bool); ok_r[5] = False
+        ok_c = np.ones(n, bool); ok_c[7] = False
+        o = oracle_nn1(rows[:1, ok_r], cols[:1, ok_c], oform, onorm)
+        assert np.array_equal(npy(r.row_min)[0, ok_r], o.row_min[0])
+        assert np.array_equal(npy(r.col_min)[0, ok_c], o.col_min[0])
+        # sample 1: every distance NaN -> no finite minimum anywhere: arg 0, value NaN or +inf
+        assert not np.isfinite(npy(r.row_min)[1]).any() and not np.isfinite(npy(r.col_min)[1]).any()
+        assert (ra[1] == 0).all() and (ca[1] == 0).all()
+
+
+def test_nn1_raw_and_packed_paths_agree():
+    """The same clouds through the dense (streamed) and the strided (packed) path: identical outputs and gradients."""
+    rs = np.random.RandomState(12)
+    rows = rs.randn(4, 1200, 3).astype(np.float32); cols = (rows[:, :1000] + 0.02 * rs.randn(4, 1000, 3)).astype(np.float32)
+    wide_r = torch.zeros(4, 1200, 5, device="cuda"); wide_r[:, :, 1:4] = cu(rows)
+    wide_c = torch.zeros(4, 1000, 4, device="cuda"); wide_c[:, :, :3] = cu(cols)
+    outs = []
+    for tr, tc in ((cu(rows), cu(cols)), (wide_r[:, :, 1:4], wide_c[:, :, :3]),
+                   (cu(rows.transpose(0, 2, 1)).transpose(1, 2), cu(cols.transpose(0, 2, 1)).transpose(1, 2))):
+        tr = tr.detach().requires_grad_(True); tc = tc.detach().requires_grad_(True)
+        r = F.nn1(tr, tc, F.FORM_ROW_COL, F.NORM_MULSUM, transform=F.VALUE_SQRT_CLAMP, cache=False)
+        (r.row_sum.sum() + 2 * r.col_max.sum() + (r.col_min * r.col_min).sum()).backward()
+        outs.append([npy(x) for x in (r.row_min, r.row_arg, r.col_min, r.col_arg, r.row_sum, r.col_max, r.col_argmax, tr.grad, tc.grad)])
+    for other in outs[1:]:
+        for a, b in zip(outs[0][:7], other[:7]):
+            assert np.array_equal(a, b)
+        for a, b in zip(outs[0][7:], other[7:]):
+            assert rel_inf(a, b) < 2e-6          # atomics: summation order only
+
+
+def test_nn1_prezeroed_backward_and_retain_graph():
+    """The forward clears the gradient buffers of the first backward; a second backward through a
+    retained graph must allocate afresh and give the same gradient (not an accumulated one)."""
+    g = load_golden("a2_distance_ragged")
+    a = cu(g["preds"], grad=True); o = cu(g["gts"])
+    c1, c2 = pcd.distance.chamfer(a, o)
+    loss = c1.sum() + c2.sum()
+    g1, = torch.autograd.grad(loss, a, retain_graph=True)
+    g1 = g1.clone()
+    g2, = torch.autograd.grad(loss, a)
+    assert rel_inf(npy(g2), npy(g1)) < 2e-6
+    w = np.ones(g["preds"].shape[0], np.float32)
+    ref, _ = O.chamfer_distance_grads(g["preds"], g["gts"], w, w)
+    assert rel_inf(npy(g1), ref) < RTOL
+
+
+def test_nn1_cache_is_not_served_under_no_grad_after_data_mutation():
+    """x.data.add_() does not bump x._version; a no_grad result must never come from the cache."""
+    g = load_golden("a2_distance_ragged")
+    a = cu(g["preds"], grad=True); o = cu(g["gts"])
+    with torch.no_grad():
+        c_before = npy(pcd.distance.chamfer(a, o)[0]).copy()
+        a.data.add_(0.05)
+        c_after = npy(pcd.distance.chamfer(a, o)[0])
+    assert not np.array_equal(c_before, c_after)
+    ref = O.chamfer_distance(g["preds"] + np.float32(0.05), g["gts"])[0]
+    np.testing.assert_allclose(c_after, ref, rtol=RTOL)
+    # with a graph being recorded the second call of the same forward IS served by the cache (one sweep) ...
+    n0 = F.launches()
+    pcd.distance.chamfer(a, o); pcd.distance.hausdorff(a, o)
+    assert F.launches() - n0 == 3
+    # ... and after an in-place clip the documented clear_cache() makes the next call recompute
+    a.data.sub_(0.05); F.clear_cache()
+    np.testing.assert_allclose(npy(pcd.distance.chamfer(a, o)[0]), O.chamfer_distance(npy(a), g["gts"])[0], rtol=RTOL)
+
+
 # ------------------------------------------------- error behaviour
 def test_errors_are_loud():
     with pytest.raises(RuntimeError):
@@ -432,7 +539,8 @@ def test_errors_are_loud():
         F.knn(torch.zeros(1, 4, 3, device="cuda"), torch.zeros(1, 4, 3, device="cuda"), 5)       # K > M
     lib = pcd._lib.load()
     assert lib.pcd_nn1_forward(None, 0, 0, 0, None, 0, 0, 0, 1, 1, 1, 0, 0, 0, 0, 1.0, 1.0,
-                               None, None, None, None, None, None, None, 0, None) == 1
+                               None, None, None, None, None, None, None, 0, None, 0, None, 0, 0, 0,
+                               None, None, None) == 1
     assert b"NULL" in lib.pcd_last_error()
 
 

@@ -31,11 +31,10 @@ def time_sweep(B, N, M, reps=10, form=F.FORM_SUM_FIRST, norm=F.NORM_FMA):
     for _ in range(3):
         F.nn1(ori, adv, form, norm, cache=False)
     for k in range(reps):
-        lib.pcd_nn1_set_sweep_events(e0[k].cuda_event, e1[k].cuda_event)
+        F.time_next_sweep(e0[k], e1[k])
         t0[k].record()
         F.nn1(ori, adv, form, norm, cache=False)
         t1[k].record()
-    lib.pcd_nn1_set_sweep_events(None, None)
     torch.cuda.synchronize()
     sw = sorted(a.elapsed_time(b) for a, b in zip(e0, e1))
     tot = sorted(a.elapsed_time(b) for a, b in zip(t0, t1))
@@ -65,7 +64,7 @@ def main():
         return
     if args.scaling:
         for R in (8, 16):
-            os.environ["PCD_SWEEP_R"] = str(R)
+            F.force_tiling(R, 0)
             for B in (8, 16, 32, 64, 128, 256):
                 sw, tot = time_sweep(B, 4096, 4096)
                 print(f"R={R} B={B:4d} N=M=4096: sweep {sw*1e3:8.1f} us   {B*4096*4096/sw/1e9:6.2f} Tpair/s")
@@ -74,7 +73,7 @@ def main():
         pairs = B * N * M
         for R in (2, 4, 8, 16):
             for MT in (128, 256):
-                os.environ["PCD_SWEEP_R"] = str(R); os.environ["PCD_SWEEP_MT"] = str(MT)
+                F.force_tiling(R, MT)
                 sw, tot = time_sweep(B, N, M)
                 print(f"B={B} N={N} M={M} R={R} MT={MT}: sweep {sw*1e3:8.1f} us  fwd total {tot*1e3:8.1f} us  "
                       f"{pairs/sw/1e9:8.2f} Tpair/s  {8*pairs/sw/1e9:6.1f} TFLOP/s")
