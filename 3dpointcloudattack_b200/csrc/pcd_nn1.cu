@@ -54,12 +54,14 @@ constexpr int kColChunk = 32;     // columns per row-direction tag
 constexpr int kMaxColTile = 256;  // columns per TMA stage
 constexpr int kRowPadUnit = 2048; // rows are padded to a multiple of 128*R, R <= 16
 constexpr int kFixupThreads = 256;
-constexpr int kFixupPoints = kFixupThreads / 4;   // four lanes per point
+constexpr int kFixupCtasPerSm = 2;                // 128 registers per thread: twelve 16-byte loads in flight per lane
+constexpr int kFixupMaxWarps = 16384;             // upper bound of the persistent fix-up grid (any device)
 
 struct Nn1Layout {
     int Npad, Mpad;
-    size_t rowkey, colkey, counters, rowpk, rowpp, colpk, total;
+    size_t rowkey, colkey, counters, partials, rowpk, rowpp, colpk, total;
     size_t nkeys;
+    int partial_slots;     // fix-up partial slots per sample and side
 };
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // keys + counters first (all the dense-input path touches), the packed records of the strided
@@ -73,6 +75,8 @@ static Nn1Layout nn1_layout(int B, int N, int M) {
     L.colkey = off; off += (size_t)B * L.Mpad * 8;
     L.nkeys = (size_t)B * L.Npad + (size_t)B * L.Mpad;
     L.counters = off; off = align_up(off + (size_t)B * 4, 256);
+    L.partial_slots = kFixupMaxWarps / B + 2;                  // warps that can touch one sample (see nn1_fixup_kernel)
+    L.partials = off; off = align_up(off + (size_t)B * 2 * L.partial_slots * 16, 256);   // per sample, side and warp: (sum, max, argmax, -)
     L.rowpk = off; off = align_up(off + (size_t)B * L.Npad * 16, 256);
     L.rowpp = off; off = align_up(off + (size_t)B * L.Npad * 16, 256);   // the same records in sweep (slot) order
     L.colpk = off; off = align_up(off + (size_t)B * L.Mpad * 16 + 64, 256);   // +64: the sweep prefetches one record past a tile
@@ -515,7 +519,13 @@ struct FixupArgs {
     int col_vec;                  // RAW: 1 = point-major dense columns, 2 = channel-major dense columns (16-byte loads)
     int norm_kind;
     const unsigned long long *rowkey, *colkey;
-    int *counters;
+    int *counters;                // [B] octets finished per sample (armed to 0)
+    float4 *partials;             // [B][2][slots]: per warp and side (sum, max, bits of argmax) of the minima it handled
+    int slots;                    // partial slots per sample and side
+    int nwarps;                   // participating warps W (<= number of octets U)
+    int upw, urem;                // U / W, U % W: warp w owns upw (+1 if w < urem) consecutive octets
+    int nrowgroups;               // ceil(N / 32R): valid range of the lane-group part of a column tag
+    int nchunks;                  // ceil(M / 32): valid range of a row tag
     int N, M, Npad, Mpad, R, transform, B;
     float *row_min; int32_t *row_arg; float *col_min; int32_t *col_arg;
     float row_scale, col_scale;
@@ -523,177 +533,471 @@ struct FixupArgs {
     float4 *zero0; size_t nzero0; float4 *zero1; size_t nzero1;     // optional buffers to clear (float4 counts)
 };
 
-// Four lanes per point.  A row point re-evaluates the 32 columns of its winning chunk, a column
-// point the R rows of its winning lane -- with the sweep's exact arithmetic -- and takes the
-// lowest index whose distance equals the minimum.  A key that was never lowered (every distance
-// through the point NaN or +inf) decodes to (NaN, tag 0xffffffff): nothing is dereferenced
-// through such a tag, the point gets arg 0.  The last block of a sample to finish (completion
-// counter) reduces the sample's minima to the per-sample statistics in a fixed order, so the
+// Persistent, barrier-free fix-up, ONE LANE PER POINT.  A row point re-evaluates the 32 columns of its
+// winning chunk, a column point the R rows of its winning lane -- with the sweep's exact arithmetic --
+// and takes the lowest index whose distance equals the minimum.  The scan of a point is a straight
+// stream of 16-byte loads and scalar math in its own lane (groups of four candidates, highest first so
+// that the lowest match is the one that sticks): no cross-lane traffic, every lane busy -- the earlier
+// four-lanes-per-point kernels spent five of six instructions on addressing and shuffles.
+// Work unit = 32 consecutive points of one side of one sample; every warp owns a contiguous range of
+// units (sample-major, rows then columns) and requests the key and the own coordinates of unit u+1
+// before it evaluates unit u, so the key -> chunk round trips of consecutive units overlap.
+// A key that was never lowered (every distance through the point NaN or +inf) decodes to
+// (NaN, tag 0xffffffff): nothing is dereferenced through such a tag, the point gets arg 0.
+// Per-sample statistics: lane-local running (sum, max, first argmax) over the warp's units of one
+// sample and side, one xor-tree per segment, one partial per (sample, side, warp); the warp whose
+// completion count closes a sample folds that sample's partials -- all in a fixed order, so the
 // sums are run-to-run deterministic.
-template <int FORM, bool RAW>
-__global__ void __launch_bounds__(kFixupThreads, RAW ? 6 : 8)   // 48-64 warps per SM: the key -> chunk load round trips are the bound
-nn1_fixup_kernel(FixupArgs a) {
-    const int b = blockIdx.y;
-    const int tid = threadIdx.x;
-    const int l4 = tid & 3;
-    int p = blockIdx.x * kFixupPoints + (tid >> 2);           // 64 points per block, rows first then columns
-    const int N = a.N, M = a.M, R = a.R;
-    const bool is_col = p >= N;
-    if (is_col) p -= N;
-    const bool live = p < (is_col ? M : N);
+struct FixPt {
+    int b, p;
+    bool live, is_col;
+    unsigned long long key;
+    float ox, oy, oz, on;
+};
 
-    if (!RAW) pdl_wait();     // PACKED: the records come from nn1_prep (complete once the sweep has started its math)
-    // own point (RAW: independent of the kernels in front of us, loaded before the dependency wait)
-    float ox = 0.f, oy = 0.f, oz = 0.f, on = 0.f;
-    if (live) {
-        if (RAW) {
-            const float *s = is_col ? a.cols + (size_t)b * a.c_sb + (size_t)p * a.c_sp : a.rows + (size_t)b * a.r_sb + (size_t)p * a.r_sp;
-            const long long sc = is_col ? a.c_sc : a.r_sc;
-            ox = __ldg(s); oy = __ldg(s + sc); oz = __ldg(s + 2 * sc);
-            on = sq_norm3(a.norm_kind, ox, oy, oz);
-            if (!is_col) { ox *= -2.f; oy *= -2.f; oz *= -2.f; }
-        } else if (is_col) {
-            const float *rec = reinterpret_cast<const float *>(a.colpk) + ((size_t)b * a.Mpad + (p & ~1)) * 4 + (p & 1);
-            ox = rec[0]; oy = rec[2]; oz = rec[4]; on = rec[6];
+// lowest column j in [j0, j0+32) with d(row record, column j) == v   (0x7fffffff: none)
+template <int FORM, bool RAW, int NORM>
+__device__ __forceinline__ int fixup_scan_cols(const FixupArgs &a, int b, int j0, float qx, float qy, float qz, float qn, float v) {
+    int arg = 0x7fffffff;
+    if (RAW) {
+        int ng = (a.M - j0 + 3) >> 2;                 // valid groups of 4 columns (M % 4 == 0)
+        if (ng > 8) ng = 8;
+        if (a.col_vec == 1) {                         // point-major: 4 columns = 12 consecutive floats
+            const float4 *g = reinterpret_cast<const float4 *>(a.cols + (size_t)b * a.c_sb + (size_t)j0 * 3);
+#pragma unroll 4
+            for (int k = ng - 1; k >= 0; --k) {
+                const float4 f0 = __ldg(g + 3 * k), f1 = __ldg(g + 3 * k + 1), f2 = __ldg(g + 3 * k + 2);
+                const float cx[4] = {f0.x, f0.w, f1.z, f2.y}, cy[4] = {f0.y, f1.x, f1.w, f2.z}, cz[4] = {f0.z, f1.y, f2.x, f2.w};
+#pragma unroll
+                for (int t = 3; t >= 0; --t)
+                    if (pair_dist_scalar<FORM>(qx, qy, qz, qn, cx[t], cy[t], cz[t], sq_norm3(NORM, cx[t], cy[t], cz[t])) == v) arg = j0 + 4 * k + t;
+            }
+        } else {                                      // channel-major: 4 columns = one float4 per channel
+            const float *g = a.cols + (size_t)b * a.c_sb + j0;
+#pragma unroll 4
+            for (int k = ng - 1; k >= 0; --k) {
+                const float4 fx = __ldg(reinterpret_cast<const float4 *>(g) + k);
+                const float4 fy = __ldg(reinterpret_cast<const float4 *>(g + a.c_sc) + k);
+                const float4 fz = __ldg(reinterpret_cast<const float4 *>(g + 2 * a.c_sc) + k);
+                const float cx[4] = {fx.x, fx.y, fx.z, fx.w}, cy[4] = {fy.x, fy.y, fy.z, fy.w}, cz[4] = {fz.x, fz.y, fz.z, fz.w};
+#pragma unroll
+                for (int t = 3; t >= 0; --t)
+                    if (pair_dist_scalar<FORM>(qx, qy, qz, qn, cx[t], cy[t], cz[t], sq_norm3(NORM, cx[t], cy[t], cz[t])) == v) arg = j0 + 4 * k + t;
+            }
+        }
+    } else {                                          // packed pair records {x0,x1,y0,y1},{z0,z1,n0,n1}; padded, inert beyond M
+        const float4 *rec = a.colpk + (size_t)b * a.Mpad + j0;
+#pragma unroll 4
+        for (int k = 7; k >= 0; --k) {
+            const float4 a0 = __ldg(rec + 4 * k), c0 = __ldg(rec + 4 * k + 1), a1 = __ldg(rec + 4 * k + 2), c1 = __ldg(rec + 4 * k + 3);
+            const int j = j0 + 4 * k;
+            if (pair_dist_scalar<FORM>(qx, qy, qz, qn, a1.y, a1.w, c1.y, c1.w) == v) arg = j + 3;
+            if (pair_dist_scalar<FORM>(qx, qy, qz, qn, a1.x, a1.z, c1.x, c1.z) == v) arg = j + 2;
+            if (pair_dist_scalar<FORM>(qx, qy, qz, qn, a0.y, a0.w, c0.y, c0.w) == v) arg = j + 1;
+            if (pair_dist_scalar<FORM>(qx, qy, qz, qn, a0.x, a0.z, c0.x, c0.z) == v) arg = j;
         }
     }
-    // optional zero fill (gradient buffers of the coming backward); independent of the sweep as well
+    return arg;
+}
+
+// lowest row i in [i0, i0+R) with d(row i, column record) == v
+template <int FORM, bool RAW, int NORM>
+__device__ __forceinline__ int fixup_scan_rows(const FixupArgs &a, int b, int i0, float cx, float cy, float cz, float cn, float v) {
+    int arg = 0x7fffffff;
+    const int R = a.R, N = a.N;
+    if (RAW) {
+        if (R >= 4) {                                 // groups of 4 rows: three 16-byte loads in either dense layout (N % 4 == 0)
+            int ng = (N - i0 + 3) >> 2;
+            if (ng > (R >> 2)) ng = R >> 2;
+            if (a.r_sp == 3) {
+                const float4 *g = reinterpret_cast<const float4 *>(a.rows + (size_t)b * a.r_sb + (size_t)i0 * 3);
+#pragma unroll 4
+                for (int k = ng - 1; k >= 0; --k) {
+                    const float4 f0 = __ldg(g + 3 * k), f1 = __ldg(g + 3 * k + 1), f2 = __ldg(g + 3 * k + 2);
+                    const float x[4] = {f0.x, f0.w, f1.z, f2.y}, y[4] = {f0.y, f1.x, f1.w, f2.z}, z[4] = {f0.z, f1.y, f2.x, f2.w};
+#pragma unroll
+                    for (int t = 3; t >= 0; --t)
+                        if (pair_dist_scalar<FORM>(-2.f * x[t], -2.f * y[t], -2.f * z[t], sq_norm3(NORM, x[t], y[t], z[t]), cx, cy, cz, cn) == v) arg = i0 + 4 * k + t;
+                }
+            } else {
+                const float *g = a.rows + (size_t)b * a.r_sb + i0;
+#pragma unroll 4
+                for (int k = ng - 1; k >= 0; --k) {
+                    const float4 fx = __ldg(reinterpret_cast<const float4 *>(g) + k);
+                    const float4 fy = __ldg(reinterpret_cast<const float4 *>(g + a.r_sc) + k);
+                    const float4 fz = __ldg(reinterpret_cast<const float4 *>(g + 2 * a.r_sc) + k);
+                    const float x[4] = {fx.x, fx.y, fx.z, fx.w}, y[4] = {fy.x, fy.y, fy.z, fy.w}, z[4] = {fz.x, fz.y, fz.z, fz.w};
+#pragma unroll
+                    for (int t = 3; t >= 0; --t)
+                        if (pair_dist_scalar<FORM>(-2.f * x[t], -2.f * y[t], -2.f * z[t], sq_norm3(NORM, x[t], y[t], z[t]), cx, cy, cz, cn) == v) arg = i0 + 4 * k + t;
+                }
+            }
+        } else {                                      // R = 2
+            for (int t = R - 1; t >= 0; --t) {
+                const int i = i0 + t;
+                if (i < N) {
+                    const float *s = a.rows + (size_t)b * a.r_sb + (size_t)i * a.r_sp;
+                    const float x = __ldg(s), y = __ldg(s + a.r_sc), z = __ldg(s + 2 * a.r_sc);
+                    if (pair_dist_scalar<FORM>(-2.f * x, -2.f * y, -2.f * z, sq_norm3(NORM, x, y, z), cx, cy, cz, cn) == v) arg = i;
+                }
+            }
+        }
+    } else {
+        const float4 *rq = a.rowpk + (size_t)b * a.Npad + i0;
+#pragma unroll 4
+        for (int t = R - 1; t >= 0; --t) {
+            const float4 q = __ldg(rq + t);
+            if (i0 + t < N && pair_dist_scalar<FORM>(q.x, q.y, q.z, q.w, cx, cy, cz, cn) == v) arg = i0 + t;
+        }
+    }
+    return arg;
+}
+
+template <int FORM, bool RAW, int NORM>
+__global__ void __launch_bounds__(kFixupThreads, kFixupCtasPerSm)
+nn1_fixup_kernel(FixupArgs a) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int N = a.N, M = a.M, R = a.R;
+    const float ninf = -__int_as_float(0x7f800000);
+
+    if (!RAW) pdl_wait();     // PACKED: the records come from nn1_prep (complete once the sweep has started its math)
+    // optional zero fill (gradient buffers of the coming backward); independent of the kernels in front of us
     {
-        const size_t nthreads = (size_t)gridDim.x * gridDim.y * kFixupThreads;
-        const size_t t0 = ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * kFixupThreads + tid;
+        const size_t nthreads = (size_t)gridDim.x * kFixupThreads;
+        const size_t t0 = (size_t)blockIdx.x * kFixupThreads + tid;
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
         for (size_t t = t0; t < a.nzero0; t += nthreads) a.zero0[t] = z;
         for (size_t t = t0; t < a.nzero1; t += nthreads) a.zero1[t] = z;
     }
+    const int w = blockIdx.x * (kFixupThreads / 32) + (tid >> 5);
+    if (w >= a.nwarps) return;
+    const int urow = (N + 31) >> 5, ucol = (M + 31) >> 5, Us = urow + ucol;    // units per sample
+    // warp w owns the units [w*upw + min(w, urem), ... + upw (+1 if w < urem)): no division in the hot path
+    const int u_begin = w * a.upw + min(w, a.urem), u_end = u_begin + a.upw + (w < a.urem ? 1 : 0);
+    // inverse map: the warp that owns unit x
+    auto warp_of = [&](int x) -> int {
+        const int split = a.urem * (a.upw + 1);
+        return x < split ? x / (a.upw + 1) : a.urem + (x - split) / a.upw;
+    };
+
+    // request everything of unit (b, o) that does not depend on another load: key and own coordinates of this lane's point
+    auto fetch = [&](int b_, int o) -> FixPt {
+        FixPt f;
+        f.b = b_;
+        f.is_col = o >= urow;
+        f.p = (f.is_col ? o - urow : o) * 32 + lane;
+        f.live = f.p < (f.is_col ? M : N);
+        f.key = 0ull; f.ox = f.oy = f.oz = f.on = 0.f;
+        if (f.live) {
+            f.key = f.is_col ? a.colkey[(size_t)f.b * a.Mpad + f.p] : a.rowkey[(size_t)f.b * a.Npad + row_slot(f.p, R)];
+            if (RAW) {
+                const float *s = f.is_col ? a.cols + (size_t)f.b * a.c_sb + (size_t)f.p * a.c_sp
+                                          : a.rows + (size_t)f.b * a.r_sb + (size_t)f.p * a.r_sp;
+                const long long sc = f.is_col ? a.c_sc : a.r_sc;
+                f.ox = __ldg(s); f.oy = __ldg(s + sc); f.oz = __ldg(s + 2 * sc);
+            } else if (f.is_col) {
+                const float *rec = reinterpret_cast<const float *>(a.colpk) + ((size_t)f.b * a.Mpad + (f.p & ~1)) * 4 + (f.p & 1);
+                f.ox = rec[0]; f.oy = rec[2]; f.oz = rec[4]; f.on = rec[6];
+            } else {
+                const float4 q = __ldg(&a.rowpk[(size_t)f.b * a.Npad + f.p]);
+                f.ox = q.x; f.oy = q.y; f.oz = q.z; f.on = q.w;
+            }
+        }
+        return f;
+    };
+
     if (RAW) pdl_wait();      // the keys: the sweep has completed and flushed
 
-    int arg = 0x7fffffff;
-    float v = 0.f;
-    if (live) {
-        if (!is_col) {
-            const unsigned long long key = a.rowkey[(size_t)b * a.Npad + row_slot(p, R)];
-            v = ordered_to_f32((uint32_t)(key >> 32));
-            const uint32_t tag = (uint32_t)key;
-            const int j0 = (int)tag * kColChunk;
-            if (tag < (uint32_t)((M + kColChunk - 1) / kColChunk)) {
-                if (RAW) {
-                    // lane l4 takes the 8 consecutive columns j0 + 8*l4 ..: six 16-byte loads (M % 4 == 0: validity per 4 columns)
-                    const int j = j0 + 8 * l4;
-                    float f[24];
-                    float4 *f4 = reinterpret_cast<float4 *>(f);
-                    const bool v0 = j < M, v1 = j + 4 < M;
-                    if (a.col_vec == 1) {
-                        const float4 *g = reinterpret_cast<const float4 *>(a.cols + (size_t)b * a.c_sb + (size_t)j * 3);
+    // lane-local running statistics of the current sample, per side
+    float acc_s[2] = {0.f, 0.f}, acc_mx[2] = {ninf, ninf};
+    int acc_am[2] = {0x7fffffff, 0x7fffffff};
+    // close the warp's segment of sample b: partials, completion count, and -- if we are last -- the sample's statistics
+    auto finish_sample = [&](int b) {
+        const int s0 = b * Us, s1 = s0 + Us;                                     // the sample's unit range
+        const int w0 = warp_of(s0), w1 = warp_of(s1 - 1);                         // warps holding its first / last unit
 #pragma unroll
-                        for (int t = 0; t < 6; ++t) f4[t] = (t < 3 ? v0 : v1) ? __ldg(g + t) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    } else {
-                        const float *g = a.cols + (size_t)b * a.c_sb + j;
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            const float4 *gc = reinterpret_cast<const float4 *>(g + (size_t)c * a.c_sc);
-                            f4[2 * c] = v0 ? __ldg(gc) : make_float4(0.f, 0.f, 0.f, 0.f);
-                            f4[2 * c + 1] = v1 ? __ldg(gc + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        }
-                    }
-#pragma unroll
-                    for (int t = 7; t >= 0; --t) {
-                        float cx, cy, cz;
-                        if (a.col_vec == 1) { cx = f[3 * t]; cy = f[3 * t + 1]; cz = f[3 * t + 2]; }
-                        else { cx = f[t]; cy = f[8 + t]; cz = f[16 + t]; }
-                        const float cn = sq_norm3(a.norm_kind, cx, cy, cz);
-                        if ((t < 4 ? v0 : v1) && pair_dist_scalar<FORM>(ox, oy, oz, on, cx, cy, cz, cn) == v) arg = j + t;
-                    }
-                } else {
-                    const float4 q = __ldg(&a.rowpk[(size_t)b * a.Npad + p]);
-                    const float4 *rec = a.colpk + (size_t)b * a.Mpad + j0;
-                    // lane l4 takes the pair records l4, l4+4, l4+8, l4+12 (columns 2 rec, 2 rec + 1): eight
-                    // independent 16-byte loads in flight per lane, highest column first so the lowest match wins
-                    float4 x[4], c[4];
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) { x[t] = __ldg(&rec[2 * (l4 + 4 * t)]); c[t] = __ldg(&rec[2 * (l4 + 4 * t) + 1]); }
-#pragma unroll
-                    for (int t = 3; t >= 0; --t) {
-                        const int j = j0 + 2 * (l4 + 4 * t);
-                        if (pair_dist_scalar<FORM>(q.x, q.y, q.z, q.w, x[t].y, x[t].w, c[t].y, c[t].w) == v) arg = j + 1;
-                        if (pair_dist_scalar<FORM>(q.x, q.y, q.z, q.w, x[t].x, x[t].z, c[t].x, c[t].z) == v) arg = j;
-                    }
-                }
-            }
-        } else {
-            const unsigned long long key = a.colkey[(size_t)b * a.Mpad + p];
-            v = ordered_to_f32((uint32_t)(key >> 32));
-            const uint32_t tag = (uint32_t)key;
-            if ((tag >> 5) < (uint32_t)((N + 32 * R - 1) / (32 * R))) {
-                const int i0 = (int)(tag >> 5) * (32 * R) + (int)(tag & 31u) * R;
-                // lane l4 takes rows l4, l4+4, l4+8, l4+12 of the winning lane's R rows (R = 2, 4, 8 or 16)
-                float4 q[4];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const int i = i0 + l4 + 4 * t;
-                    q[t] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7fc00000));
-                    if (l4 + 4 * t < R && i < N) {
-                        if (RAW) {
-                            const float *s = a.rows + (size_t)b * a.r_sb + (size_t)i * a.r_sp;
-                            const float x = __ldg(s), y = __ldg(s + a.r_sc), z = __ldg(s + 2 * a.r_sc);
-                            q[t] = make_float4(-2.f * x, -2.f * y, -2.f * z, sq_norm3(a.norm_kind, x, y, z));
-                        } else {
-                            q[t] = __ldg(&a.rowpk[(size_t)b * a.Npad + i]);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int t = 3; t >= 0; --t)
-                    if (l4 + 4 * t < R && i0 + l4 + 4 * t < N &&
-                        pair_dist_scalar<FORM>(q[t].x, q[t].y, q[t].z, q[t].w, ox, oy, oz, on) == v) arg = i0 + l4 + 4 * t;
-            }
+        for (int side = 0; side < 2; ++side) {
+            float sv = acc_s[side], mx = acc_mx[side];
+            int am = acc_am[side];
+            reduce_smf(sv, mx, am);
+            if (lane == 0) a.partials[((size_t)b * 2 + side) * a.slots + (size_t)(w - w0)] = make_float4(sv, mx, __int_as_float(am), 0.f);
+            acc_s[side] = 0.f; acc_mx[side] = ninf; acc_am[side] = 0x7fffffff;
         }
-    }
-#pragma unroll
-    for (int o = 2; o > 0; o >>= 1) arg = min(arg, __shfl_xor_sync(0xffffffffu, arg, o, 4));   // all lanes take part
-    if (live && l4 == 0) {
-        if (arg == 0x7fffffff) arg = 0;        // no finite minimum (NaN / inf inputs)
-        const float val = apply_transform(a.transform, v);
-        if (!is_col) { a.row_min[(size_t)b * N + p] = val; a.row_arg[(size_t)b * N + p] = arg; }
-        else { a.col_min[(size_t)b * M + p] = val; a.col_arg[(size_t)b * M + p] = arg; }
-    }
-
-    // ---- per-sample statistics by the last block of the sample ----
-    __shared__ int s_last;
-    __shared__ float ws[kFixupThreads / 32], wmx[kFixupThreads / 32];
-    __shared__ int wam[kFixupThreads / 32];
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(&a.counters[b], 1) == (int)gridDim.x - 1);
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    const int lane = tid & 31, warp = tid >> 5;
-    for (int side = 0; side < 2; ++side) {
-        const int n = side ? M : N;
-        const float *vals = (side ? a.col_min : a.row_min) + (size_t)b * n;
-        float s = 0.f, mx = -__int_as_float(0x7f800000);
-        int am = 0x7fffffff;
-        for (int i = tid; i < n; i += kFixupThreads) {
-            const float x = __ldcg(vals + i);
-            s += x;
-            if (x > mx) { mx = x; am = i; }
+        int last = 0;
+        if (lane == 0) {
+            const int done = min(u_end, s1) - max(u_begin, s0);
+            __threadfence();
+            last = atomicAdd(&a.counters[b], done) + done == Us;
         }
-        reduce_smf(s, mx, am);
-        if (lane == 0) { ws[warp] = s; wmx[warp] = mx; wam[warp] = am; }
-        __syncthreads();
-        if (warp == 0) {
-            const bool has = lane < kFixupThreads / 32;
-            s = has ? ws[lane] : 0.f;
-            mx = has ? wmx[lane] : -__int_as_float(0x7f800000);
-            am = has ? wam[lane] : 0x7fffffff;
-            reduce_smf(s, mx, am);
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (!last) return;
+        __threadfence();
+        const int nslots = w1 - w0 + 1;
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            float sv = 0.f, mx = ninf;
+            int am = 0x7fffffff;
+            for (int k = lane; k < nslots; k += 32) {
+                const float4 t = __ldcg(&a.partials[((size_t)b * 2 + side) * a.slots + k]);
+                sv += t.x;
+                const int ta = __float_as_int(t.z);
+                if (t.y > mx || (t.y == mx && ta < am)) { mx = t.y; am = ta; }
+            }
+            reduce_smf(sv, mx, am);
             if (lane == 0) {
-                a.stats_f[(side * 2 + 0) * a.B + b] = s * (side ? a.col_scale : a.row_scale);
+                a.stats_f[(side * 2 + 0) * a.B + b] = sv * (side ? a.col_scale : a.row_scale);
                 a.stats_f[(side * 2 + 1) * a.B + b] = mx;
                 a.stats_i[side * a.B + b] = am == 0x7fffffff ? 0 : am;
             }
         }
-        __syncthreads();
+    };
+
+    int nb = u_begin / Us, no = u_begin - nb * Us;        // (sample, unit in sample) of the NEXT unit to fetch
+    FixPt cur = fetch(nb, no);
+    for (int u = u_begin; u < u_end; ++u) {
+        FixPt nxt = cur;
+        if (++no == Us) { no = 0; ++nb; }
+        if (u + 1 < u_end) nxt = fetch(nb, no);
+        const int b = cur.b, p = cur.p;
+        if (cur.live) {
+            const float v = ordered_to_f32((uint32_t)(cur.key >> 32));
+            const uint32_t tag = (uint32_t)cur.key;
+            float ox = cur.ox, oy = cur.oy, oz = cur.oz, on = cur.on;
+            if (RAW) on = sq_norm3(NORM, ox, oy, oz);
+            int arg = 0x7fffffff;
+            if (!cur.is_col) {
+                if (RAW) { ox *= -2.f; oy *= -2.f; oz *= -2.f; }
+                if (tag < (uint32_t)a.nchunks) arg = fixup_scan_cols<FORM, RAW, NORM>(a, b, (int)tag * kColChunk, ox, oy, oz, on, v);
+            } else if ((tag >> 5) < (uint32_t)a.nrowgroups) {
+                arg = fixup_scan_rows<FORM, RAW, NORM>(a, b, (int)(tag >> 5) * (32 * R) + (int)(tag & 31u) * R, ox, oy, oz, on, v);
+            }
+            if (arg == 0x7fffffff) arg = 0;        // no finite minimum (NaN / inf inputs)
+            const float val = apply_transform(a.transform, v);
+            // constant indices only: a run-time side index would push the accumulators into local memory
+            if (!cur.is_col) {
+                a.row_min[(size_t)b * N + p] = val; a.row_arg[(size_t)b * N + p] = arg;
+                acc_s[0] += val;
+                if (val > acc_mx[0]) { acc_mx[0] = val; acc_am[0] = p; }
+            } else {
+                a.col_min[(size_t)b * M + p] = val; a.col_arg[(size_t)b * M + p] = arg;
+                acc_s[1] += val;
+                if (val > acc_mx[1]) { acc_mx[1] = val; acc_am[1] = p; }
+            }
+        }
+        if (u + 1 == u_end || nxt.b != b) finish_sample(b);       // warp-uniform: every lane of a unit is in the same sample
+        cur = nxt;
+    }
+}
+
+// ---------------------------------------------------------------- fix-up, shared-memory staged
+// The lane-per-point fix-up above is bound by L1 tag look-ups: every lane of a 16-byte load touches its
+// own cache line (winning chunks of neighbouring points are unrelated), 4.7 M tag cycles at BASELINE
+// config 2 = 16 us.  When the cloud that is being re-scanned fits into shared memory (N, M <= 16 K
+// points) it is staged there once per CTA by bulk copies -- issued BEFORE the dependency wait, so
+// they overlap the tail of the sweep -- and the scans become bank-conflict-free LDS.128 streams:
+//   job    = (sample b, side): side 0 = the rows re-scan columns (stage the column cloud),
+//                              side 1 = the columns re-scan rows (stage the row cloud)
+//   slice  = `parts` equal unit ranges per job (unit = 32 points, one per lane); one CTA per slice
+//   order  = lane l visits its point's candidate groups rotated by l (group (l + i) mod G): the lanes of a
+//            quarter warp then sit in different banks; the lowest matching index is kept with min().
+// Statistics: lane-local -> warp xor-tree -> CTA (fixed warp order) -> one partial per slice; the CTA
+// whose completion count closes a sample folds the 2 x parts partials in a fixed order.
+struct StagedArgs {
+    FixupArgs f;
+    int parts;             // slices per job
+    int stage_stride;      // channel-major staging: floats between the channel rows (multiple of 32)
+};
+
+template <int FORM, int NORM>
+__global__ void __launch_bounds__(kFixupThreads, 3)
+nn1_fixup_staged_kernel(StagedArgs sa) {
+    const FixupArgs &a = sa.f;
+    extern __shared__ __align__(128) float stage[];
+    __shared__ uint64_t bar;
+    __shared__ float red_s[kFixupThreads / 32], red_mx[kFixupThreads / 32];
+    __shared__ int red_am[kFixupThreads / 32];
+    __shared__ int s_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int N = a.N, M = a.M, R = a.R;
+    const float ninf = -__int_as_float(0x7f800000);
+    const int job = blockIdx.x / sa.parts, q = blockIdx.x - job * sa.parts;
+    const int b = job >> 1, side = job & 1;
+    const int n_own = side ? M : N, n_opp = side ? N : M;            // points of this side / candidates
+    const float *own = side ? a.cols + (size_t)b * a.c_sb : a.rows + (size_t)b * a.r_sb;
+    const long long own_sp = side ? a.c_sp : a.r_sp, own_sc = side ? a.c_sc : a.r_sc;
+    const float *opp = side ? a.rows + (size_t)b * a.r_sb : a.cols + (size_t)b * a.c_sb;
+    const bool opp_cm = (side ? a.r_sp : a.c_sp) == 1;
+    const long long opp_sc = side ? a.r_sc : a.c_sc;
+
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+        fence_proxy_async();
+        mbar_expect_tx(&bar, (uint32_t)n_opp * 12u);
+        if (opp_cm) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) tma_load_1d(stage + (size_t)c * sa.stage_stride, opp + (size_t)c * opp_sc, (uint32_t)n_opp * 4u, &bar);
+        } else {
+            tma_load_1d(stage, opp, (uint32_t)n_opp * 12u, &bar);
+        }
+    }
+    {   // optional zero fill (gradient buffers of the coming backward)
+        const size_t nthreads = (size_t)gridDim.x * kFixupThreads;
+        const size_t t0 = (size_t)blockIdx.x * kFixupThreads + tid;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (size_t t = t0; t < a.nzero0; t += nthreads) a.zero0[t] = z;
+        for (size_t t = t0; t < a.nzero1; t += nthreads) a.zero1[t] = z;
+    }
+    __syncthreads();          // the barrier is initialised
+    pdl_wait();               // the keys: the sweep has completed and flushed
+    mbar_wait(&bar, 0);       // the candidate cloud is in shared memory
+
+    const int units = (n_own + 31) >> 5;
+    const int u0 = (int)((long long)units * q / sa.parts), u1 = (int)((long long)units * (q + 1) / sa.parts);
+    const unsigned long long *keys = side ? a.colkey + (size_t)b * a.Mpad : a.rowkey + (size_t)b * a.Npad;
+    float *out_min = side ? a.col_min + (size_t)b * M : a.row_min + (size_t)b * N;
+    int32_t *out_arg = side ? a.col_arg + (size_t)b * M : a.row_arg + (size_t)b * N;
+
+    float acc_s = 0.f, acc_mx = ninf;
+    int acc_am = 0x7fffffff;
+    // software pipeline over this warp's units: key and own coordinates of the next unit are requested first
+    unsigned long long key = 0ull;
+    float px = 0.f, py = 0.f, pz = 0.f;
+    auto fetch = [&](int u, unsigned long long &k, float &x, float &y, float &z) {
+        const int p = u * 32 + lane;
+        k = 0ull; x = y = z = 0.f;
+        if (u < u1 && p < n_own) {
+            k = keys[side ? p : row_slot(p, R)];
+            const float *s = own + (size_t)p * own_sp;
+            x = __ldg(s); y = __ldg(s + own_sc); z = __ldg(s + 2 * own_sc);
+        }
+    };
+    fetch(u0 + warp, key, px, py, pz);
+    for (int u = u0 + warp; u < u1; u += kFixupThreads / 32) {
+        unsigned long long nkey; float nx, ny, nz;
+        fetch(u + kFixupThreads / 32, nkey, nx, ny, nz);
+        const int p = u * 32 + lane;
+        if (p < n_own) {
+            const float v = ordered_to_f32((uint32_t)(key >> 32));
+            const uint32_t tag = (uint32_t)key;
+            const float pn = sq_norm3(NORM, px, py, pz);
+            int arg = 0x7fffffff;
+            if (side == 0) {
+                // row point (-2x, -2y, -2z, n) against the 32 columns of chunk `tag`: 8 groups of 4 columns
+                if (tag < (uint32_t)a.nchunks) {
+                    const float qx = -2.f * px, qy = -2.f * py, qz = -2.f * pz;
+                    const int j0 = (int)tag * kColChunk;
+#pragma unroll 4
+                    for (int i = 0; i < 8; ++i) {
+                        const int k = (lane + i) & 7, j = j0 + 4 * k;
+                        if (j < n_opp) {                        // n_opp % 4 == 0: whole groups
+                            float cx[4], cy[4], cz[4];
+                            if (opp_cm) {
+                                const float4 fx = *reinterpret_cast<const float4 *>(stage + j);
+                                const float4 fy = *reinterpret_cast<const float4 *>(stage + sa.stage_stride + j);
+                                const float4 fz = *reinterpret_cast<const float4 *>(stage + 2 * sa.stage_stride + j);
+                                cx[0] = fx.x; cx[1] = fx.y; cx[2] = fx.z; cx[3] = fx.w;
+                                cy[0] = fy.x; cy[1] = fy.y; cy[2] = fy.z; cy[3] = fy.w;
+                                cz[0] = fz.x; cz[1] = fz.y; cz[2] = fz.z; cz[3] = fz.w;
+                            } else {
+                                const float4 *g = reinterpret_cast<const float4 *>(stage + (size_t)j * 3);
+                                const float4 f0 = g[0], f1 = g[1], f2 = g[2];
+                                cx[0] = f0.x; cx[1] = f0.w; cx[2] = f1.z; cx[3] = f2.y;
+                                cy[0] = f0.y; cy[1] = f1.x; cy[2] = f1.w; cy[3] = f2.z;
+                                cz[0] = f0.z; cz[1] = f1.y; cz[2] = f2.x; cz[3] = f2.w;
+                            }
+#pragma unroll
+                            for (int t = 0; t < 4; ++t)
+                                if (pair_dist_scalar<FORM>(qx, qy, qz, pn, cx[t], cy[t], cz[t], sq_norm3(NORM, cx[t], cy[t], cz[t])) == v)
+                                    arg = min(arg, j + t);
+                        }
+                    }
+                }
+            } else if ((tag >> 5) < (uint32_t)a.nrowgroups) {
+                // column point (x, y, z, n) against the R rows of the winning lane
+                const int i0 = (int)(tag >> 5) * (32 * R) + (int)(tag & 31u) * R;
+                if (R >= 4) {
+                    const int ng = R >> 2;
+#pragma unroll 4
+                    for (int i = 0; i < ng; ++i) {
+                        const int k = (lane + i) & (ng - 1), r0 = i0 + 4 * k;
+                        if (r0 < n_opp) {
+                            float x[4], y[4], z[4];
+                            if (opp_cm) {
+                                const float4 fx = *reinterpret_cast<const float4 *>(stage + r0);
+                                const float4 fy = *reinterpret_cast<const float4 *>(stage + sa.stage_stride + r0);
+                                const float4 fz = *reinterpret_cast<const float4 *>(stage + 2 * sa.stage_stride + r0);
+                                x[0] = fx.x; x[1] = fx.y; x[2] = fx.z; x[3] = fx.w;
+                                y[0] = fy.x; y[1] = fy.y; y[2] = fy.z; y[3] = fy.w;
+                                z[0] = fz.x; z[1] = fz.y; z[2] = fz.z; z[3] = fz.w;
+                            } else {
+                                const float4 *g = reinterpret_cast<const float4 *>(stage + (size_t)r0 * 3);
+                                const float4 f0 = g[0], f1 = g[1], f2 = g[2];
+                                x[0] = f0.x; x[1] = f0.w; x[2] = f1.z; x[3] = f2.y;
+                                y[0] = f0.y; y[1] = f1.x; y[2] = f1.w; y[3] = f2.z;
+                                z[0] = f0.z; z[1] = f1.y; z[2] = f2.x; z[3] = f2.w;
+                            }
+#pragma unroll
+                            for (int t = 0; t < 4; ++t)
+                                if (pair_dist_scalar<FORM>(-2.f * x[t], -2.f * y[t], -2.f * z[t], sq_norm3(NORM, x[t], y[t], z[t]), px, py, pz, pn) == v)
+                                    arg = min(arg, r0 + t);
+                        }
+                    }
+                } else {
+                    for (int t = 0; t < R; ++t) {
+                        const int i = i0 + t;
+                        if (i < n_opp) {
+                            float x, y, z;
+                            if (opp_cm) { x = stage[i]; y = stage[sa.stage_stride + i]; z = stage[2 * sa.stage_stride + i]; }
+                            else { x = stage[3 * i]; y = stage[3 * i + 1]; z = stage[3 * i + 2]; }
+                            if (pair_dist_scalar<FORM>(-2.f * x, -2.f * y, -2.f * z, sq_norm3(NORM, x, y, z), px, py, pz, pn) == v) arg = min(arg, i);
+                        }
+                    }
+                }
+            }
+            if (arg == 0x7fffffff) arg = 0;        // no finite minimum (NaN / inf inputs)
+            const float val = apply_transform(a.transform, v);
+            out_min[p] = val; out_arg[p] = arg;
+            acc_s += val;
+            if (val > acc_mx) { acc_mx = val; acc_am = p; }
+        }
+        key = nkey; px = nx; py = ny; pz = nz;
+    }
+
+    // slice partial: warp tree, warps in order
+    reduce_smf(acc_s, acc_mx, acc_am);
+    if (lane == 0) { red_s[warp] = acc_s; red_mx[warp] = acc_mx; red_am[warp] = acc_am; }
+    __syncthreads();
+    if (warp == 0) {
+        const bool has = lane < kFixupThreads / 32;
+        float sv = has ? red_s[lane] : 0.f, mx = has ? red_mx[lane] : ninf;
+        int am = has ? red_am[lane] : 0x7fffffff;
+        reduce_smf(sv, mx, am);
+        if (lane == 0) {
+            a.partials[((size_t)b * 2 + side) * a.slots + q] = make_float4(sv, mx, __int_as_float(am), 0.f);
+            __threadfence();
+            s_last = atomicAdd(&a.counters[b], 1) == 2 * sa.parts - 1;
+        }
+    }
+    __syncthreads();
+    if (!s_last || warp >= 2) return;
+    __threadfence();
+    {   // last CTA of sample b: warp `sd` folds the parts partials of that side (lane-strided, then the tree)
+        const int sd = warp;
+        float sv = 0.f, mx = ninf;
+        int am = 0x7fffffff;
+        for (int k = lane; k < sa.parts; k += 32) {
+            const float4 t = __ldcg(&a.partials[((size_t)b * 2 + sd) * a.slots + k]);
+            sv += t.x;
+            const int ta = __float_as_int(t.z);
+            if (t.y > mx || (t.y == mx && ta < am)) { mx = t.y; am = ta; }
+        }
+        reduce_smf(sv, mx, am);
+        if (lane == 0) {
+            a.stats_f[(sd * 2 + 0) * a.B + b] = sv * (sd ? a.col_scale : a.row_scale);
+            a.stats_f[(sd * 2 + 1) * a.B + b] = mx;
+            a.stats_i[sd * a.B + b] = am == 0x7fffffff ? 0 : am;
+        }
     }
 }
 
@@ -833,6 +1137,11 @@ static cudaError_t launch_sweep(const SweepSrc &src, unsigned long long *rowkey,
         cudaError_t e = cudaFuncSetAttribute(nn1_sweep_kernel<FORM, R, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)sizeof(Smem));
         if (e != cudaSuccess) return e;
+        // ask for the shared-memory carve-out explicitly: the register-limited residency (2 CTAs at R = 16) needs
+        // 2 x 55 KB, more than the default split provides
+        e = cudaFuncSetAttribute(nn1_sweep_kernel<FORM, R, RAW>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 (int)cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
         int o = 0;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, nn1_sweep_kernel<FORM, R, RAW>, kSweepThreads, sizeof(Smem));
         if (e != cudaSuccess) return e;
@@ -863,11 +1172,57 @@ static cudaError_t launch_sweep_f(int form, int R, const SweepSrc &src, unsigned
     return launch_sweep_r<PCD_FORM_SUM_FIRST, RAW>(R, src, rowkey, colkey, B, N, M, Npad, Mpad, mt, sms, st);
 }
 
+template <bool RAW, int NORM>
+static cudaError_t launch_fixup_n(int form, const FixupArgs &a, dim3 grid, cudaStream_t st) {
+    if (form == PCD_FORM_ROW_COL) return launch_kernel(nn1_fixup_kernel<PCD_FORM_ROW_COL, RAW, NORM>, grid, dim3(kFixupThreads), 0, st, true, a);
+    if (form == PCD_FORM_COL_ROW) return launch_kernel(nn1_fixup_kernel<PCD_FORM_COL_ROW, RAW, NORM>, grid, dim3(kFixupThreads), 0, st, true, a);
+    return launch_kernel(nn1_fixup_kernel<PCD_FORM_SUM_FIRST, RAW, NORM>, grid, dim3(kFixupThreads), 0, st, true, a);
+}
 template <bool RAW>
 static cudaError_t launch_fixup(int form, const FixupArgs &a, dim3 grid, cudaStream_t st) {
-    if (form == PCD_FORM_ROW_COL) return launch_kernel(nn1_fixup_kernel<PCD_FORM_ROW_COL, RAW>, grid, dim3(kFixupThreads), 0, st, true, a);
-    if (form == PCD_FORM_COL_ROW) return launch_kernel(nn1_fixup_kernel<PCD_FORM_COL_ROW, RAW>, grid, dim3(kFixupThreads), 0, st, true, a);
-    return launch_kernel(nn1_fixup_kernel<PCD_FORM_SUM_FIRST, RAW>, grid, dim3(kFixupThreads), 0, st, true, a);
+    // the norm rounding is a template parameter of the streamed variant only (the packed records carry their norms)
+    if constexpr (RAW) {
+        if (a.norm_kind == PCD_NORM_FMA) return launch_fixup_n<true, PCD_NORM_FMA>(form, a, grid, st);
+    }
+    return launch_fixup_n<RAW, PCD_NORM_MULSUM>(form, a, grid, st);
+}
+
+// Shared-memory staged fix-up (dense clouds of up to kStageMaxBytes): see nn1_fixup_staged_kernel.
+constexpr size_t kStageMaxBytes = 200 * 1024;
+
+// One CTA per (sample, side, slice); `parts` slices per job are chosen so that the whole grid is resident at once
+// (a second wave of CTAs would wait for the first one to drain: +40 % at BASELINE config 2).
+template <int FORM, int NORM>
+static cudaError_t launch_fixup_staged_fn(StagedArgs sa, int B, int units_min, int max_parts, int sms, size_t smem, cudaStream_t st) {
+    static PerDeviceInt attr_set = {};
+    const int dev = current_device();
+    if (dev < 0) return cudaErrorInvalidDevice;
+    if (!attr_set.v[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(nn1_fixup_staged_kernel<FORM, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageMaxBytes);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(nn1_fixup_staged_kernel<FORM, NORM>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 (int)cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        attr_set.v[dev] = 1;
+    }
+    // residency for this staging size: 1 .. 3 CTAs per SM (register bound 3); the query is cheap next to the launch
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nn1_fixup_staged_kernel<FORM, NORM>, kFixupThreads, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    int parts = sms * per_sm / (2 * B);
+    if (parts > units_min) parts = units_min;
+    if (parts > max_parts) parts = max_parts;
+    if (parts < 1) parts = 1;
+    sa.parts = parts;
+    return launch_kernel(nn1_fixup_staged_kernel<FORM, NORM>, dim3((unsigned)(2 * B * parts)), dim3(kFixupThreads), smem, st, true, sa);
+}
+template <int NORM>
+static cudaError_t launch_fixup_staged_n(int form, const StagedArgs &sa, int B, int units_min, int max_parts, int sms, size_t smem,
+                                         cudaStream_t st) {
+    if (form == PCD_FORM_ROW_COL) return launch_fixup_staged_fn<PCD_FORM_ROW_COL, NORM>(sa, B, units_min, max_parts, sms, smem, st);
+    if (form == PCD_FORM_COL_ROW) return launch_fixup_staged_fn<PCD_FORM_COL_ROW, NORM>(sa, B, units_min, max_parts, sms, smem, st);
+    return launch_fixup_staged_fn<PCD_FORM_SUM_FIRST, NORM>(sa, B, units_min, max_parts, sms, smem, st);
 }
 
 // Tile-shape heuristic.  R rows per lane (register blocking: the per-step overhead -- operand
@@ -997,13 +1352,35 @@ extern "C" int pcd_nn1_forward(const float *rows, int64_t r_sb, int64_t r_sp, in
                        : launch_sweep_f<false>(form, R, src, rowkey, colkey, B, N, M, L.Npad, L.Mpad, mt, sms, st));
     if (sweep_stop_event) PCD_CUDA_CHECK(cudaEventRecord((cudaEvent_t)sweep_stop_event, st));
     {
+        // persistent grid: every warp of every resident CTA owns a contiguous range of units (32 points of one side)
+        const long long octets = (long long)B * ((N + 31) / 32 + (M + 31) / 32);
+        if (octets >= (1LL << 31)) {
+            set_error("pcd_nn1_forward: B * (N + M) too large");
+            return PCD_ERR_ARG;
+        }
+        long long nwarps = (long long)sms * kFixupCtasPerSm * (kFixupThreads / 32);
+        if (nwarps > kFixupMaxWarps) nwarps = kFixupMaxWarps;
+        if (nwarps > octets) nwarps = octets;
         FixupArgs a{rows, (long long)r_sb, (long long)r_sp, (long long)r_sc, cols, (long long)c_sb, (long long)c_sp, (long long)c_sc,
                     rowpk, (const float4 *)colpk, col_cm ? 2 : 1, norm_kind, rowkey, colkey, counters,
-                    N, M, L.Npad, L.Mpad, R, transform, B, row_min, row_arg, col_min, col_arg,
+                    (float4 *)(ws + L.partials), L.partial_slots, (int)nwarps, (int)(octets / nwarps), (int)(octets % nwarps),
+                    (N + 32 * R - 1) / (32 * R), (M + kColChunk - 1) / kColChunk, N, M, L.Npad, L.Mpad, R, transform, B, row_min, row_arg, col_min, col_arg,
                     row_sum_scale, col_sum_scale, stats_f, stats_i,
                     (float4 *)zero0, zero0_floats / 4, (float4 *)zero1, zero1_floats / 4};
-        const dim3 grid((N + M + kFixupPoints - 1) / kFixupPoints, B);
-        PCD_CUDA_CHECK(raw ? launch_fixup<true>(form, a, grid, st) : launch_fixup<false>(form, a, grid, st));
+        const int nmax = N > M ? N : M;
+        const size_t stage_stride = align_up((size_t)nmax, 32);
+        const size_t stage_bytes = stage_stride * 12;
+        if (raw && stage_bytes <= kStageMaxBytes) {
+            // one CTA per (sample, side, slice): the re-scanned cloud is staged in shared memory
+            const int units_min = ((N < M ? N : M) + 31) / 32;
+            StagedArgs sa{a, 1, (int)stage_stride};
+            PCD_CUDA_CHECK(norm_kind == PCD_NORM_FMA
+                               ? launch_fixup_staged_n<PCD_NORM_FMA>(form, sa, B, units_min, L.partial_slots, sms, stage_bytes, st)
+                               : launch_fixup_staged_n<PCD_NORM_MULSUM>(form, sa, B, units_min, L.partial_slots, sms, stage_bytes, st));
+        } else {
+            const dim3 grid((unsigned)((nwarps + kFixupThreads / 32 - 1) / (kFixupThreads / 32)));
+            PCD_CUDA_CHECK(raw ? launch_fixup<true>(form, a, grid, st) : launch_fixup<false>(form, a, grid, st));
+        }
     }
     return PCD_OK;
 }

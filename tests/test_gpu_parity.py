@@ -124,6 +124,15 @@ def test_nn1_every_tiling(tiling):
         F.force_tiling(0, 0)
 
 
+def test_nn1_clouds_too_large_for_shared_memory_staging():
+    """> 17 K points per cloud: the fix-up re-scans from global memory instead of a staged copy (same results)."""
+    rs = np.random.RandomState(77)
+    cols = (rs.rand(1, 17408, 3) - 0.5).astype(np.float32)
+    rows = (cols[:, :17200] + 0.002 * rs.randn(1, 17200, 3)).astype(np.float32)
+    check_nn1(rows, cols, "sum_first_fma")
+    check_nn1(np.ascontiguousarray(cols[:, :17100]), rows, "row_col_mulsum")
+
+
 def test_nn1_full_size_c2_against_oracle():
     """BASELINE config 2 (B=32, N=M=4096, sigma=0.01): every index and value against the C oracle."""
     synth = importlib.import_module("3dpointcloudattack_b200.synth")
@@ -187,7 +196,7 @@ def test_fused_chamfer_hausdorff_shares_one_sweep():
     with torch.no_grad():
         p.add_(0.001)                        # in-place update bumps the version -> no stale hit
     c1b, _ = pcd.distance.chamfer(p, t)
-    assert F.launches() - n0 == 4 + 1 + 4
+    assert F.launches() - n0 == 3 + 1 + 3
     assert not torch.equal(c1, c1b)
 
 
@@ -485,8 +494,11 @@ def test_nn1_raw_and_packed_paths_agree():
         (r.row_sum.sum() + 2 * r.col_max.sum() + (r.col_min * r.col_min).sum()).backward()
         outs.append([npy(x) for x in (r.row_min, r.row_arg, r.col_min, r.col_arg, r.row_sum, r.col_max, r.col_argmax, tr.grad, tc.grad)])
     for other in outs[1:]:
-        for a, b in zip(outs[0][:7], other[:7]):
-            assert np.array_equal(a, b)
+        for k, (a, b) in enumerate(zip(outs[0][:7], other[:7])):
+            if k == 4:
+                np.testing.assert_allclose(a, b, rtol=2e-6)      # per-sample sums: the paths fold in different (fixed) orders
+            else:
+                assert np.array_equal(a, b)
         for a, b in zip(outs[0][7:], other[7:]):
             assert rel_inf(a, b) < 2e-6          # atomics: summation order only
 
