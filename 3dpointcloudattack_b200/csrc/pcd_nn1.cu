@@ -61,7 +61,7 @@ struct Nn1Layout {
     int Npad, Mpad;
     size_t rowkey, colkey, counters, partials, rowpk, rowpp, colpk, total;
     size_t nkeys;
-    int partial_slots;     // fix-up partial slots per sample and side
+    int partial_slots;     // fix-up partials per sample (one per 32-point unit)
 };
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // keys + counters first (all the dense-input path touches), the packed records of the strided
@@ -75,8 +75,8 @@ static Nn1Layout nn1_layout(int B, int N, int M) {
     L.colkey = off; off += (size_t)B * L.Mpad * 8;
     L.nkeys = (size_t)B * L.Npad + (size_t)B * L.Mpad;
     L.counters = off; off = align_up(off + (size_t)B * 4, 256);
-    L.partial_slots = kFixupMaxWarps / B + 2;                  // warps that can touch one sample (see nn1_fixup_kernel)
-    L.partials = off; off = align_up(off + (size_t)B * 2 * L.partial_slots * 16, 256);   // per sample, side and warp: (sum, max, argmax, -)
+    L.partial_slots = (N + 31) / 32 + (M + 31) / 32;          // one partial per unit of 32 points: rows first, then columns
+    L.partials = off; off = align_up(off + (size_t)B * L.partial_slots * 16, 256);       // (sum, max, bits of argmax, -)
     L.rowpk = off; off = align_up(off + (size_t)B * L.Npad * 16, 256);
     L.rowpp = off; off = align_up(off + (size_t)B * L.Npad * 16, 256);   // the same records in sweep (slot) order
     L.colpk = off; off = align_up(off + (size_t)B * L.Mpad * 16 + 64, 256);   // +64: the sweep prefetches one record past a tile
@@ -520,8 +520,8 @@ struct FixupArgs {
     int norm_kind;
     const unsigned long long *rowkey, *colkey;
     int *counters;                // [B] octets finished per sample (armed to 0)
-    float4 *partials;             // [B][2][slots]: per warp and side (sum, max, bits of argmax) of the minima it handled
-    int slots;                    // partial slots per sample and side
+    float4 *partials;             // [B][slots]: per 32-point unit (rows first, then columns) the (sum, max, bits of argmax) of its minima
+    int slots;                    // units per sample
     int nwarps;                   // participating warps W (<= number of octets U)
     int upw, urem;                // U / W, U % W: warp w owns upw (+1 if w < urem) consecutive octets
     int nrowgroups;               // ceil(N / 32R): valid range of the lane-group part of a column tag
@@ -548,6 +548,36 @@ struct FixupArgs {
 // sample and side, one xor-tree per segment, one partial per (sample, side, warp); the warp whose
 // completion count closes a sample folds that sample's partials -- all in a fixed order, so the
 // sums are run-to-run deterministic.
+// Statistics of one sample from its unit partials, by one warp per side: lane-strided over the units in
+// index order, then the xor tree -- an order that depends on nothing but (N, M), so a sample's sums are
+// bit-identical whatever the batch size, the launch geometry or the operand path.
+__device__ __forceinline__ void fold_sample_side(const FixupArgs &a, int b, int side, int lane) {
+    const float ninf = -__int_as_float(0x7f800000);
+    const int urow = (a.N + 31) >> 5, ucol = (a.M + 31) >> 5;
+    const int first = side ? urow : 0, count = side ? ucol : urow;
+    float sv = 0.f, mx = ninf;
+    int am = 0x7fffffff;
+    for (int k = lane; k < count; k += 32) {
+        const float4 t = __ldcg(&a.partials[(size_t)b * a.slots + first + k]);
+        sv += t.x;
+        const int ta = __float_as_int(t.z);
+        if (t.y > mx || (t.y == mx && ta < am)) { mx = t.y; am = ta; }
+    }
+    reduce_smf(sv, mx, am);
+    if (lane == 0) {
+        a.stats_f[(side * 2 + 0) * a.B + b] = sv * (side ? a.col_scale : a.row_scale);
+        a.stats_f[(side * 2 + 1) * a.B + b] = mx;
+        a.stats_i[side * a.B + b] = am == 0x7fffffff ? 0 : am;
+    }
+}
+// the partial of one unit: xor tree over its 32 lanes (dead lanes are neutral)
+__device__ __forceinline__ void store_unit_partial(const FixupArgs &a, int b, int unit_in_sample, bool live, float val, int p, int lane) {
+    float sv = live ? val : 0.f, mx = live ? val : -__int_as_float(0x7f800000);
+    int am = live ? p : 0x7fffffff;
+    reduce_smf(sv, mx, am);
+    if (lane == 0) a.partials[(size_t)b * a.slots + unit_in_sample] = make_float4(sv, mx, __int_as_float(am), 0.f);
+}
+
 struct FixPt {
     int b, p;
     bool live, is_col;
@@ -674,12 +704,6 @@ nn1_fixup_kernel(FixupArgs a) {
     const int urow = (N + 31) >> 5, ucol = (M + 31) >> 5, Us = urow + ucol;    // units per sample
     // warp w owns the units [w*upw + min(w, urem), ... + upw (+1 if w < urem)): no division in the hot path
     const int u_begin = w * a.upw + min(w, a.urem), u_end = u_begin + a.upw + (w < a.urem ? 1 : 0);
-    // inverse map: the warp that owns unit x
-    auto warp_of = [&](int x) -> int {
-        const int split = a.urem * (a.upw + 1);
-        return x < split ? x / (a.upw + 1) : a.urem + (x - split) / a.upw;
-    };
-
     // request everything of unit (b, o) that does not depend on another load: key and own coordinates of this lane's point
     auto fetch = [&](int b_, int o) -> FixPt {
         FixPt f;
@@ -708,21 +732,9 @@ nn1_fixup_kernel(FixupArgs a) {
 
     if (RAW) pdl_wait();      // the keys: the sweep has completed and flushed
 
-    // lane-local running statistics of the current sample, per side
-    float acc_s[2] = {0.f, 0.f}, acc_mx[2] = {ninf, ninf};
-    int acc_am[2] = {0x7fffffff, 0x7fffffff};
-    // close the warp's segment of sample b: partials, completion count, and -- if we are last -- the sample's statistics
+    // close the warp's segment of sample b: completion count, and -- if we are last -- the sample's statistics
     auto finish_sample = [&](int b) {
         const int s0 = b * Us, s1 = s0 + Us;                                     // the sample's unit range
-        const int w0 = warp_of(s0), w1 = warp_of(s1 - 1);                         // warps holding its first / last unit
-#pragma unroll
-        for (int side = 0; side < 2; ++side) {
-            float sv = acc_s[side], mx = acc_mx[side];
-            int am = acc_am[side];
-            reduce_smf(sv, mx, am);
-            if (lane == 0) a.partials[((size_t)b * 2 + side) * a.slots + (size_t)(w - w0)] = make_float4(sv, mx, __int_as_float(am), 0.f);
-            acc_s[side] = 0.f; acc_mx[side] = ninf; acc_am[side] = 0x7fffffff;
-        }
         int last = 0;
         if (lane == 0) {
             const int done = min(u_end, s1) - max(u_begin, s0);
@@ -732,24 +744,8 @@ nn1_fixup_kernel(FixupArgs a) {
         last = __shfl_sync(0xffffffffu, last, 0);
         if (!last) return;
         __threadfence();
-        const int nslots = w1 - w0 + 1;
-#pragma unroll
-        for (int side = 0; side < 2; ++side) {
-            float sv = 0.f, mx = ninf;
-            int am = 0x7fffffff;
-            for (int k = lane; k < nslots; k += 32) {
-                const float4 t = __ldcg(&a.partials[((size_t)b * 2 + side) * a.slots + k]);
-                sv += t.x;
-                const int ta = __float_as_int(t.z);
-                if (t.y > mx || (t.y == mx && ta < am)) { mx = t.y; am = ta; }
-            }
-            reduce_smf(sv, mx, am);
-            if (lane == 0) {
-                a.stats_f[(side * 2 + 0) * a.B + b] = sv * (side ? a.col_scale : a.row_scale);
-                a.stats_f[(side * 2 + 1) * a.B + b] = mx;
-                a.stats_i[side * a.B + b] = am == 0x7fffffff ? 0 : am;
-            }
-        }
+        fold_sample_side(a, b, 0, lane);
+        fold_sample_side(a, b, 1, lane);
     };
 
     int nb = u_begin / Us, no = u_begin - nb * Us;        // (sample, unit in sample) of the NEXT unit to fetch
@@ -759,6 +755,7 @@ nn1_fixup_kernel(FixupArgs a) {
         if (++no == Us) { no = 0; ++nb; }
         if (u + 1 < u_end) nxt = fetch(nb, no);
         const int b = cur.b, p = cur.p;
+        float val = 0.f;
         if (cur.live) {
             const float v = ordered_to_f32((uint32_t)(cur.key >> 32));
             const uint32_t tag = (uint32_t)cur.key;
@@ -772,18 +769,11 @@ nn1_fixup_kernel(FixupArgs a) {
                 arg = fixup_scan_rows<FORM, RAW, NORM>(a, b, (int)(tag >> 5) * (32 * R) + (int)(tag & 31u) * R, ox, oy, oz, on, v);
             }
             if (arg == 0x7fffffff) arg = 0;        // no finite minimum (NaN / inf inputs)
-            const float val = apply_transform(a.transform, v);
-            // constant indices only: a run-time side index would push the accumulators into local memory
-            if (!cur.is_col) {
-                a.row_min[(size_t)b * N + p] = val; a.row_arg[(size_t)b * N + p] = arg;
-                acc_s[0] += val;
-                if (val > acc_mx[0]) { acc_mx[0] = val; acc_am[0] = p; }
-            } else {
-                a.col_min[(size_t)b * M + p] = val; a.col_arg[(size_t)b * M + p] = arg;
-                acc_s[1] += val;
-                if (val > acc_mx[1]) { acc_mx[1] = val; acc_am[1] = p; }
-            }
+            val = apply_transform(a.transform, v);
+            if (!cur.is_col) { a.row_min[(size_t)b * N + p] = val; a.row_arg[(size_t)b * N + p] = arg; }
+            else { a.col_min[(size_t)b * M + p] = val; a.col_arg[(size_t)b * M + p] = arg; }
         }
+        store_unit_partial(a, b, u - b * Us, cur.live, val, p, lane);
         if (u + 1 == u_end || nxt.b != b) finish_sample(b);       // warp-uniform: every lane of a unit is in the same sample
         cur = nxt;
     }
@@ -804,8 +794,9 @@ nn1_fixup_kernel(FixupArgs a) {
 // whose completion count closes a sample folds the 2 x parts partials in a fixed order.
 struct StagedArgs {
     FixupArgs f;
-    int parts;             // slices per job
-    int stage_stride;      // channel-major staging: floats between the channel rows (multiple of 32)
+    int parts_row, parts_col;   // slices per (sample, side): a row point scans 32 candidates, a column point R, so the
+                                // sides get slice counts in proportion to their work
+    int stage_stride;           // channel-major staging: floats between the channel rows (multiple of 32)
 };
 
 template <int FORM, int NORM>
@@ -814,14 +805,13 @@ nn1_fixup_staged_kernel(StagedArgs sa) {
     const FixupArgs &a = sa.f;
     extern __shared__ __align__(128) float stage[];
     __shared__ uint64_t bar;
-    __shared__ float red_s[kFixupThreads / 32], red_mx[kFixupThreads / 32];
-    __shared__ int red_am[kFixupThreads / 32];
     __shared__ int s_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = a.N, M = a.M, R = a.R;
-    const float ninf = -__int_as_float(0x7f800000);
-    const int job = blockIdx.x / sa.parts, q = blockIdx.x - job * sa.parts;
-    const int b = job >> 1, side = job & 1;
+    const int per_sample = sa.parts_row + sa.parts_col;
+    const int b = blockIdx.x / per_sample, rem = blockIdx.x - b * per_sample;
+    const int side = rem >= sa.parts_row ? 1 : 0, q = side ? rem - sa.parts_row : rem;
+    const int parts = side ? sa.parts_col : sa.parts_row;
     const int n_own = side ? M : N, n_opp = side ? N : M;            // points of this side / candidates
     const float *own = side ? a.cols + (size_t)b * a.c_sb : a.rows + (size_t)b * a.r_sb;
     const long long own_sp = side ? a.c_sp : a.r_sp, own_sc = side ? a.c_sc : a.r_sc;
@@ -853,13 +843,11 @@ nn1_fixup_staged_kernel(StagedArgs sa) {
     mbar_wait(&bar, 0);       // the candidate cloud is in shared memory
 
     const int units = (n_own + 31) >> 5;
-    const int u0 = (int)((long long)units * q / sa.parts), u1 = (int)((long long)units * (q + 1) / sa.parts);
+    const int u0 = (int)((long long)units * q / parts), u1 = (int)((long long)units * (q + 1) / parts);
     const unsigned long long *keys = side ? a.colkey + (size_t)b * a.Mpad : a.rowkey + (size_t)b * a.Npad;
     float *out_min = side ? a.col_min + (size_t)b * M : a.row_min + (size_t)b * N;
     int32_t *out_arg = side ? a.col_arg + (size_t)b * M : a.row_arg + (size_t)b * N;
 
-    float acc_s = 0.f, acc_mx = ninf;
-    int acc_am = 0x7fffffff;
     // software pipeline over this warp's units: key and own coordinates of the next unit are requested first
     unsigned long long key = 0ull;
     float px = 0.f, py = 0.f, pz = 0.f;
@@ -877,6 +865,7 @@ nn1_fixup_staged_kernel(StagedArgs sa) {
         unsigned long long nkey; float nx, ny, nz;
         fetch(u + kFixupThreads / 32, nkey, nx, ny, nz);
         const int p = u * 32 + lane;
+        float val = 0.f;
         if (p < n_own) {
             const float v = ordered_to_f32((uint32_t)(key >> 32));
             const uint32_t tag = (uint32_t)key;
@@ -956,49 +945,19 @@ nn1_fixup_staged_kernel(StagedArgs sa) {
                 }
             }
             if (arg == 0x7fffffff) arg = 0;        // no finite minimum (NaN / inf inputs)
-            const float val = apply_transform(a.transform, v);
+            val = apply_transform(a.transform, v);
             out_min[p] = val; out_arg[p] = arg;
-            acc_s += val;
-            if (val > acc_mx) { acc_mx = val; acc_am = p; }
         }
+        store_unit_partial(a, b, (side ? (N + 31) >> 5 : 0) + u, p < n_own, val, p, lane);
         key = nkey; px = nx; py = ny; pz = nz;
     }
-
-    // slice partial: warp tree, warps in order
-    reduce_smf(acc_s, acc_mx, acc_am);
-    if (lane == 0) { red_s[warp] = acc_s; red_mx[warp] = acc_mx; red_am[warp] = acc_am; }
+    if (lane == 0) __threadfence();       // this warp's unit partials are visible before the CTA reports completion
     __syncthreads();
-    if (warp == 0) {
-        const bool has = lane < kFixupThreads / 32;
-        float sv = has ? red_s[lane] : 0.f, mx = has ? red_mx[lane] : ninf;
-        int am = has ? red_am[lane] : 0x7fffffff;
-        reduce_smf(sv, mx, am);
-        if (lane == 0) {
-            a.partials[((size_t)b * 2 + side) * a.slots + q] = make_float4(sv, mx, __int_as_float(am), 0.f);
-            __threadfence();
-            s_last = atomicAdd(&a.counters[b], 1) == 2 * sa.parts - 1;
-        }
-    }
+    if (tid == 0) s_last = atomicAdd(&a.counters[b], 1) == per_sample - 1;
     __syncthreads();
     if (!s_last || warp >= 2) return;
     __threadfence();
-    {   // last CTA of sample b: warp `sd` folds the parts partials of that side (lane-strided, then the tree)
-        const int sd = warp;
-        float sv = 0.f, mx = ninf;
-        int am = 0x7fffffff;
-        for (int k = lane; k < sa.parts; k += 32) {
-            const float4 t = __ldcg(&a.partials[((size_t)b * 2 + sd) * a.slots + k]);
-            sv += t.x;
-            const int ta = __float_as_int(t.z);
-            if (t.y > mx || (t.y == mx && ta < am)) { mx = t.y; am = ta; }
-        }
-        reduce_smf(sv, mx, am);
-        if (lane == 0) {
-            a.stats_f[(sd * 2 + 0) * a.B + b] = sv * (sd ? a.col_scale : a.row_scale);
-            a.stats_f[(sd * 2 + 1) * a.B + b] = mx;
-            a.stats_i[sd * a.B + b] = am == 0x7fffffff ? 0 : am;
-        }
-    }
+    fold_sample_side(a, b, warp, lane);   // last CTA of sample b: one warp per side
 }
 
 // -------------------------------------------------------------------------------- backward
@@ -1193,7 +1152,7 @@ constexpr size_t kStageMaxBytes = 200 * 1024;
 // One CTA per (sample, side, slice); `parts` slices per job are chosen so that the whole grid is resident at once
 // (a second wave of CTAs would wait for the first one to drain: +40 % at BASELINE config 2).
 template <int FORM, int NORM>
-static cudaError_t launch_fixup_staged_fn(StagedArgs sa, int B, int units_min, int max_parts, int sms, size_t smem, cudaStream_t st) {
+static cudaError_t launch_fixup_staged_fn(StagedArgs sa, int B, int max_parts, int sms, size_t smem, cudaStream_t st) {
     static PerDeviceInt attr_set = {};
     const int dev = current_device();
     if (dev < 0) return cudaErrorInvalidDevice;
@@ -1210,19 +1169,26 @@ static cudaError_t launch_fixup_staged_fn(StagedArgs sa, int B, int units_min, i
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nn1_fixup_staged_kernel<FORM, NORM>, kFixupThreads, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
-    int parts = sms * per_sm / (2 * B);
-    if (parts > units_min) parts = units_min;
-    if (parts > max_parts) parts = max_parts;
-    if (parts < 1) parts = 1;
-    sa.parts = parts;
-    return launch_kernel(nn1_fixup_staged_kernel<FORM, NORM>, dim3((unsigned)(2 * B * parts)), dim3(kFixupThreads), smem, st, true, sa);
+    // slices per sample, split between the sides in proportion to their scan work (32 candidates per row point, R per column point)
+    const int urow = (sa.f.N + 31) / 32, ucol = (sa.f.M + 31) / 32;
+    int total = sms * per_sm / B;
+    if (total < 2) total = 2;
+    const double wr = 32.0 * sa.f.N, wc = (double)sa.f.R * sa.f.M;
+    int pr = (int)(total * wr / (wr + wc) + 0.5);
+    if (pr < 1) pr = 1;
+    if (pr > total - 1) pr = total - 1;
+    int pc = total - pr;
+    if (pr > urow) pr = urow;
+    if (pc > ucol) pc = ucol;
+    (void)max_parts;
+    sa.parts_row = pr; sa.parts_col = pc;
+    return launch_kernel(nn1_fixup_staged_kernel<FORM, NORM>, dim3((unsigned)(B * (pr + pc))), dim3(kFixupThreads), smem, st, true, sa);
 }
 template <int NORM>
-static cudaError_t launch_fixup_staged_n(int form, const StagedArgs &sa, int B, int units_min, int max_parts, int sms, size_t smem,
-                                         cudaStream_t st) {
-    if (form == PCD_FORM_ROW_COL) return launch_fixup_staged_fn<PCD_FORM_ROW_COL, NORM>(sa, B, units_min, max_parts, sms, smem, st);
-    if (form == PCD_FORM_COL_ROW) return launch_fixup_staged_fn<PCD_FORM_COL_ROW, NORM>(sa, B, units_min, max_parts, sms, smem, st);
-    return launch_fixup_staged_fn<PCD_FORM_SUM_FIRST, NORM>(sa, B, units_min, max_parts, sms, smem, st);
+static cudaError_t launch_fixup_staged_n(int form, const StagedArgs &sa, int B, int max_parts, int sms, size_t smem, cudaStream_t st) {
+    if (form == PCD_FORM_ROW_COL) return launch_fixup_staged_fn<PCD_FORM_ROW_COL, NORM>(sa, B, max_parts, sms, smem, st);
+    if (form == PCD_FORM_COL_ROW) return launch_fixup_staged_fn<PCD_FORM_COL_ROW, NORM>(sa, B, max_parts, sms, smem, st);
+    return launch_fixup_staged_fn<PCD_FORM_SUM_FIRST, NORM>(sa, B, max_parts, sms, smem, st);
 }
 
 // Tile-shape heuristic.  R rows per lane (register blocking: the per-step overhead -- operand
@@ -1372,11 +1338,10 @@ extern "C" int pcd_nn1_forward(const float *rows, int64_t r_sb, int64_t r_sp, in
         const size_t stage_bytes = stage_stride * 12;
         if (raw && stage_bytes <= kStageMaxBytes) {
             // one CTA per (sample, side, slice): the re-scanned cloud is staged in shared memory
-            const int units_min = ((N < M ? N : M) + 31) / 32;
-            StagedArgs sa{a, 1, (int)stage_stride};
+            StagedArgs sa{a, 1, 1, (int)stage_stride};
             PCD_CUDA_CHECK(norm_kind == PCD_NORM_FMA
-                               ? launch_fixup_staged_n<PCD_NORM_FMA>(form, sa, B, units_min, L.partial_slots, sms, stage_bytes, st)
-                               : launch_fixup_staged_n<PCD_NORM_MULSUM>(form, sa, B, units_min, L.partial_slots, sms, stage_bytes, st));
+                               ? launch_fixup_staged_n<PCD_NORM_FMA>(form, sa, B, L.partial_slots, sms, stage_bytes, st)
+                               : launch_fixup_staged_n<PCD_NORM_MULSUM>(form, sa, B, L.partial_slots, sms, stage_bytes, st));
         } else {
             const dim3 grid((unsigned)((nwarps + kFixupThreads / 32 - 1) / (kFixupThreads / 32)));
             PCD_CUDA_CHECK(raw ? launch_fixup<true>(form, a, grid, st) : launch_fixup<false>(form, a, grid, st));

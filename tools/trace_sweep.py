@@ -53,6 +53,13 @@ def main():
     print("  loop end         ", q(loop_end))
     print("  CTA end          ", q(end))
     print("  CTA busy (end-start)", q(end - start))
+    # per SM: when the first / the last of its co-resident CTAs finished
+    sm_first, sm_last = {}, {}
+    for i in range(len(t)):
+        k = int(smid[i])
+        sm_first[k] = min(sm_first.get(k, 1e9), float(end[i])); sm_last[k] = max(sm_last.get(k, 0.0), float(end[i]))
+    print("  per SM: first CTA done", q(np.array(list(sm_first.values()))))
+    print("  per SM: last CTA done ", q(np.array(list(sm_last.values()))))
     # per-SM: co-resident CTAs
     order = np.argsort(end)
     print("  earliest-finishing CTAs:", [(int(i), round(float(end[i]), 1)) for i in order[:5]])
