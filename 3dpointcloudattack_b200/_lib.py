@@ -35,6 +35,10 @@ SIGNATURES = {
     "pcd_edge_feature_forward": (_I, [_P, _P, _I, _I, _I, _I, _I, _c.POINTER(_I), _P, _P]),
     "pcd_edge_feature_backward": (_I, [_P, _P, _I, _I, _I, _I, _I, _c.POINTER(_I), _P, _P]),
     "pcd_fps": (_I, [_P, _L, _L, _L, _I, _I, _I, _P, _P, _P]),
+    "pcd_local_frames": (_I, _CLOUD + [_P, _I, _I, _I, _I] + _CLOUD + [_P, _P, _P]),
+    "pcd_kappa_forward": (_I, _CLOUD + _CLOUD + [_P, _P, _I, _I, _I, _I, _P, _P]),
+    "pcd_kappa_backward": (_I, _CLOUD + _CLOUD + [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
+    "pcd_graph_laplacian": (_I, _CLOUD + [_P, _I, _I, _I, _P, _P]),
     "pcd_fp32_probe_launch": (_I, [_I, _I, _P, _c.POINTER(_c.c_double), _P]),
 }
 

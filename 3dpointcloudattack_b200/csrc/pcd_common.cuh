@@ -194,6 +194,9 @@ static inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
+#ifdef PCD_NO_PDL            // development builds only (tools/): measure the chain without programmatic launches
+    programmatic = false;
+#endif
     cfg.numAttrs = programmatic ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }

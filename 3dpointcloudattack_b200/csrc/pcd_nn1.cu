@@ -1178,8 +1178,10 @@ static cudaError_t launch_fixup_staged_fn(StagedArgs sa, int B, int max_parts, i
     if (pr < 1) pr = 1;
     if (pr > total - 1) pr = total - 1;
     int pc = total - pr;
-    if (pr > urow) pr = urow;
-    if (pc > ucol) pc = ucol;
+    // a slice should give every warp of its CTA at least one unit (each CTA stages the whole candidate cloud)
+    const int wpc = kFixupThreads / 32;
+    if (pr > (urow + wpc - 1) / wpc) pr = (urow + wpc - 1) / wpc;
+    if (pc > (ucol + wpc - 1) / wpc) pc = (ucol + wpc - 1) / wpc;
     (void)max_parts;
     sa.parts_row = pr; sa.parts_col = pc;
     return launch_kernel(nn1_fixup_staged_kernel<FORM, NORM>, dim3((unsigned)(B * (pr + pc))), dim3(kFixupThreads), smem, st, true, sa);

@@ -17,6 +17,7 @@ from ._lib import (EDGE_CENTER, EDGE_DIFF, EDGE_NEIGHBOR, FORM_COL_ROW, FORM_ROW
                    VALUE_SQRT_CLAMP, VALUE_SQUARED)
 
 __all__ = ["nn1", "NN1Result", "time_next_sweep", "clear_cache", "knn", "ball_query", "edge_feature", "farthest_point_sample", "fp32_peak_flops",
+           "local_frames", "kappa", "graph_laplacian",
            "EDGE_CENTER", "EDGE_NEIGHBOR", "EDGE_DIFF",
            "FORM_ROW_COL", "FORM_COL_ROW", "FORM_SUM_FIRST", "NORM_MULSUM", "NORM_FMA",
            "VALUE_SQUARED", "VALUE_SQRT_CLAMP"]
@@ -406,6 +407,111 @@ def farthest_point_sample(xyz, npoint, start=None):
         _lib.check(st, "pcd_fps")
     _launch_count += 1
     return out
+
+
+# ------------------------------------------------ local geometry on a k-NN graph
+def _idx32(idx, dev):
+    return idx.detach().to(device=dev, dtype=torch.int32).contiguous()
+
+
+def local_frames(pc, idx, skip_first=True, normals=True, frames=False):
+    """Per-point covariance eigen-frame of the k-NN patch (pcd_local_frames in include/pcdist.h;
+    attack/GeoA3/utility.py:43-92, :119-152).  pc [B,N,3] fp32 (any strides), idx [B,N,K1] integer
+    (self-kNN of pc; column 0 is dropped when skip_first) -> (normal [B,N,3] or None,
+    evecs [B,N,3,3] rows by ascending eigenvalue or None, evals [B,N,3] or None).  No gradient."""
+    global _launch_count
+    _check_cloud(pc, "pc")
+    lib = _lib.load()
+    B, N, _ = pc.shape
+    dev = pc.device
+    idx32 = _idx32(idx, dev)
+    if idx32.dim() != 3 or idx32.shape[:2] != (B, N):
+        raise ValueError(f"idx must be [B, N, K], got {tuple(idx32.shape)} for pc {tuple(pc.shape)}")
+    K1 = idx32.shape[2]
+    if K1 - int(bool(skip_first)) < 1:
+        raise ValueError("need at least one neighbour")
+    with _on(dev):
+        normal = torch.empty((B, N, 3), dtype=torch.float32, device=dev) if normals else None
+        evecs = torch.empty((B, N, 3, 3), dtype=torch.float32, device=dev) if frames else None
+        evals = torch.empty((B, N, 3), dtype=torch.float32, device=dev) if frames else None
+        x = pc.detach()
+        st = lib.pcd_local_frames(*_cloud_args(x), idx32.data_ptr(), B, N, K1, int(bool(skip_first)),
+                                  _ptr(normal), *([normal.stride(0), normal.stride(1), normal.stride(2)] if normals else [0, 0, 0]),
+                                  _ptr(evecs), _ptr(evals), _stream(dev))
+        _lib.check(st, "pcd_local_frames")
+    _launch_count += 1
+    return normal, evecs, evals
+
+
+class _Kappa(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pc, normal, nidx, idx, skip_first):
+        global _launch_count
+        lib = _lib.load()
+        B, N, _ = pc.shape
+        dev = pc.device
+        with _on(dev):
+            kappa = torch.empty((B, N), dtype=torch.float32, device=dev)
+            st = lib.pcd_kappa_forward(*_cloud_args(pc), *_cloud_args(normal), _ptr(nidx), idx.data_ptr(), B, N, idx.shape[2],
+                                       int(skip_first), kappa.data_ptr(), _stream(dev))
+            _lib.check(st, "pcd_kappa_forward")
+        _launch_count += 1
+        ctx.save_for_backward(pc, normal, idx)
+        ctx.nidx, ctx.skip_first = nidx, skip_first
+        return kappa
+
+    @staticmethod
+    def backward(ctx, g):
+        global _launch_count
+        if g is None or not ctx.needs_input_grad[0]:
+            return None, None, None, None, None
+        pc, normal, idx = ctx.saved_tensors
+        lib = _lib.load()
+        B, N, _ = pc.shape
+        dev = pc.device
+        with _on(dev):
+            grad = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
+            g = g.contiguous()
+            st = lib.pcd_kappa_backward(*_cloud_args(pc), *_cloud_args(normal), _ptr(ctx.nidx), idx.data_ptr(), B, N, idx.shape[2],
+                                        int(ctx.skip_first), g.data_ptr(), grad.data_ptr(), _stream(dev))
+            _lib.check(st, "pcd_kappa_backward")
+        _launch_count += 2
+        return grad, None, None, None, None
+
+
+def kappa(pc, normal, idx, nidx=None, skip_first=True):
+    """mean_j |<unit(q_j - p_i), n>| over the k-NN patch (pcd_kappa_forward; loss_utils.py:60-90, :116-125).
+    pc [B,N,3] (any strides, differentiable), normal [B,N,3] (any strides, constant), idx [B,N,K1] self-kNN of pc,
+    nidx [B,N] optional: take the normal of point nidx[b,i] instead of i (the adv->ori neighbour) -> [B,N]."""
+    _check_cloud(pc, "pc"); _check_cloud(normal, "normal")
+    if pc.shape != normal.shape:
+        raise ValueError("pc and normal must have the same shape")
+    dev = pc.device
+    idx32 = _idx32(idx, dev)
+    if idx32.dim() != 3 or idx32.shape[:2] != pc.shape[:2]:
+        raise ValueError(f"idx must be [B, N, K], got {tuple(idx32.shape)}")
+    n32 = None if nidx is None else _idx32(nidx.reshape(pc.shape[0], pc.shape[1]), dev)
+    return _Kappa.apply(pc, normal.detach(), n32, idx32, bool(skip_first))
+
+
+def graph_laplacian(pc, idx):
+    """Dense L = D - A of the symmetrised k-NN graph with Gaussian weights (pcd_graph_laplacian;
+    attack/AOF/TAOF_attack.py:31-52 up to the eigensolver).  pc [B,N,3] (any strides), idx [B,N,K] -> [B,N,N]."""
+    global _launch_count
+    _check_cloud(pc, "pc")
+    lib = _lib.load()
+    B, N, _ = pc.shape
+    dev = pc.device
+    idx32 = _idx32(idx, dev)
+    if idx32.dim() != 3 or idx32.shape[:2] != (B, N):
+        raise ValueError(f"idx must be [B, N, K], got {tuple(idx32.shape)}")
+    with _on(dev):
+        L = torch.empty((B, N, N), dtype=torch.float32, device=dev)
+        x = pc.detach()
+        st = lib.pcd_graph_laplacian(*_cloud_args(x), idx32.data_ptr(), B, N, idx32.shape[2], L.data_ptr(), _stream(dev))
+        _lib.check(st, "pcd_graph_laplacian")
+    _launch_count += 3
+    return L
 
 
 def fp32_peak_flops(iters=2048):

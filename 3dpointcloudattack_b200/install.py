@@ -11,7 +11,7 @@ patched.  Modules that cannot be imported (missing open3d etc.) are skipped and 
 import importlib
 
 from . import (curvenet_util, dgcnn, dis_utils_torch, dist_utils, distance, knn_utils, loss_utils,
-               pointnet2_utils, set_distance)
+               pointnet2_utils, set_distance, taof, utility)
 
 # reference module -> (our module, names)
 PATCHES = {
@@ -26,13 +26,14 @@ PATCHES = {
     "attack.GeoA3.knn_utils": (knn_utils, ["knn_points", "knn_gather"]),
     "attack.GeoA3.loss_utils": (loss_utils, ["knn_points", "knn_gather", "chamfer_loss", "pseudo_chamfer_loss",
                                             "hausdorff_loss", "_get_kappa_ori", "_get_kappa_adv", "curvature_loss",
-                                            "kNN_smoothing_loss"]),
+                                            "kNN_smoothing_loss", "displacement_loss", "corresponding_normal_loss",
+                                            "repulsion_loss", "distance_kmean_loss"]),
     "attack.GeoA3.GeoA3_attack": (knn_utils, ["knn_points", "knn_gather"]),
-    "attack.GeoA3.utility": (knn_utils, ["knn_points", "knn_gather"]),
+    "attack.GeoA3.utility": (utility, ["estimate_normal", "estimate_perpendicular", "estimate_normal_via_ori_normal"]),
     "model.dgcnn": (dgcnn, ["knn", "get_graph_feature"]),
     "pointnet.model": (dgcnn, ["knn", "get_graph_feature"]),
-    "attack.AOF.TAOF_attack": (dgcnn, ["knn"]),            # same formulation as dgcnn.knn (TAOF_attack.py:13-28)
-    "attack.AOF.Eval_AOF": (dgcnn, ["knn"]),
+    "attack.AOF.TAOF_attack": (taof, ["knn", "get_Laplace_from_pc"]),   # knn = dgcnn.knn's formulation (TAOF_attack.py:13-28)
+    "attack.AOF.Eval_AOF": (taof, ["knn", "get_Laplace_from_pc"]),
     "model.curvenet_util": (curvenet_util, ["knn", "normal_knn", "farthest_point_sample"]),
     "model.pointnet2_utils": (pointnet2_utils, ["query_ball_point", "farthest_point_sample"]),
     "pointnet.pointnet2_utils": (pointnet2_utils, ["query_ball_point", "farthest_point_sample"]),
@@ -61,6 +62,12 @@ def install(modules=None, strict=False):
         if name == "model.curvenet_util":
             ref.query_ball_point = pointnet2_utils.query_ball_point          # copy at curvenet_util.py:93-113
             ref.LPFA.group_feature = curvenet_util.group_feature             # method :206-236
+        if name in ("attack.GeoA3.utility", "attack.GeoA3.GeoA3_attack"):
+            ref.knn_points, ref.knn_gather = knn_utils.knn_points, knn_utils.knn_gather
+        if name == "attack.GeoA3.GeoA3_attack":
+            for n in ("estimate_normal", "estimate_perpendicular", "estimate_normal_via_ori_normal"):
+                if hasattr(ref, n):
+                    setattr(ref, n, getattr(utility, n))
         if name.endswith("dist_utils") and hasattr(ref, "chamfer"):
             ref.chamfer, ref.hausdorff = distance.chamfer, distance.hausdorff
         report[name] = "patched"

@@ -227,6 +227,45 @@ int pcd_fps(const float *xyz, int64_t sb, int64_t sp, int64_t sc, int B, int N, 
             const int32_t *start, int32_t *out, void *stream);
 
 /* ------------------------------------------------------------------------------------
+ * Local geometry on a k-NN graph (the consumers of the k-NN select in GeoA3 / AOF), each ONE pass
+ * over the index tensor -- the [B,N,K,3] neighbour gather of the reference never reaches HBM.
+ * idx [B,N,K1] int32 is the output of pcd_knn_forward on the cloud itself; skip_first != 0 drops
+ * column 0 (the point itself), as the reference's `[..., 1:]` slices do.
+ *
+ * pcd_local_frames   attack/GeoA3/utility.py:43-92 (estimate_normal) and :119-152
+ *   (estimate_perpendicular): covariance of the k = K1 - skip neighbours formed in fp32 exactly as the
+ *   reference forms it (mean, centring, bmm, 1/(k-1)), eigen-frame by a cyclic Jacobi iteration in
+ *   fp64 (the reference's torch.symeig no longer exists).  Outputs, each optional (NULL):
+ *     normal [B,N,3] via strides: eigenvector of the smallest eigenvalue times
+ *            -sign(<n, sum of the centred neighbours>) (utility.py:67-69; that sum is rounding noise
+ *            around zero, so the sign is as arbitrary as the reference's -- every consumer is sign-free)
+ *     evecs [B,N,3,3] contiguous: rows = eigenvectors by ascending eigenvalue; evals [B,N,3].
+ * pcd_kappa_forward / _backward   attack/GeoA3/loss_utils.py:60-70 (_get_kappa_ori), :72-90
+ *   (_get_kappa_adv), :116-125 (corresponding_normal_loss):
+ *     kappa[b,i] = mean_j |< (q_j - p_i) / max(|q_j - p_i|, 1e-12), n >|,  n = normal[b, nidx ? nidx[b,i] : i]
+ *   (nidx = the adv->ori nearest-neighbour index of _get_kappa_adv, NULL for the point's own normal).
+ *   The backward writes grad_pc [B,N,3] contiguous in full (own term + scatter through idx); the
+ *   normals are constants, as in the reference (gathered from the detached ori normals).
+ * pcd_graph_laplacian   attack/AOF/TAOF_attack.py:31-52 (get_Laplace_from_pc) up to the eigensolver:
+ *   L [B,N,N] = D - A with A_ij = exp(-((dx^2 + dy^2) + dz^2)) on the symmetrised k-NN graph (idx [B,N,K],
+ *   self column included).  Dense by design: the reference hands it to a dense eigendecomposition.
+ * ---------------------------------------------------------------------------------- */
+int pcd_local_frames(const float *pc, int64_t sb, int64_t sp, int64_t sc, const int32_t *idx,
+                     int B, int N, int K1, int skip_first,
+                     float *normal, int64_t n_sb, int64_t n_sp, int64_t n_sc,
+                     float *evecs, float *evals, void *stream);
+int pcd_kappa_forward(const float *pc, int64_t sb, int64_t sp, int64_t sc,
+                      const float *normal, int64_t n_sb, int64_t n_sp, int64_t n_sc,
+                      const int32_t *nidx, const int32_t *idx, int B, int N, int K1, int skip_first,
+                      float *kappa, void *stream);
+int pcd_kappa_backward(const float *pc, int64_t sb, int64_t sp, int64_t sc,
+                       const float *normal, int64_t n_sb, int64_t n_sp, int64_t n_sc,
+                       const int32_t *nidx, const int32_t *idx, int B, int N, int K1, int skip_first,
+                       const float *g_kappa, float *grad_pc, void *stream);
+int pcd_graph_laplacian(const float *pc, int64_t sb, int64_t sp, int64_t sc, const int32_t *idx,
+                        int B, int N, int K, float *L, void *stream);
+
+/* ------------------------------------------------------------------------------------
  * Measurement helper (bench.py): launches ONE FFMA-only probe kernel on `stream` (variant 0 =
  * scalar FFMA, 1 = packed FFMA2) and stores the number of FLOPs that launch performs in
  * *flop_count (HOST pointer).  The caller times it with its own CUDA events: achieved FLOP/s =

@@ -240,9 +240,125 @@ def feature_knn():
     save("a6_knn_graph_features", **out)
 
 
+def local_geometry():
+    """f-4: attack/GeoA3/utility.py estimate_normal, the brute-force k-NN losses of
+    attack/GeoA3/loss_utils.py:107-141 and attack/AOF/TAOF_attack.py get_Laplace_from_pc, run UNMODIFIED.
+    Environment work-around (no arithmetic of the reference is touched): `torch.symeig` was removed from torch;
+    it is provided as the shim its deprecation note prescribes, torch.linalg.eigh(A, UPLO='U'), and the shim
+    records the matrices it is handed so that the Laplacian the reference assembles can be stored."""
+    seen = []
+
+    def symeig(A, eigenvectors=False, upper=True):
+        seen.append(A.detach().clone())
+        e, v = torch.linalg.eigh(A, UPLO="U" if upper else "L")
+        return e, v
+
+    torch.symeig = symeig
+    from attack.GeoA3 import utility as U
+    from attack.GeoA3 import loss_utils as LU
+    from attack.AOF import TAOF_attack as TA
+    rs = np.random.RandomState(20261021)
+    ori = np.stack([face_fixture(512, 5), face_fixture(512, 6)])
+    adv = (ori + 0.01 * rs.randn(*ori.shape)).astype(np.float32)
+    ori_cf = np.ascontiguousarray(ori.transpose(0, 2, 1)); adv_cf = np.ascontiguousarray(adv.transpose(0, 2, 1))
+    out = {"ori": ori_cf, "adv": adv_cf}
+    for k in (3, 8, 16):
+        seen.clear()
+        out[f"normal_k{k}"] = n(U.estimate_normal(t(adv_cf), k))
+        out[f"cov_k{k}"] = torch.stack(seen).numpy()                     # [b, n, 3, 3] as the reference formed it
+    nrm = out["normal_k8"]
+    gN = rs.randn(2, 512).astype(np.float32)
+    a_ = t(adv_cf, True)
+    v = LU.displacement_loss(a_, t(ori_cf), k=16); (v * t(gN)).sum().backward()
+    out["displacement_loss"] = n(v); out["displacement_loss_g"] = n(a_.grad)
+    a_ = t(adv_cf, True)
+    v = LU.corresponding_normal_loss(a_, t(nrm), k=2); (v * t(gN)).sum().backward()
+    out["corresponding_normal_loss"] = n(v); out["corresponding_normal_loss_g"] = n(a_.grad)
+    a_ = t(adv_cf, True)
+    v = LU.repulsion_loss(a_, k=4, h=0.03); (v * t(gN)).sum().backward()
+    out["repulsion_loss"] = n(v); out["repulsion_loss_g"] = n(a_.grad)
+    a_ = t(adv_cf, True)
+    v = LU.distance_kmean_loss(a_, 8); (v * t(gN)).sum().backward()
+    out["distance_kmean_loss"] = n(v); out["distance_kmean_loss_g"] = n(a_.grad)
+    # kappa with its gradient (the a4 fixture stores the values; here k = 16 with a gradient w.r.t. the cloud)
+    a_ = t(adv_cf, True)
+    kap, _ = LU._get_kappa_adv(a_, t(ori_cf), t(nrm), 16); (kap * t(gN)).sum().backward()
+    out["kappa_adv_k16"] = n(kap); out["kappa_adv_k16_g"] = n(a_.grad); out["gN"] = gN
+    # AOF Laplacian on 256 points (dense [B,N,N]); k = 30 is hard-coded in the reference
+    seen.clear()
+    small = np.ascontiguousarray(adv_cf[:, :, :256])
+    e, vv = TA.get_Laplace_from_pc(t(small))
+    out["lap_pc"] = small; out["lap_L"] = seen[0].numpy(); out["lap_e"] = n(e)
+    save("f4_local_geometry", **out)
+
+
+def geoa3_loop():
+    """L4: the reference's own GeoA3 attack (attack/GeoA3/GeoA3_attack.py:185-473), unmodified, on CPU
+    at B = 1 against tests/tiny_victim.TinyVictim, in two configurations (plain, and projected + clipped offsets).
+    Environment work-arounds only: torch.symeig -> torch.linalg.eigh (see local_geometry), the module's bare
+    `from utility import ...` needs attack/GeoA3 on sys.path, and nn.init.normal_ is wrapped to RECORD the offset
+    draws the loop starts from (the values are passed through unchanged)."""
+    import argparse
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
+    sys.path.insert(0, os.path.join(REF, "attack", "GeoA3"))
+    import tiny_victim
+    torch.symeig = lambda A, eigenvectors=False, upper=True: torch.linalg.eigh(A, UPLO="U" if upper else "L")
+    from attack.GeoA3 import GeoA3_attack as GA
+    victim = tiny_victim.make(seed=3)
+    data = face_fixture(256, 7)[None]                                   # [1,256,3]
+    with torch.no_grad():
+        label = victim(t(data).transpose(1, 2))[0].argmax(1)
+    out = dict(tiny_victim.state_to_npz(victim), data=data, label=n(label))
+    draws = []
+    real_normal_ = torch.nn.init.normal_
+
+    def recording_normal_(tensor, mean=0., std=1.):
+        r = real_normal_(tensor, mean=mean, std=std)
+        draws.append(n(r).copy())
+        return r
+
+    base = dict(arch="tiny", classes=7, attack_label="Untarget", attack_method="untarget", initial_const=10., lr=0.01,
+                optim="adam", binary_max_steps=3, iter_max_steps=15, metric="Loss", cls_loss_type="Margin", confidence=0.,
+                dis_loss_type="CD", is_cd_single_side=False, dis_loss_weight=1.0, hd_loss_weight=0.1, curv_loss_weight=1.0,
+                curv_loss_knn=16, uniform_loss_weight=0.0, is_pre_jitter_input=False, calculate_project_jitter_noise_iter=50,
+                jitter_k=16, jitter_sigma=0.01, jitter_clip=0.05, is_save_normal=False, is_partial_var=False, knn_range=3,
+                is_subsample_opt=False, npoint=256, eval_num=1, is_use_lr_scheduler=False, is_pro_grad=False,
+                is_real_offset=False, cc_linf=0., is_debug=False, binary_step=3, num_iter=15, output_path="/tmp")
+    class _Transposed(torch.nn.Module):
+        """the transfer checks at the end of geoA3_attack (:407-471, not on the path) feed [b,n,3] clouds"""
+
+        def __init__(self, m):
+            super().__init__()
+            self.m = m
+
+        def forward(self, x):
+            return self.m(x.transpose(2, 1))
+
+    vt = _Transposed(victim)
+    GA.nn.init.normal_ = recording_normal_
+    try:
+        for tag, extra in (("plain", {}), ("proj_clip", dict(is_pro_grad=True, cc_linf=0.02, is_use_lr_scheduler=True))):
+            draws.clear()
+            torch.manual_seed(21)
+            cfg = argparse.Namespace(**dict(base, **extra))
+            best_attack, target, ok, best_step, all_loss = GA.geoA3_attack(victim, vt, vt, vt, vt, vt,
+                                                                           t(data), label.clone(), cfg, 0, 1)
+            out.update({tag + "_best_attack": n(best_attack), tag + "_success": np.asarray(ok), tag + "_best_step": np.asarray(best_step),
+                        tag + "_offsets": np.stack(draws), tag + "_loss_n": np.asarray(all_loss, np.float32)})
+    finally:
+        GA.nn.init.normal_ = real_normal_
+    save("l4_geoa3_loop", **out)
+
+
 def main():
     torch.set_num_threads(1)
     _prepare_reference()
+    if "--geoa3" in sys.argv:          # the reference's GeoA3 loop at B = 1 (added in round 2)
+        geoa3_loop()
+        return
+    if "--geometry" in sys.argv:       # f-4 (added in round 2)
+        local_geometry()
+        return
     if "--features" in sys.argv:       # a6 for C = 64 / 128 (added in round 2)
         feature_knn()
         return

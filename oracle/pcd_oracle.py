@@ -407,3 +407,98 @@ def three_nn_interpolate(xyz1, xyz2, points2):
     recip = np.float32(1.0) / (d + np.float32(1e-8))
     w = recip / recip.sum(2, keepdims=True, dtype=np.float32)
     return (index_points(points2, i.astype(np.int64)) * w[..., None]).sum(2, dtype=np.float32), d, i
+
+
+# ------------------------ f-4: attack/GeoA3/utility.py:43-92, loss_utils.py:60-141, AOF TAOF_attack.py:31-52
+def self_knn_idx(pc_cf, K):
+    """Self k-NN of a [b,3,n] cloud in knn_points arithmetic (exact for p1 is p2) -> idx [b,n,K] int64."""
+    pm = _cf_to_pm(pc_cf)
+    _, i = knn_points(pm, pm, K)
+    return i
+
+
+def patch_covariance(pc_pm, idx, skip_first=True):
+    """utility.py:56-62: fp32 covariance of each point's k neighbours, formed as the reference forms it --
+    mean = sum / k, centred set, bmm (k ascending), times fp32(1/(k-1)).  Returns (cov [b,n,3,3] fp32,
+    nbr_sum [b,n,3] fp32 = sum of the centred neighbours, :68)."""
+    pc = _f32(pc_pm)
+    nb = idx[:, :, 1:] if skip_first else idx
+    B, N, k = nb.shape
+    pts = pc[np.arange(B)[:, None, None], nb]                       # [b,n,k,3]
+    s = np.zeros((B, N, 3), np.float32)
+    for j in range(k):
+        s = (s + pts[:, :, j]).astype(np.float32)
+    mean = (s / np.float32(k)).astype(np.float32)
+    c = (pts - mean[:, :, None, :]).astype(np.float32)
+    cov = np.zeros((B, N, 3, 3), np.float32)
+    nsum = np.zeros((B, N, 3), np.float32)
+    for j in range(k):
+        # fma(c_a, c_b, acc): evaluate in float64 and round once (the product of two fp32 is exact in fp64)
+        cov = (cov.astype(np.float64) + c[:, :, j, :, None].astype(np.float64) * c[:, :, j, None, :].astype(np.float64)).astype(np.float32)
+        nsum = (nsum + c[:, :, j]).astype(np.float32)
+    fact = np.float32(1.0) / np.float32(k - 1)
+    return (fact * cov).astype(np.float32), nsum
+
+
+def local_frames(pc_pm, idx, skip_first=True):
+    """Eigen-frame of patch_covariance in float64 (numpy eigh): (evals [b,n,3] ascending, evecs [b,n,3,3] with
+    ROWS = eigenvectors in that order, nbr_sum).  The normal of estimate_normal is +-evecs[..., 0, :]."""
+    cov, nsum = patch_covariance(pc_pm, idx, skip_first)
+    w, v = np.linalg.eigh(cov.astype(np.float64))
+    return w, np.swapaxes(v, -1, -2), nsum
+
+
+def kappa(pc_pm, normal_pm, idx, nidx=None, skip_first=True, dtype=np.float32):
+    """loss_utils.py:60-90: mean_j |<unit(q_j - p), n>|, unit(d) = d / max(|d|, 1e-12); n = normal[nidx or self].
+    dtype float32 restates the reference's op order; float64 is the closed form used to pin tolerances."""
+    pc = np.asarray(pc_pm, dtype); nrm = np.asarray(normal_pm, dtype)
+    nb = idx[:, :, 1:] if skip_first else idx
+    B, N, k = nb.shape
+    ar = np.arange(B)[:, None]
+    n_ = nrm[ar, nidx] if nidx is not None else nrm
+    q = pc[np.arange(B)[:, None, None], nb]
+    d = (q - pc[:, :, None, :]).astype(dtype)
+    r = np.sqrt(((d[..., 0] * d[..., 0]).astype(dtype) + (d[..., 1] * d[..., 1]).astype(dtype)).astype(dtype) + (d[..., 2] * d[..., 2]).astype(dtype)).astype(dtype)
+    u = (d / np.maximum(r, dtype(1e-12))[..., None]).astype(dtype)
+    dot = ((u[..., 0] * n_[:, :, None, 0]).astype(dtype) + (u[..., 1] * n_[:, :, None, 1]).astype(dtype)).astype(dtype) + (u[..., 2] * n_[:, :, None, 2]).astype(dtype)
+    a = np.abs(dot.astype(dtype))
+    acc = np.zeros((B, N), dtype)
+    for j in range(k):
+        acc = (acc + a[:, :, j]).astype(dtype)
+    return (acc / dtype(k)).astype(dtype)
+
+
+def kappa_grad64(pc_pm, normal_pm, idx, g, nidx=None, skip_first=True):
+    """float64 closed-form gradient of sum_{b,i} g[b,i] kappa[b,i] w.r.t. the cloud (normals constant)."""
+    pc = np.asarray(pc_pm, np.float64); nrm = np.asarray(normal_pm, np.float64); g = np.asarray(g, np.float64)
+    nb = idx[:, :, 1:] if skip_first else idx
+    B, N, k = nb.shape
+    n_ = nrm[np.arange(B)[:, None], nidx] if nidx is not None else nrm
+    q = pc[np.arange(B)[:, None, None], nb]
+    d = q - pc[:, :, None, :]
+    r = np.maximum(np.sqrt((d * d).sum(-1)), 1e-300)
+    u = d / r[..., None]
+    s = (u * n_[:, :, None, :]).sum(-1)
+    term = (np.sign(s) * g[:, :, None] / k)[..., None] * (n_[:, :, None, :] - s[..., None] * u) / r[..., None]     # d/d(d_ij)
+    grad = np.zeros_like(pc)
+    grad -= term.sum(2)
+    for b in range(B):
+        np.add.at(grad[b], nb[b].reshape(-1), term[b].reshape(-1, 3))
+    return grad
+
+
+def graph_laplacian(pc_pm, idx):
+    """attack/AOF/TAOF_attack.py:36-50: L = D - A, A_ij = exp(-((dx^2 + dy^2) + dz^2)) on the symmetrised k-NN graph."""
+    pc = _f32(pc_pm)
+    B, N, _ = pc.shape
+    L = np.zeros((B, N, N), np.float32)
+    for b in range(B):
+        d = (pc[b][:, None, :] - pc[b][None, :, :]).astype(np.float32)
+        d2 = ((d[..., 0] * d[..., 0]).astype(np.float32) + (d[..., 1] * d[..., 1]).astype(np.float32)).astype(np.float32) + (d[..., 2] * d[..., 2]).astype(np.float32)
+        A = np.exp(-d2.astype(np.float32)).astype(np.float32)
+        mask = np.zeros((N, N), bool)
+        mask[np.arange(N)[:, None], idx[b]] = True
+        mask |= mask.T
+        A = np.where(mask, A, np.float32(0))
+        L[b] = np.diag(A.sum(1, dtype=np.float64).astype(np.float32)) - A
+    return L

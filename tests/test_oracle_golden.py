@@ -218,3 +218,32 @@ def test_f_three_nn_interpolation():
     out, d, i = O.three_nn_interpolate(x1, x2, g["fp_feat"].transpose(0, 2, 1))
     assert d.min() > 1e-6                                           # well conditioned: no coincident pairs
     np.testing.assert_allclose(out.transpose(0, 2, 1), g["fp_out"], rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------ f-4: local geometry (round 2)
+def test_f4_local_geometry_oracle_vs_reference():
+    """oracle/make_golden.py --geometry ran the UNMODIFIED estimate_normal / kappa / brute-force losses / AOF
+    Laplacian (torch.symeig provided as torch.linalg.eigh, the environment shim its deprecation note prescribes)."""
+    g = load_golden("f4_local_geometry")
+    adv = g["adv"]; pm = O._cf_to_pm(adv)
+    for k in (3, 8, 16):
+        idx = O.self_knn_idx(adv, k + 1)
+        cov, _ = O.patch_covariance(pm, idx)
+        assert rel_inf(cov, g[f"cov_k{k}"]) < 3e-7                         # library bmm / mean order: rounding only
+        w, v, _ = O.local_frames(pm, idx)
+        nref = g[f"normal_k{k}"].transpose(0, 2, 1)
+        unit = np.linalg.norm(nref, axis=-1) > 0.5                          # the reference's sign(0) = 0 zeroes a few normals
+        assert unit.mean() > 0.95
+        cos = np.abs((v[:, :, 0, :] * nref).sum(-1))
+        assert cos[unit].min() > 1 - 1e-5                                   # sign-free comparison (see utility.py:67-69)
+    nrm = g["normal_k8"].transpose(0, 2, 1)
+    nidx = O.knn_points(pm, O._cf_to_pm(g["ori"]), 1)[1][:, :, 0]
+    idx = O.self_knn_idx(adv, 17)
+    kap = O.kappa(pm, nrm, idx, nidx=nidx)
+    np.testing.assert_allclose(kap, g["kappa_adv_k16"], rtol=0, atol=3e-7)
+    g64 = O.kappa_grad64(pm, nrm, idx, g["gN"], nidx=nidx)
+    assert rel_inf(g["kappa_adv_k16_g"].transpose(0, 2, 1), g64) < 1e-5      # reference fp32 autograd vs fp64 closed form
+    small = g["lap_pc"]
+    L = O.graph_laplacian(O._cf_to_pm(small), O.dgcnn_knn(small, 30))
+    np.testing.assert_allclose(L, g["lap_L"], rtol=0, atol=1e-5)
+    assert ((L != 0) == (g["lap_L"] != 0)).all()                            # identical sparsity: same symmetrised graph
