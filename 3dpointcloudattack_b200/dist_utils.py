@@ -66,15 +66,9 @@ class KNNDist(nn.Module):
 
     def forward(self, pc, weights=None, batch_avg=True):
         B, K = pc.shape[:2]
-        dists, _ = F.knn(pc, pc, self.k + 1, form=F.FORM_COL_ROW, norm=F.NORM_MULSUM)
-        value = dists[..., 1:]                                   # [B, K, k]
-        value = torch.mean(value, dim=-1)                        # [B, K]
-        with torch.no_grad():
-            mean = torch.mean(value, dim=-1)
-            std = torch.std(value, dim=-1)
-            threshold = mean + self.alpha * std
-            weight_mask = (value > threshold[:, None]).float().detach()
-        loss = torch.mean(value * weight_mask, dim=1)            # [B]
+        # k-NN select + ONE fused epilogue kernel (value, unbiased std, threshold, mask, masked mean) and ONE backward
+        # kernel through the indices, instead of nine torch launches and their autograd nodes (dist_utils.py:143-153)
+        loss, _, _, _ = F.knn_outlier_loss(pc, self.k, self.alpha, form=F.FORM_COL_ROW, norm=F.NORM_MULSUM)   # [B]
         loss = loss * _weights(weights, B, pc.device)
         if batch_avg:
             return loss.mean()

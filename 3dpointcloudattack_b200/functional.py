@@ -17,7 +17,7 @@ from ._lib import (EDGE_CENTER, EDGE_DIFF, EDGE_NEIGHBOR, FORM_COL_ROW, FORM_ROW
                    VALUE_SQRT_CLAMP, VALUE_SQUARED)
 
 __all__ = ["nn1", "NN1Result", "time_next_sweep", "clear_cache", "knn", "ball_query", "edge_feature", "farthest_point_sample", "fp32_peak_flops",
-           "local_frames", "kappa", "graph_laplacian",
+           "local_frames", "kappa", "graph_laplacian", "knn_outlier_loss",
            "EDGE_CENTER", "EDGE_NEIGHBOR", "EDGE_DIFF",
            "FORM_ROW_COL", "FORM_COL_ROW", "FORM_SUM_FIRST", "NORM_MULSUM", "NORM_FMA",
            "VALUE_SQUARED", "VALUE_SQRT_CLAMP"]
@@ -407,6 +407,64 @@ def farthest_point_sample(xyz, npoint, start=None):
         _lib.check(st, "pcd_fps")
     _launch_count += 1
     return out
+
+
+# ------------------------------------------------ k-NN outlier / smoothing loss with a fused epilogue
+class _KnnOutlierLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pc, k, alpha, form, norm, swap_norms):
+        global _launch_count
+        lib = _lib.load()
+        B, N, _ = pc.shape
+        dev = pc.device
+        K1 = k + 1
+        with _on(dev):
+            x = pc.detach()
+            dists = torch.empty((B, N, K1), dtype=torch.float32, device=dev)
+            idx = torch.empty((B, N, K1), dtype=torch.int32, device=dev)
+            ws_bytes = lib.pcd_knn_workspace_bytes(B, N, N, 3, K1)
+            ws = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=dev)
+            st = lib.pcd_knn_forward(*_cloud_args(x), *_cloud_args(x), B, N, N, 3, K1, form, norm, int(swap_norms),
+                                     dists.data_ptr(), idx.data_ptr(), ws.data_ptr(), ws_bytes, _stream(dev))
+            _lib.check(st, "pcd_knn_forward")
+            value = torch.empty((B, N), dtype=torch.float32, device=dev)
+            mask = torch.empty((B, N), dtype=torch.float32, device=dev)
+            loss = torch.empty((B,), dtype=torch.float32, device=dev)
+            thr = torch.empty((B,), dtype=torch.float32, device=dev)
+            st = lib.pcd_knn_outlier_forward(dists.data_ptr(), B, N, K1, 1, float(alpha), value.data_ptr(), mask.data_ptr(),
+                                             loss.data_ptr(), thr.data_ptr(), _stream(dev))
+            _lib.check(st, "pcd_knn_outlier_forward")
+        _launch_count += 3
+        ctx.save_for_backward(pc, idx, mask)
+        ctx.mark_non_differentiable(value, mask, thr)
+        return loss, value, mask, thr
+
+    @staticmethod
+    def backward(ctx, g_loss, _gv, _gm, _gt):
+        global _launch_count
+        if g_loss is None or not ctx.needs_input_grad[0]:
+            return (None,) * 6
+        pc, idx, mask = ctx.saved_tensors
+        lib = _lib.load()
+        B, N, _ = pc.shape
+        dev = pc.device
+        with _on(dev):
+            grad = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
+            st = lib.pcd_knn_outlier_backward(*_cloud_args(pc), idx.data_ptr(), mask.data_ptr(), g_loss.data_ptr(), g_loss.stride(0),
+                                              B, N, idx.shape[2], 1, grad.data_ptr(), _stream(dev))
+            _lib.check(st, "pcd_knn_outlier_backward")
+        _launch_count += 2
+        return grad, None, None, None, None, None
+
+
+def knn_outlier_loss(pc, k, alpha, form=FORM_COL_ROW, norm=NORM_MULSUM, swap_norms=False):
+    """Self k-NN select + fused outlier-loss epilogue (pcd_knn_outlier_forward in include/pcdist.h):
+    pc [B,N,3] (any strides) -> (loss [B] differentiable, value [B,N], mask [B,N], threshold [B])."""
+    _check_cloud(pc, "pc")
+    k = int(k)
+    if not 1 <= k + 1 <= min(pc.shape[1], _lib.KNN_MAX_K):
+        raise ValueError(f"k={k} out of range for N={pc.shape[1]}")
+    return _KnnOutlierLoss.apply(pc, k, float(alpha), form, norm, bool(swap_norms))
 
 
 # ------------------------------------------------ local geometry on a k-NN graph (SURVEY 8f row 4)

@@ -117,11 +117,8 @@ def distance_kmean_loss(pc, k):
 
 
 def kNN_smoothing_loss(adv_pc, k, threshold_coef=1.05):
-    """loss_utils.py:143-157 (the threshold is differentiated through, unlike KNNDist)."""
-    inter_KNN = knn_points(adv_pc.permute(0, 2, 1), adv_pc.permute(0, 2, 1), K=k + 1)
-    knn_dis = inter_KNN.dists[:, :, 1:].contiguous().mean(-1)
-    knn_dis_mean = knn_dis.mean(-1)
-    knn_dis_std = knn_dis.std(-1)
-    threshold = knn_dis_mean + threshold_coef * knn_dis_std
-    condition = torch.gt(knn_dis, threshold.unsqueeze(1)).float()
-    return (knn_dis * condition).mean(1)
+    """loss_utils.py:143-157.  The reference computes the threshold inside the autograd graph, but the comparison that
+    consumes it is a .float() of a boolean, so no gradient flows through it: same fused epilogue as KNNDist."""
+    loss, _, _, _ = F.knn_outlier_loss(adv_pc.permute(0, 2, 1), k, threshold_coef, form=F.FORM_COL_ROW, norm=F.NORM_MULSUM,
+                                       swap_norms=True)
+    return loss

@@ -227,6 +227,25 @@ int pcd_fps(const float *xyz, int64_t sb, int64_t sp, int64_t sc, int B, int N, 
             const int32_t *start, int32_t *out, void *stream);
 
 /* ------------------------------------------------------------------------------------
+ * Fused epilogue of the k-NN outlier / smoothing loss.  Replaces the nine-launch torch chain of
+ *   attack/CW/CW_utils/dist_utils.py:143-153 (KNNDist; copies in Gen3DAdv, SIadv)
+ *   attack/GeoA3/loss_utils.py:148-157 (kNN_smoothing_loss)
+ * on the dists [B,N,K1] / idx [B,N,K1] of pcd_knn_forward(cloud, cloud, K1 = k + 1):
+ *   value[b,i] = mean_j dists[b,i,j] (column 0 dropped when skip_first), threshold[b] = mean_i value +
+ *   alpha * std_i value (unbiased), mask = value > threshold, loss[b] = mean_i value * mask.
+ * forward: one kernel, one CTA per sample, fixed reduction order; outputs value, mask [B,N] (0/1
+ *   floats), loss [B], threshold [B] (optional).
+ * backward: d(sum_b g_loss[b] loss[b]) / d cloud through idx (the comparison is non-differentiable in
+ *   both reference variants); g_loss read with element stride g_stride (0 = one broadcast value);
+ *   grad_pc [B,N,3] contiguous, written in full; one memset + one kernel, only masked points work.
+ * ---------------------------------------------------------------------------------- */
+int pcd_knn_outlier_forward(const float *dists, int B, int N, int K1, int skip_first, float alpha,
+                            float *value, float *mask, float *loss, float *threshold, void *stream);
+int pcd_knn_outlier_backward(const float *pc, int64_t sb, int64_t sp, int64_t sc, const int32_t *idx,
+                             const float *mask, const float *g_loss, int64_t g_stride,
+                             int B, int N, int K1, int skip_first, float *grad_pc, void *stream);
+
+/* ------------------------------------------------------------------------------------
  * Local geometry on a k-NN graph (the consumers of the k-NN select in GeoA3 / AOF), each ONE pass
  * over the index tensor -- the [B,N,K,3] neighbour gather of the reference never reaches HBM.
  * idx [B,N,K1] int32 is the output of pcd_knn_forward on the cloud itself; skip_first != 0 drops

@@ -854,11 +854,16 @@ def test_l4_geoa3_loop_batch_safe_and_graph():
     .item() and one shared output_label, i.e. is B = 1 only); the CUDA-graph loop reproduces the eager one."""
     g = load_golden("l4_geoa3_loop")
     _, b1, ok1, l1, s1 = _geoa3(g, "plain")
-    _, b3, ok3, l3, s3 = _geoa3(g, "plain", reps=3)
+    # global_batch=1: the reference's loss is a batch MEAN, so B = 3 scales every gradient by 1/3 and Adam's eps = 1e-8 then
+    # perturbs the steps; with the B = 1 normalisation the three copies must reproduce the single run
+    _, b3, ok3, l3, s3 = _geoa3(g, "plain", reps=3, global_batch=1)
     for k in range(3):
         assert (np.abs(b3[k] - b1[0]) < 1e-5).mean() > 0.99 and ok3[k] == ok1[0] and s3[k] == s1[0]
     _, bg, okg, lg, sg = _geoa3(g, "plain", use_graph=True)
-    assert (np.abs(bg - b1) < 1e-5).mean() > 0.99 and okg.tolist() == ok1.tolist()
+    # capturable Adam evaluates its bias corrections with fp32 tensor ops (eager: Python doubles): updates differ by 1e-7
+    # relative per step, 45 steps
+    dg = np.abs(bg - b1)
+    assert (dg < 1e-4).mean() > 0.99 and np.median(dg) < 1e-5 and okg.tolist() == ok1.tolist(), (float(dg.max()), float(np.median(dg)))
 
 
 def test_l4_loops_are_batch_safe():
