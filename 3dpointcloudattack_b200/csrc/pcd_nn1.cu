@@ -1245,6 +1245,17 @@ extern "C" size_t pcd_nn1_workspace_bytes(int B, int N, int M) {
     return nn1_layout(B, N, M).total;
 }
 
+extern "C" int pcd_nn1_query_tiling(int B, int N, int M, int *rows_per_lane, int *col_tile) {
+    if (B <= 0 || N <= 0 || M <= 0 || !rows_per_lane || !col_tile) {
+        set_error("pcd_nn1_query_tiling: bad argument");
+        return PCD_ERR_ARG;
+    }
+    const int sms = num_sms();
+    if (sms <= 0) return cuda_fail(cudaGetLastError(), "no CUDA device");
+    choose_tiling(B, N, M, sms, 0, 0, rows_per_lane, col_tile);
+    return PCD_OK;
+}
+
 extern "C" int pcd_nn1_forward(const float *rows, int64_t r_sb, int64_t r_sp, int64_t r_sc,
                                const float *cols, int64_t c_sb, int64_t c_sp, int64_t c_sc,
                                int B, int N, int M, int form, int norm_kind, int swap_norms, int transform,

@@ -41,7 +41,21 @@ UNIT = "Gpair/s"
 B_PER_GPU, NPTS, SIGMA = 32, 4096, 0.01
 FLOP_PER_PAIR = 8.0
 BWD_BYTES_PER_POINT_DIR = 68.0
-SWEEP_DRAM_BYTES_PER_LAUNCH = 6324992   # ncu capture of nn1_sweep_kernel<2,16> at B=32 N=M=4096 (read 6.32 MB, write 0)
+NCU_COUNTERS = os.path.join(ROOT, "profiles", "r2_ncu_counters.json")   # written by tools/ncu_counters.py from an ncu --set full capture
+
+
+def sweep_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one nn1_sweep_kernel launch at the headline workload, read from the
+    committed counter file by kernel name (None if the file or the kernel is missing)."""
+    try:
+        with open(NCU_COUNTERS) as f:
+            d = json.load(f)
+        for name, c in d["kernels"].items():
+            if "nn1_sweep_kernel" in name:
+                return int(c["dram__bytes_read.sum"] + c["dram__bytes_write.sum"]), name, d.get("source", "")
+    except Exception:
+        pass
+    return None, None, None
 
 
 def load_peaks():
@@ -394,43 +408,30 @@ def run_ours(args):
     h2d = adv_h.numel() * 4 + ori_h.numel() * 4
     d2h = loss_h.numel() * 4 + grad_h.numel() * 4
 
-    # ---------------- secondary: the per-GPU shard of BASELINE configs[4] (B=512 N=M=16384 over 8 GPUs = 64 per GPU) ----
-    def large_cloud(Bl=64, Nl=16384, reps=10):
-        synth = importlib.import_module("3dpointcloudattack_b200.synth")
-        o_l = synth.face_clouds(4, Nl, seed=4321).to(dev).repeat(Bl // 4, 1, 1).contiguous()
-        a_l = (o_l + SIGMA * torch.randn(o_l.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(7))).requires_grad_(True)
-        ts, sw, bw = [], [], []
-        for k in range(reps + 1):
-            a_l.grad = None
-            s0, s1, e0, e1 = ev(), ev(), ev(), ev()
-            for x in (s0, s1):
-                x.record()                                 # materialise the cudaEvent handles
-            flush.zero_()
-            F.time_next_sweep(s0, s1)
-            e0.record()
-            step(a_l, o_l)
-            e1.record()
-            torch.cuda.synchronize()
-            if k:
-                ts.append(e0.elapsed_time(e1)); sw.append(s0.elapsed_time(s1))
-        bw = [time_backward_kernel(a_l.detach(), o_l, 5)]
-        pairs = float(Bl) * Nl * Nl
-        med = lambda v: sorted(v)[len(v) // 2]
-        t, w, bk = med(ts), med(sw), med(bw)
-        bwd_gbs = 2.0 * Bl * Nl * BWD_BYTES_PER_POINT_DIR / (bk * 1e-3) / 1e9
-        return {"workload": f"chamfer+hausdorff fwd+bwd B={Bl}/GPU N=M={Nl} (per-GPU shard of BASELINE configs[4])",
-                "ms_per_step": t, "value": pairs / (t * 1e-3) / 1e9, "unit": UNIT,
-                "sweep_ms": w, "sweep_tflops": FLOP_PER_PAIR * pairs / (w * 1e-3) / 1e12,
-                "backward_ms": bk, "backward_gbs": bwd_gbs, "backward_hbm_frac": bwd_gbs / load_peaks()[0]}
-
-    large = large_cloud()
-
     # ---------------- secondary metric: CW attack iterations/s (device-resident loop, section 8f-1) ----
     cw = run_cw(pcd, dev, rank, world, B)
 
+    # ---------------- the other BASELINE configs (tools/bench_configs.py) ---------------------------
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_configs as BC
+    fp32_peak = F.fp32_peak_flops(2048)
+    gpu_ref = BC.gpu_reference(pcd, adv, ori, flush) if rank == 0 else None
+    c2 = BC.config2(pcd, dev, rank, with_reference=(rank == 0 and world == 1))
+    c3 = BC.config3(pcd, dev, rank, world, with_reference=(rank == 0 and world == 1))
+    c4 = BC.config4(pcd, dev, rank, world, flush, fp32_peak, load_peaks()[0])
+    # the backward kernel where it is large enough for the HBM roofline: the 8-GPU shard of configs[4] (B=64, N=16384, 143 MB)
+    synth = importlib.import_module("3dpointcloudattack_b200.synth")
+    o_l = synth.face_clouds(4, 16384, seed=4321).to(dev).repeat(16, 1, 1).contiguous()
+    a_l = o_l + SIGMA * torch.randn(o_l.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(7))
+    bwl_ms = time_backward_kernel(a_l, o_l, 7)
+    bwl_gbs = 2.0 * 64 * 16384 * BWD_BYTES_PER_POINT_DIR / (bwl_ms * 1e-3) / 1e9
+    backward_large = {"workload": "nn1_bwd_kernel<2> at B=64 N=M=16384 (143 MB algorithmic)", "ms": bwl_ms, "achieved": bwl_gbs,
+                      "unit": "GB/s", "peak": load_peaks()[0], "frac": bwl_gbs / load_peaks()[0]}
+    del o_l, a_l
+
     # ---------------- max over ranks, final all-gather (the only collective of the path) ---------
-    cw_t = torch.tensor([cw["eager"], cw["graph"]], device=dev, dtype=torch.float64)
-    t = torch.tensor([total_ms, e2e_total_ms], device=dev, dtype=torch.float64)
+    cw_t = torch.tensor([cw["eager"], cw["graph"], c2["iters_per_s_eager"]], device=dev, dtype=torch.float64)
+    t = torch.tensor([total_ms, e2e_total_ms, c3["ms_per_iteration"], c4["ms_per_step"], c4["sweep_ms"]], device=dev, dtype=torch.float64)
     gather_ms = None
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -444,6 +445,13 @@ def run_ours(args):
         g1.record(); torch.cuda.synchronize()
         gather_ms = g0.elapsed_time(g1)
     total_ms, e2e_total_ms = float(t[0]), float(t[1])
+    # strong-scaling configs: the slowest rank decides (MAX over ranks), throughput is the GLOBAL batch over that time
+    c3["ms_per_iteration"] = float(t[2]); c3["iters_per_s"] = 1e3 / float(t[2])
+    c3["sample_iters_per_s"] = c3["global_batch"] * 1e3 / float(t[2])
+    c4["ms_per_step"] = float(t[3]); c4["sweep_ms_slowest_rank"] = float(t[4])
+    c4["value"] = c4["pairs_per_step_global"] / (float(t[3]) * 1e-3) / 1e9; c4["unit"] = UNIT
+    c2["iters_per_s_eager"] = float(cw_t[2])
+    c2["sample_iters_per_s"] = float(cw_t[2]) * 64 * world
 
     pairs_step_rank = float(B) * NPTS * NPTS
     value = pairs_step_rank * world * args.steps / (total_ms * 1e-3) / 1e9
@@ -451,7 +459,6 @@ def run_ours(args):
 
     if rank == 0:
         hbm_gbs, hbm_src = load_peaks()
-        fp32_peak = F.fp32_peak_flops(2048)
         sweep_avg_ms = sum(sweep_ms) / len(sweep_ms)
         achieved = FLOP_PER_PAIR * pairs_step_rank / (sweep_avg_ms * 1e-3) / 1e12
         bwd_avg_ms = bwdk_med_ms                              # nn1_bwd_kernel<2> alone (gradient buffer pre-zeroed by the forward)
@@ -486,9 +493,9 @@ def run_ours(args):
             "gpu_launches": launches,
             "clocks": sampler.summary(),
             "roofline": {"bound": "fp32", "kernel": "nn1_sweep_kernel", "achieved": achieved, "peak": fp32_peak / 1e12,
-                         "unit": "TFLOP/s", "frac": achieved / (fp32_peak / 1e12), "traffic": SWEEP_DRAM_BYTES_PER_LAUNCH,
-                         "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one launch at this "
-                                           "workload (profiles/r1_v6_ncu_summary.txt); algorithmic input bytes = 6.29 MB",
+                         "unit": "TFLOP/s", "frac": achieved / (fp32_peak / 1e12), "traffic": sweep_traffic()[0],
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of %s in profiles/r2_ncu_counters.json "
+                                           "(%s); algorithmic input bytes = 3.15 MB (both clouds, streamed raw)" % sweep_traffic()[1:],
                          "peak_source": "FFMA/FFMA2 micro-kernel measured in this run (pcd_fp32_probe_launch between CUDA events)",
                          "ms_per_launch": sweep_avg_ms, "flop_per_pair": FLOP_PER_PAIR},
             "roofline_backward": {"bound": "hbm", "kernel": "nn1_bwd_kernel<2>", "achieved": bwd_bytes / (bwd_avg_ms * 1e-3) / 1e9,
@@ -497,9 +504,13 @@ def run_ours(args):
                                   "loss_backward_ms_with_autograd": bwd_autograd_ms,
                                   "note": "algorithmic 68 B per (point, direction) = 17.8 MB: too small for the HBM roofline (launch "
                                           "latency); one pcd_nn1_backward launch between two events, L2 flushed, median; "
-                                          "large_cloud.backward_* is the same kernel at 143 MB"},
+                                          "backward_large is the same kernel at 143 MB"},
+            "backward_large": backward_large,
             "cpu_baseline": cpu,
-            "large_cloud": dict(large, sweep_frac=large["sweep_tflops"] / (fp32_peak / 1e12)),
+            "gpu_reference": gpu_ref,
+            "configs2": c2,
+            "configs3": c3,
+            "configs4": c4,
             "cw_attack": {"metric": "CW attack iters/s", "iters_per_s_graph": float(cw_t[1]), "iters_per_s_eager": float(cw_t[0]),
                           "sample_iters_per_s_graph": float(cw_t[1]) * B * world,
                           "config": f"PointNet(106) random init, B={B}/GPU N={NPTS}, w*(Chamfer+Hausdorff avg) + logits loss kappa=30, "

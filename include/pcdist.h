@@ -111,6 +111,10 @@ const char *pcd_last_error(void);
  * ---------------------------------------------------------------------------------- */
 size_t pcd_nn1_workspace_bytes(int B, int N, int M);
 
+/* The tile shape the heuristic of pcd_nn1_forward picks for this problem on the current device
+ * (HOST out-pointers): rows per lane R (2, 4, 8, 16) and the TMA stage width.  For reports. */
+int pcd_nn1_query_tiling(int B, int N, int M, int *rows_per_lane, int *col_tile);
+
 int pcd_nn1_forward(const float *rows, int64_t r_sb, int64_t r_sp, int64_t r_sc,
                     const float *cols, int64_t c_sb, int64_t c_sp, int64_t c_sc,
                     int B, int N, int M,
