@@ -222,4 +222,17 @@ static inline int num_sms() {
     return cache.v[dev];
 }
 
+// Opt a kernel in to more than 48 KB of dynamic shared memory ONCE per (kernel, device) and size: the attribute call
+// costs microseconds and the entry points are meant to be allocation- and configuration-free in steady state.
+template <typename K>
+static inline cudaError_t opt_in_smem(K kernel, size_t bytes) {
+    static PerDeviceInt done = {};                 // one instance per kernel type K == per kernel
+    const int dev = current_device();
+    if (dev < 0) return cudaErrorInvalidDevice;
+    if (done.v[dev] >= (int)bytes) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) done.v[dev] = (int)bytes;
+    return e;
+}
+
 }  // namespace pcd

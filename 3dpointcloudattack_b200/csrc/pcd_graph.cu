@@ -95,8 +95,12 @@ edge_feature_bwd_kernel(const float *__restrict__ g, const int32_t *__restrict__
     __syncthreads();
     const int32_t *ib = idx + (size_t)b * NK;
     const long long nslots = NK / VEC;
-    for (long long sl = threadIdx.x; sl < nslots; sl += kEdgeThreads) {
-        const long long e0 = sl * VEC;
+    // warp-uniform trip count: every lane of a warp runs the same number of iterations (lanes past the end carry a
+    // neutral slot), so the segmented scan below always runs converged, with the full mask
+    const long long nslots_up = (nslots + 31) / 32 * 32;
+    for (long long sl = threadIdx.x; sl < nslots_up; sl += kEdgeThreads) {
+        const bool valid = sl < nslots;
+        const long long e0 = (valid ? sl : 0) * VEC;
         int m[VEC];
         if (VEC == 4) {
             const int4 v = *reinterpret_cast<const int4 *>(ib + e0);
@@ -107,42 +111,44 @@ edge_feature_bwd_kernel(const float *__restrict__ g, const int32_t *__restrict__
         float sn[VEC], own = 0.f;
 #pragma unroll
         for (int i = 0; i < VEC; ++i) { sn[i] = 0.f; m[i] = min(max(m[i], 0), N - 1); }
-        for (int q = 0; q < nblocks; ++q) {
-            const int op = (ops >> (2 * q)) & 3;
-            const float *gp = g + (((size_t)b * nblocks + q) * C + c) * NK + e0;
-            float ga[VEC];
-            if (VEC == 4) {
-                const float4 gv = __ldcs(reinterpret_cast<const float4 *>(gp));
-                ga[0] = gv.x; ga[1 % VEC] = gv.y; ga[2 % VEC] = gv.z; ga[3 % VEC] = gv.w;
-            } else {
-                ga[0] = __ldcs(gp);
+        if (valid) {
+            for (int q = 0; q < nblocks; ++q) {
+                const int op = (ops >> (2 * q)) & 3;
+                const float *gp = g + (((size_t)b * nblocks + q) * C + c) * NK + e0;
+                float ga[VEC];
+                if (VEC == 4) {
+                    const float4 gv = __ldcs(reinterpret_cast<const float4 *>(gp));
+                    ga[0] = gv.x; ga[1 % VEC] = gv.y; ga[2 % VEC] = gv.z; ga[3 % VEC] = gv.w;
+                } else {
+                    ga[0] = __ldcs(gp);
+                }
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    if (op != PCD_EDGE_CENTER) sn[i] += ga[i];
+                    if (op == PCD_EDGE_CENTER) own += ga[i];
+                    if (op == PCD_EDGE_DIFF) own -= ga[i];
+                }
             }
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-                if (op != PCD_EDGE_CENTER) sn[i] += ga[i];
-                if (op == PCD_EDGE_CENTER) own += ga[i];
-                if (op == PCD_EDGE_DIFF) own -= ga[i];
-            }
+            for (int i = 0; i < VEC; ++i) atomicAdd(&acc[m[i]], sn[i]);
         }
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) atomicAdd(&acc[m[i]], sn[i]);
         // own term: consecutive lanes share the centre n (k / VEC slots each).  Shared-memory float
         // atomics are compare-and-swap loops, and same-address lanes serialise them, so the lanes of
         // a run first add up with a segmented shuffle scan and only the run's last lane touches acc[n].
         // (Batching the loads of several slots per thread ahead of the atomics was measured slower:
         // the CAS loops are latency bound and want occupancy -- 64 warps/SM -- more than load ILP.)
-        const int n = (int)(e0 / k);
-        const unsigned active = __activemask();
+        const int n = valid ? (int)(e0 / k) : -1;              // -1: a run of its own that adds nothing
         const int lane = threadIdx.x & 31;
+        __syncwarp();                                          // reconverge after the CAS loops
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const float up = __shfl_up_sync(active, own, o);
-            const int nup = __shfl_up_sync(active, n, o);
+            const float up = __shfl_up_sync(0xffffffffu, own, o);
+            const int nup = __shfl_up_sync(0xffffffffu, n, o);
             if (lane >= o && nup == n) own += up;
         }
-        const int ndown = __shfl_down_sync(active, n, 1);
-        const bool last = lane == 31 || ndown != n || !((active >> (lane + 1)) & 1u);
-        if (last) atomicAdd(&acc[n], own);
+        const int ndown = __shfl_down_sync(0xffffffffu, n, 1);
+        const bool last = lane == 31 || ndown != n;
+        if (last && valid) atomicAdd(&acc[n], own);
     }
     __syncthreads();
     float *dst = gx + ((size_t)b * C + c) * N;
@@ -297,8 +303,7 @@ extern "C" int pcd_edge_feature_forward(const float *x, const int32_t *idx, int 
     const long long sps = (nslots + slices - 1) / slices;
     const dim3 grid((unsigned)((nslots + sps - 1) / sps), cgroups, B);
     if (smem > 48 * 1024) {      // per device and function: requested on every call (~1 us), no process-wide memo
-        if (vec) PCD_CUDA_CHECK(cudaFuncSetAttribute(edge_feature_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else PCD_CUDA_CHECK(cudaFuncSetAttribute(edge_feature_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PCD_CUDA_CHECK(vec ? opt_in_smem(edge_feature_fwd_kernel<4>, smem) : opt_in_smem(edge_feature_fwd_kernel<1>, smem));
     }
     if (vec) edge_feature_fwd_kernel<4><<<grid, kEdgeThreads, smem, st>>>(x, idx, C, N, k, nblocks, packed, CG, sps, out);
     else edge_feature_fwd_kernel<1><<<grid, kEdgeThreads, smem, st>>>(x, idx, C, N, k, nblocks, packed, CG, sps, out);
@@ -325,8 +330,7 @@ extern "C" int pcd_edge_feature_backward(const float *g, const int32_t *idx, int
     cudaStream_t st = (cudaStream_t)stream;
     const bool vec = (k & 3) == 0;
     if (smem > 48 * 1024) {
-        if (vec) PCD_CUDA_CHECK(cudaFuncSetAttribute(edge_feature_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else PCD_CUDA_CHECK(cudaFuncSetAttribute(edge_feature_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PCD_CUDA_CHECK(vec ? opt_in_smem(edge_feature_bwd_kernel<4>, smem) : opt_in_smem(edge_feature_bwd_kernel<1>, smem));
     }
     if (vec) edge_feature_bwd_kernel<4><<<dim3(C, B), kEdgeThreads, smem, st>>>(g, idx, C, N, k, nblocks, packed, gx);
     else edge_feature_bwd_kernel<1><<<dim3(C, B), kEdgeThreads, smem, st>>>(g, idx, C, N, k, nblocks, packed, gx);
@@ -345,8 +349,7 @@ extern "C" int pcd_fps(const float *xyz, int64_t sb, int64_t sp, int64_t sc, int
     do {                                                                                                         \
         constexpr size_t sm_bytes = (size_t)(T) * (PPT) * sizeof(float4);                                        \
         if (sm_bytes > 48 * 1024)                                                                                \
-            PCD_CUDA_CHECK(cudaFuncSetAttribute(fps_kernel<T, PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                                (int)sm_bytes));                                                                                                        \
+            PCD_CUDA_CHECK(opt_in_smem(fps_kernel<T, PPT>, sm_bytes));                                                                                                        \
         fps_kernel<T, PPT><<<B, T, sm_bytes, st>>>(xyz, sb, sp, sc, N, npoint, start, out);                      \
     } while (0)
     if (N <= 256) PCD_FPS(128, 2);
@@ -362,7 +365,7 @@ extern "C" int pcd_fps(const float *xyz, int64_t sb, int64_t sp, int64_t sc, int
             return PCD_ERR_UNSUPPORTED;
         }
         if (smem > 48 * 1024)
-            PCD_CUDA_CHECK(cudaFuncSetAttribute(fps_large_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            PCD_CUDA_CHECK(opt_in_smem(fps_large_kernel<1024>, smem));
         fps_large_kernel<1024><<<B, 1024, smem, st>>>(xyz, sb, sp, sc, N, npoint, start, out);
     }
 #undef PCD_FPS

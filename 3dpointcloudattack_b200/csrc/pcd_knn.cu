@@ -1138,7 +1138,7 @@ extern "C" size_t pcd_knn_workspace_bytes(int B, int N, int M, int C, int K) {
 extern "C" int pcd_knn_forward(const float *rows, int64_t r_sb, int64_t r_sp, int64_t r_sc,
                                const float *cols, int64_t c_sb, int64_t c_sp, int64_t c_sc,
                                int B, int N, int M, int C, int K, int form, int norm_kind, int swap_norms,
-                               float *dists, int32_t *idx, void *workspace, size_t workspace_bytes, void *stream) {
+                               float *dists, int32_t *idx, void *workspace, size_t workspace_bytes, int strategy, void *stream) {
     if (!rows || !cols || !idx || !workspace) {
         set_error("pcd_knn_forward: NULL pointer argument");
         return PCD_ERR_ARG;
@@ -1160,9 +1160,8 @@ extern "C" int pcd_knn_forward(const float *rows, int64_t r_sb, int64_t r_sp, in
         set_error("pcd_knn_forward: workspace %zu < required %zu bytes", workspace_bytes, L.total);
         return PCD_ERR_WORKSPACE;
     }
-    int dev = 0, sms = 0;
-    PCD_CUDA_CHECK(cudaGetDevice(&dev));
-    PCD_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int sms = num_sms();
+    if (sms <= 0) return cuda_fail(cudaGetLastError(), "no CUDA device");
     cudaStream_t st = (cudaStream_t)stream;
     char *ws = (char *)workspace;
     const long long total = (long long)B * (L.Npad + L.Mpad);
@@ -1175,8 +1174,10 @@ extern "C" int pcd_knn_forward(const float *rows, int64_t r_sb, int64_t r_sp, in
         knn3_prep_kernel<<<pgrid, 256, 0, st>>>(rows, r_sb, r_sp, r_sc, cols, c_sb, c_sp, c_sc, B, N, M, L.Npad, L.Mpad,
                                                 norm_kind, swap_norms, rowq, colq, colpk);
         PCD_CUDA_CHECK(cudaGetLastError());
-        const bool prepass = L.prepass && !getenv("PCD_KNN_NO_PREPASS");
-        const bool collect = prepass && !getenv("PCD_KNN_NO_COLLECT");
+        // strategy (per call; the library reads no environment): 0 = chunk-minima bound + collect + final,
+        // 1 = bound + warp-per-row select (no collect pass), 2 = warp-per-row select alone.  Same results.
+        const bool prepass = L.prepass && strategy != PCD_KNN_SELECT_ONLY;
+        const bool collect = prepass && strategy != PCD_KNN_BOUND_SELECT;
         int *ovf_cnt = (int *)(ws + L.ovf_cnt), *ovf_rows = (int *)(ws + L.ovf_rows);
         if (prepass) {
             const int W = L.W, G = L.G;
@@ -1246,11 +1247,20 @@ extern "C" int pcd_knn_forward(const float *rows, int64_t r_sb, int64_t r_sp, in
         PCD_CUDA_CHECK(cudaGetLastError());
         const size_t smem = knnc_smem_bytes(C);
         const dim3 fgrid(L.Npad / kFcCtaRows, B);
+        static PerDeviceInt smem_set[2] = {};                    // largest dynamic shared-memory size opted in so far, per device
+        const int dv = current_device();
+        if (dv < 0) return cuda_fail(cudaErrorInvalidDevice, "cudaGetDevice");
         if (NL == 1) {
-            PCD_CUDA_CHECK(cudaFuncSetAttribute(knnc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (smem_set[0].v[dv] < (int)smem) {
+                PCD_CUDA_CHECK(cudaFuncSetAttribute(knnc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                smem_set[0].v[dv] = (int)smem;
+            }
             knnc_kernel<1><<<fgrid, kKnnThreads, smem, st>>>(rowf, rown, colS, N, M, C, L.Npad, L.Mpad, K, form, dists, idx);
         } else {
-            PCD_CUDA_CHECK(cudaFuncSetAttribute(knnc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (smem_set[1].v[dv] < (int)smem) {
+                PCD_CUDA_CHECK(cudaFuncSetAttribute(knnc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                smem_set[1].v[dv] = (int)smem;
+            }
             knnc_kernel<2><<<fgrid, kKnnThreads, smem, st>>>(rowf, rown, colS, N, M, C, L.Npad, L.Mpad, K, form, dists, idx);
         }
         PCD_CUDA_CHECK(cudaGetLastError());
@@ -1272,9 +1282,8 @@ extern "C" int pcd_knn_backward(const float *rows, int64_t r_sb, int64_t r_sp, i
         return PCD_ERR_ARG;
     }
     if (!grad_rows && !grad_cols) return PCD_OK;
-    int dev = 0, sms = 0;
-    PCD_CUDA_CHECK(cudaGetDevice(&dev));
-    PCD_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int sms = num_sms();
+    if (sms <= 0) return cuda_fail(cudaGetLastError(), "no CUDA device");
     KnnBwdArgs a{rows, r_sb, r_sp, r_sc, cols, c_sb, c_sp, c_sc, B, N, M, K, swap_norms, idx, g_dists,
                  grad_rows, gr_sb, gr_sp, gr_sc, grad_cols, gc_sb, gc_sp, gc_sc};
     const long long total = (long long)B * (N + M);
@@ -1295,9 +1304,8 @@ extern "C" int pcd_ball_query(const float *xyz, int64_t x_sb, int64_t x_sp, int6
         set_error("pcd_ball_query: bad argument");
         return PCD_ERR_ARG;
     }
-    int dev = 0, sms = 0;
-    PCD_CUDA_CHECK(cudaGetDevice(&dev));
-    PCD_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int sms = num_sms();
+    if (sms <= 0) return cuda_fail(cudaGetLastError(), "no CUDA device");
     const long long rows = (long long)B * S;
     const long long want = (rows + 7) / 8;
     const int grid = (int)(want < (long long)sms * 8 ? want : (long long)sms * 8);

@@ -240,6 +240,16 @@ def clear_cache():
 
 
 # -------------------------------------------------------------------------------- k-NN
+KNN_AUTO, KNN_BOUND_SELECT, KNN_SELECT_ONLY = 0, 1, 2
+_knn_strategy = KNN_AUTO
+
+
+def force_knn_strategy(strategy=KNN_AUTO):
+    """Tests / tuning: pick the xyz k-NN pipeline of the following calls explicitly (pcd_knn_strategy in include/pcdist.h)."""
+    global _knn_strategy
+    _knn_strategy = int(strategy)
+
+
 class _KNN(torch.autograd.Function):
     @staticmethod
     def forward(ctx, rows, cols, K, form, norm, swap_norms, want_dists):
@@ -255,7 +265,7 @@ class _KNN(torch.autograd.Function):
             ws = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=dev)
             st = lib.pcd_knn_forward(*_cloud_args(rows), *_cloud_args(cols), B, N, M, C, K,
                                      form, norm, int(swap_norms), dists.data_ptr(), idx.data_ptr(),
-                                     ws.data_ptr(), ws_bytes, _stream(dev))
+                                     ws.data_ptr(), ws_bytes, _knn_strategy, _stream(dev))
             _lib.check(st, "pcd_knn_forward")
         _launch_count += 2
         ctx.save_for_backward(rows, cols, idx)
@@ -425,7 +435,7 @@ class _KnnOutlierLoss(torch.autograd.Function):
             ws_bytes = lib.pcd_knn_workspace_bytes(B, N, N, 3, K1)
             ws = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=dev)
             st = lib.pcd_knn_forward(*_cloud_args(x), *_cloud_args(x), B, N, N, 3, K1, form, norm, int(swap_norms),
-                                     dists.data_ptr(), idx.data_ptr(), ws.data_ptr(), ws_bytes, _stream(dev))
+                                     dists.data_ptr(), idx.data_ptr(), ws.data_ptr(), ws_bytes, _knn_strategy, _stream(dev))
             _lib.check(st, "pcd_knn_forward")
             value = torch.empty((B, N), dtype=torch.float32, device=dev)
             mask = torch.empty((B, N), dtype=torch.float32, device=dev)

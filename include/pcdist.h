@@ -62,6 +62,11 @@ enum pcd_transform { PCD_VALUE_SQUARED = 0, PCD_VALUE_SQRT_CLAMP = 1 };
 #define PCD_KNN_MAX_K 64
 #define PCD_KNN_MAX_C 128
 
+/* pcd_knn_forward `strategy` for 3-channel clouds (identical results; tests and tuning pick the pipeline explicitly,
+ * the library reads no environment): the default four-pass pipeline, the chunk-minima bound followed by the
+ * warp-per-row select, or the warp-per-row select alone. */
+enum pcd_knn_strategy { PCD_KNN_AUTO = 0, PCD_KNN_BOUND_SELECT = 1, PCD_KNN_SELECT_ONLY = 2 };
+
 int pcd_version(void);
 const char *pcd_last_error(void);
 
@@ -175,7 +180,7 @@ int pcd_knn_forward(const float *rows, int64_t r_sb, int64_t r_sp, int64_t r_sc,
                     int B, int N, int M, int C, int K,
                     int form, int norm_kind, int swap_norms,
                     float *dists, int32_t *idx,
-                    void *workspace, size_t workspace_bytes, void *stream);
+                    void *workspace, size_t workspace_bytes, int strategy, void *stream);
 
 /* Backward of dists[B,N,K] w.r.t. both clouds through idx (3-channel clouds).
  * g_dists[B,N,K] upstream.  grad_* are written in full. */

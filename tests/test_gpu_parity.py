@@ -395,14 +395,17 @@ def test_knn_collect_pipeline(case):
     assert np.array_equal(npy(i), oi) and np.array_equal(npy(d), od)
 
 
-def test_knn_collect_matches_select_only(monkeypatch):
+def test_knn_collect_matches_select_only():
     rs = np.random.RandomState(5)
     x = cu(rs.rand(4, 3000, 3).astype(np.float32))
     d1, i1 = F.knn(x, x, 20)
-    monkeypatch.setenv("PCD_KNN_NO_COLLECT", "1")
-    d2, i2 = F.knn(x, x, 20)
-    monkeypatch.setenv("PCD_KNN_NO_PREPASS", "1")
-    d3, i3 = F.knn(x, x, 20)
+    try:
+        F.force_knn_strategy(F.KNN_BOUND_SELECT)
+        d2, i2 = F.knn(x, x, 20)
+        F.force_knn_strategy(F.KNN_SELECT_ONLY)
+        d3, i3 = F.knn(x, x, 20)
+    finally:
+        F.force_knn_strategy(F.KNN_AUTO)
     assert torch.equal(i1, i2) and torch.equal(d1, d2) and torch.equal(i1, i3) and torch.equal(d1, d3)
 
 

@@ -28,9 +28,9 @@ def main():
     # k-NN xyz: collect pipeline vs warp-per-row select on a big batch
     x = torch.rand(512, 2048, 3, device="cuda")
     d1, i1 = F.knn(x, x, 20)
-    os.environ["PCD_KNN_NO_COLLECT"] = "1"
+    F.force_knn_strategy(F.KNN_BOUND_SELECT)
     d2, i2 = F.knn(x, x, 20)
-    del os.environ["PCD_KNN_NO_COLLECT"]
+    F.force_knn_strategy(F.KNN_AUTO)
     assert torch.equal(i1, i2) and torch.equal(d1, d2)
     # (expansion-form self distances are rounding noise, ~1e-7: a neighbour closer than ~6e-4 can legitimately win)
     self_first = float((i1[:, :, 0].long() == torch.arange(2048, device="cuda").expand(512, -1)).float().mean())
