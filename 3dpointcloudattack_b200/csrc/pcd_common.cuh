@@ -109,6 +109,31 @@ __device__ __forceinline__ float pair_dist_dyn(int form, float qx, float qy, flo
     return pair_dist_scalar<PCD_FORM_SUM_FIRST>(qx, qy, qz, qn, cx, cy, cz, cn);
 }
 
+// |p|^2 of two points at once, same roundings as sq_norm3.  The mul-then-add form is evaluated with the scalar
+// round-to-nearest intrinsics: ptxas CONTRACTS mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (observed with CUDA 12.9, --fmad=false
+// notwithstanding), which would change the rounding of (x*x + y*y) + z*z; __fmul_rn / __fadd_rn are never fused.
+__device__ __forceinline__ f32x2 sq_norm3_x2(int kind, f32x2 x, f32x2 y, f32x2 z) {
+    if (kind == PCD_NORM_FMA) return fma2(z, z, fma2(y, y, mul2(x, x)));
+    float x0, x1, y0, y1, z0, z1;
+    unpack2(x, x0, x1); unpack2(y, y0, y1); unpack2(z, z0, z1);
+    return pack2(__fadd_rn(__fadd_rn(__fmul_rn(x0, x0), __fmul_rn(y0, y0)), __fmul_rn(z0, z0)),
+                 __fadd_rn(__fadd_rn(__fmul_rn(x1, x1), __fmul_rn(y1, y1)), __fmul_rn(z1, z1)));
+}
+// Two distances between ONE fixed point f (coordinates fx, fy, fz, norm fn) and two candidates (packed coordinates X, Y, Z,
+// norms NN).  `row_is_fixed` says which side the fixed point is on; the factor -2 of the row operand is exact, so it is
+// applied to the fixed scalars either way: fl((-2 r).c) == fl(r.(-2 c)).  m2x etc. = -2 * the fixed coordinates.
+template <int FORM>
+__device__ __forceinline__ f32x2 pair_dist_fixed_x2(bool row_is_fixed, float m2x, float m2y, float m2z, float fn,
+                                                    f32x2 X, f32x2 Y, f32x2 Z, f32x2 NN) {
+    f32x2 t = mul2_s(m2x, X);
+    t = fma2_s(m2y, Y, t);
+    t = fma2_s(m2z, Z, t);
+    // nrow / ncol: the fixed point's norm is the row norm when row_is_fixed, else the column norm
+    if (FORM == PCD_FORM_SUM_FIRST) return add2(add2_s(fn, NN), t);                               // (nrow + ncol) + t
+    if (FORM == PCD_FORM_ROW_COL) return row_is_fixed ? add2(add2_s(fn, t), NN) : add2_s(fn, add2(t, NN));   // (t + nrow) + ncol
+    return row_is_fixed ? add2_s(fn, add2(t, NN)) : add2(add2_s(fn, t), NN);                       // (t + ncol) + nrow
+}
+
 __device__ __forceinline__ float sq_norm3(int kind, float x, float y, float z) {
     if (kind == PCD_NORM_FMA) return __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));
     return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));

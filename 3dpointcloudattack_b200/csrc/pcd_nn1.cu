@@ -341,6 +341,12 @@ nn1_sweep_kernel(SweepSrc src, unsigned long long *__restrict__ rowkey, unsigned
     uint32_t rpar = 0;
     bool armed = !RAW;     // RAW: griddepcontrol.wait not executed yet (keys are armed by our predecessor)
 
+#ifdef PCD_SWEEP_TRACE
+    long long t_row = 0, t_comp = 0, t_bar = 0, t_flush = 0, t_mark = clock64();
+#define PCD_PHASE(acc) do { const long long _n = clock64(); acc += _n - t_mark; t_mark = _n; } while (0)
+#else
+#define PCD_PHASE(acc) do { } while (0)
+#endif
     int it = 0;
     for (int u = u0; u < u1; ++it) {
         const int buf = it & 1;
@@ -388,6 +394,7 @@ nn1_sweep_kernel(SweepSrc src, unsigned long long *__restrict__ rowkey, unsigned
 #ifdef PCD_SWEEP_TRACE
         if (trace && tid == 0 && it == 0) trace[blockIdx.x * 8 + 4] = globaltimer_ns();
 #endif
+        PCD_PHASE(t_row);
 
         const float4 *t4 = sm.tile[buf];
         uint2 *cp = sm.colpart[buf][warp];
@@ -445,6 +452,7 @@ nn1_sweep_kernel(SweepSrc src, unsigned long long *__restrict__ rowkey, unsigned
             }
         }
         *reinterpret_cast<uint4 *>(&cp[pend_at]) = make_uint4(pend_lo.x, pend_lo.y, pend_hi.x, pend_hi.y);
+        PCD_PHASE(t_comp);
 
         if constexpr (RAW) {
             // next tile: raw xyz -> pair records, in front of the barrier that ends this tile
@@ -455,6 +463,7 @@ nn1_sweep_kernel(SweepSrc src, unsigned long long *__restrict__ rowkey, unsigned
             }
         }
         __syncthreads();  // tile[buf] fully read, colpart[buf] fully written, RAW: tile[buf^1] converted, craw[buf^1] and rraw free
+        PCD_PHASE(t_bar);
 
         if (tid == 0) {
             if constexpr (RAW) {
@@ -484,9 +493,15 @@ nn1_sweep_kernel(SweepSrc src, unsigned long long *__restrict__ rowkey, unsigned
                           make_key(v, (((uint32_t)qt * kSweepWarps + w) << 5) + (uint32_t)(__ffs(msk) - 1)));
         }
         u += nseg;
+        PCD_PHASE(t_flush);
     }
 #ifdef PCD_SWEEP_TRACE
-    if (trace && tid == 0) trace[blockIdx.x * 8 + 1] = globaltimer_ns();
+    if (trace && tid == 0) {
+        trace[blockIdx.x * 8 + 1] = globaltimer_ns();
+        // phase cycles of warp 0: row switch | compute | convert + barrier wait | flush  (16 bits each, in units of 64 cycles)
+        trace[blockIdx.x * 8 + 5] = (unsigned long long)t_row; trace[blockIdx.x * 8 + 6] = (unsigned long long)t_comp;
+        trace[blockIdx.x * 8 + 7] = ((unsigned long long)t_bar << 32) | (unsigned long long)(t_flush & 0xffffffffll);
+    }
 #endif
 #pragma unroll
     for (int r = 0; r < R; ++r) atomicMin(&rowkey[row_base + r * 32], make_key(best[r], btag[r]));
@@ -871,76 +886,54 @@ nn1_fixup_staged_kernel(StagedArgs sa) {
             const uint32_t tag = (uint32_t)key;
             const float pn = sq_norm3(NORM, px, py, pz);
             int arg = 0x7fffffff;
+            // Candidates come in groups of four (three LDS.128 in either dense layout) and are evaluated two at a time with the
+            // sweep's packed instruction sequence; the fixed point carries the exact factor -2 whichever side it is on.
+            const float m2x = -2.f * px, m2y = -2.f * py, m2z = -2.f * pz;
+            int c0 = 0, ngroups = 0;                         // first candidate, groups of 4
             if (side == 0) {
-                // row point (-2x, -2y, -2z, n) against the 32 columns of chunk `tag`: 8 groups of 4 columns
-                if (tag < (uint32_t)a.nchunks) {
-                    const float qx = -2.f * px, qy = -2.f * py, qz = -2.f * pz;
-                    const int j0 = (int)tag * kColChunk;
+                if (tag < (uint32_t)a.nchunks) { c0 = (int)tag * kColChunk; ngroups = 8; }              // the 32 columns of the winning chunk
+            } else if ((tag >> 5) < (uint32_t)a.nrowgroups) {
+                c0 = (int)(tag >> 5) * (32 * R) + (int)(tag & 31u) * R;                                  // the R rows of the winning lane
+                ngroups = R >> 2;
+            }
+            if (ngroups > 0) {
 #pragma unroll 4
-                    for (int i = 0; i < 8; ++i) {
-                        const int k = (lane + i) & 7, j = j0 + 4 * k;
-                        if (j < n_opp) {                        // n_opp % 4 == 0: whole groups
-                            float cx[4], cy[4], cz[4];
-                            if (opp_cm) {
-                                const float4 fx = *reinterpret_cast<const float4 *>(stage + j);
-                                const float4 fy = *reinterpret_cast<const float4 *>(stage + sa.stage_stride + j);
-                                const float4 fz = *reinterpret_cast<const float4 *>(stage + 2 * sa.stage_stride + j);
-                                cx[0] = fx.x; cx[1] = fx.y; cx[2] = fx.z; cx[3] = fx.w;
-                                cy[0] = fy.x; cy[1] = fy.y; cy[2] = fy.z; cy[3] = fy.w;
-                                cz[0] = fz.x; cz[1] = fz.y; cz[2] = fz.z; cz[3] = fz.w;
-                            } else {
-                                const float4 *g = reinterpret_cast<const float4 *>(stage + (size_t)j * 3);
-                                const float4 f0 = g[0], f1 = g[1], f2 = g[2];
-                                cx[0] = f0.x; cx[1] = f0.w; cx[2] = f1.z; cx[3] = f2.y;
-                                cy[0] = f0.y; cy[1] = f1.x; cy[2] = f1.w; cy[3] = f2.z;
-                                cz[0] = f0.z; cz[1] = f1.y; cz[2] = f2.x; cz[3] = f2.w;
-                            }
-#pragma unroll
-                            for (int t = 0; t < 4; ++t)
-                                if (pair_dist_scalar<FORM>(qx, qy, qz, pn, cx[t], cy[t], cz[t], sq_norm3(NORM, cx[t], cy[t], cz[t])) == v)
-                                    arg = min(arg, j + t);
+                for (int i = 0; i < ngroups; ++i) {
+                    const int k = (lane + i) & (ngroups - 1), j = c0 + 4 * k;                             // rotated start: conflict-free banks
+                    if (j < n_opp) {                                                                      // n_opp % 4 == 0: whole groups
+                        f32x2 X0, X1, Y0, Y1, Z0, Z1;
+                        if (opp_cm) {
+                            const float4 fx = *reinterpret_cast<const float4 *>(stage + j);
+                            const float4 fy = *reinterpret_cast<const float4 *>(stage + sa.stage_stride + j);
+                            const float4 fz = *reinterpret_cast<const float4 *>(stage + 2 * sa.stage_stride + j);
+                            X0 = pack2(fx.x, fx.y); X1 = pack2(fx.z, fx.w);
+                            Y0 = pack2(fy.x, fy.y); Y1 = pack2(fy.z, fy.w);
+                            Z0 = pack2(fz.x, fz.y); Z1 = pack2(fz.z, fz.w);
+                        } else {
+                            const float4 *g = reinterpret_cast<const float4 *>(stage + (size_t)j * 3);
+                            const float4 f0 = g[0], f1 = g[1], f2 = g[2];
+                            X0 = pack2(f0.x, f0.w); X1 = pack2(f1.z, f2.y);
+                            Y0 = pack2(f0.y, f1.x); Y1 = pack2(f1.w, f2.z);
+                            Z0 = pack2(f0.z, f1.y); Z1 = pack2(f2.x, f2.w);
                         }
+                        const f32x2 d0 = pair_dist_fixed_x2<FORM>(side == 0, m2x, m2y, m2z, pn, X0, Y0, Z0, sq_norm3_x2(NORM, X0, Y0, Z0));
+                        const f32x2 d1 = pair_dist_fixed_x2<FORM>(side == 0, m2x, m2y, m2z, pn, X1, Y1, Z1, sq_norm3_x2(NORM, X1, Y1, Z1));
+                        float e0, e1, e2, e3;
+                        unpack2(d0, e0, e1); unpack2(d1, e2, e3);
+                        if (e3 == v) arg = min(arg, j + 3);
+                        if (e2 == v) arg = min(arg, j + 2);
+                        if (e1 == v) arg = min(arg, j + 1);
+                        if (e0 == v) arg = min(arg, j);
                     }
                 }
-            } else if ((tag >> 5) < (uint32_t)a.nrowgroups) {
-                // column point (x, y, z, n) against the R rows of the winning lane
-                const int i0 = (int)(tag >> 5) * (32 * R) + (int)(tag & 31u) * R;
-                if (R >= 4) {
-                    const int ng = R >> 2;
-#pragma unroll 4
-                    for (int i = 0; i < ng; ++i) {
-                        const int k = (lane + i) & (ng - 1), r0 = i0 + 4 * k;
-                        if (r0 < n_opp) {
-                            float x[4], y[4], z[4];
-                            if (opp_cm) {
-                                const float4 fx = *reinterpret_cast<const float4 *>(stage + r0);
-                                const float4 fy = *reinterpret_cast<const float4 *>(stage + sa.stage_stride + r0);
-                                const float4 fz = *reinterpret_cast<const float4 *>(stage + 2 * sa.stage_stride + r0);
-                                x[0] = fx.x; x[1] = fx.y; x[2] = fx.z; x[3] = fx.w;
-                                y[0] = fy.x; y[1] = fy.y; y[2] = fy.z; y[3] = fy.w;
-                                z[0] = fz.x; z[1] = fz.y; z[2] = fz.z; z[3] = fz.w;
-                            } else {
-                                const float4 *g = reinterpret_cast<const float4 *>(stage + (size_t)r0 * 3);
-                                const float4 f0 = g[0], f1 = g[1], f2 = g[2];
-                                x[0] = f0.x; x[1] = f0.w; x[2] = f1.z; x[3] = f2.y;
-                                y[0] = f0.y; y[1] = f1.x; y[2] = f1.w; y[3] = f2.z;
-                                z[0] = f0.z; z[1] = f1.y; z[2] = f2.x; z[3] = f2.w;
-                            }
-#pragma unroll
-                            for (int t = 0; t < 4; ++t)
-                                if (pair_dist_scalar<FORM>(-2.f * x[t], -2.f * y[t], -2.f * z[t], sq_norm3(NORM, x[t], y[t], z[t]), px, py, pz, pn) == v)
-                                    arg = min(arg, r0 + t);
-                        }
-                    }
-                } else {
-                    for (int t = 0; t < R; ++t) {
-                        const int i = i0 + t;
-                        if (i < n_opp) {
-                            float x, y, z;
-                            if (opp_cm) { x = stage[i]; y = stage[sa.stage_stride + i]; z = stage[2 * sa.stage_stride + i]; }
-                            else { x = stage[3 * i]; y = stage[3 * i + 1]; z = stage[3 * i + 2]; }
-                            if (pair_dist_scalar<FORM>(-2.f * x, -2.f * y, -2.f * z, sq_norm3(NORM, x, y, z), px, py, pz, pn) == v) arg = min(arg, i);
-                        }
+            } else if (side == 1 && R < 4 && (tag >> 5) < (uint32_t)a.nrowgroups) {
+                for (int t = 0; t < R; ++t) {                                                             // R = 2
+                    const int i = c0 + t;
+                    if (i < n_opp) {
+                        float x, y, z;
+                        if (opp_cm) { x = stage[i]; y = stage[sa.stage_stride + i]; z = stage[2 * sa.stage_stride + i]; }
+                        else { x = stage[3 * i]; y = stage[3 * i + 1]; z = stage[3 * i + 2]; }
+                        if (pair_dist_scalar<FORM>(-2.f * x, -2.f * y, -2.f * z, sq_norm3(NORM, x, y, z), px, py, pz, pn) == v) arg = min(arg, i);
                     }
                 }
             }

@@ -64,6 +64,15 @@ def main():
     order = np.argsort(end)
     print("  earliest-finishing CTAs:", [(int(i), round(float(end[i]), 1)) for i in order[:5]])
     print("  latest-finishing CTAs:  ", [(int(i), round(float(end[i]), 1)) for i in order[-5:]])
+    # phase cycles of warp 0 of every CTA (clock64): row switch | compute | convert + barrier wait | flush
+    row_c, comp_c = t[:, 5].astype(np.float64), t[:, 6].astype(np.float64)
+    bar_c, flush_c = (t[:, 7] >> 32).astype(np.float64), (t[:, 7] & 0xffffffff).astype(np.float64)
+    tot = row_c + comp_c + bar_c + flush_c
+    early = end < np.median(end)                      # the CTA of each SM that finishes first / last
+    for name, sel in (("first-finishing CTAs", early), ("last-finishing CTAs", ~early)):
+        print(f"  {name}: cycles/1000  row switch {row_c[sel].mean()/1e3:.1f}  compute {comp_c[sel].mean()/1e3:.1f}  "
+              f"convert+barrier {bar_c[sel].mean()/1e3:.1f}  flush {flush_c[sel].mean()/1e3:.1f}  (sum {tot[sel].mean()/1e3:.1f} = "
+              f"{tot[sel].mean()/1.965e3:.1f} us at 1.965 GHz)")
     ts = np.unique(t[:, :3])
     print("  globaltimer granularity (ns):", int(np.diff(ts).min()) if len(ts) > 1 else -1)
 
