@@ -22,7 +22,7 @@ def header_symbols():
 def test_library_exports_every_declared_symbol():
     lib = pcd._lib.load()
     syms = header_symbols()
-    assert len(syms) >= 11
+    assert len(syms) >= 20
     for s in syms:
         assert hasattr(lib, s), s
     assert sorted(pcd._lib.SIGNATURES) == syms           # the ctypes table covers the header, no more no less
@@ -69,6 +69,29 @@ def test_no_cpu_fallback():
         pcd.cw_loop.CWAttack(torch.nn.Identity(), None, None).attack(a, torch.zeros(1))
     with pytest.raises(ValueError, match="pinned"):
         pcd.graph.PipelinedLoss(lambda x, y: (x.sum(), ()), a, a)
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        pcd.utility.estimate_normal(a.transpose(1, 2), 3)
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        pcd.loss_utils._get_kappa_ori(a.transpose(1, 2), a.transpose(1, 2), 2)
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        pcd.dist_utils.KNNDist(k=2)(a)
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        pcd.taof.get_Laplace_from_pc(a.transpose(1, 2))
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        pcd.geoa3_loop.GeoA3Attack(torch.nn.Identity(), classes=3).attack(a, torch.zeros(1))
+
+
+def test_geoa3_lp_clip_matches_the_reference_formula():
+    """attack/GeoA3/GeoA3_attack.py:92-101 (pure torch, runs on CPU): offsets longer than cc_linf are scaled onto the ball,
+    shorter ones pass, (near-)zero ones stay zero."""
+    torch.manual_seed(0)
+    off = torch.randn(2, 3, 50) * 0.05
+    off[0, :, 3] = 0.0
+    out = pcd.geoa3_loop.lp_clip(off, 0.02)
+    ln = off.norm(dim=1, keepdim=True)
+    ref = torch.where(ln < 0.02, off, torch.where(ln > 1e-6, off / ln * 0.02, torch.zeros_like(off)))
+    assert torch.equal(out, ref)
+    assert float(out.norm(dim=1).max()) <= 0.02 * (1 + 1e-6) and float(out[0, :, 3].abs().max()) == 0.0
 
 
 def test_product_never_imports_the_oracle():
@@ -91,6 +114,13 @@ def test_signatures_mirror_the_reference():
     assert list(inspect.signature(pcd.dist_utils.KNNDist.forward).parameters) == ["self", "pc", "weights", "batch_avg"]
     assert list(inspect.signature(pcd.dist_utils.ChamferDist.forward).parameters) == ["self", "adv_pc", "ori_pc", "weights", "batch_avg"]
     assert list(inspect.signature(pcd.dgcnn.get_graph_feature).parameters) == ["x", "k", "idx"]
+    assert list(inspect.signature(pcd.utility.estimate_normal).parameters) == ["pc", "k"]
+    assert list(inspect.signature(pcd.utility.estimate_perpendicular).parameters) == ["pc", "k", "sigma", "clip"]
+    assert list(inspect.signature(pcd.geoa3_loop.offset_proj).parameters) == ["offset", "ori_pc", "ori_normal", "project"]
+    assert list(inspect.signature(pcd.geoa3_loop.lp_clip).parameters) == ["offset", "cc_linf"]
+    assert list(inspect.signature(pcd.loss_utils.displacement_loss).parameters) == ["adv_pc", "ori_pc", "k"]
+    assert list(inspect.signature(pcd.loss_utils.repulsion_loss).parameters) == ["pc", "k", "h"]
+    assert list(inspect.signature(pcd.taof.get_Laplace_from_pc).parameters) == ["ori_pc"]
     for fn in ("euclidean_distances", "pairwise_distances", "chamfer", "sgd_hausdorff_dis", "bid_hausdorff_dis"):
         assert callable(getattr(pcd.dis_utils_torch, fn))
 
@@ -101,8 +131,10 @@ def test_install_patches_reference_modules():
     try:
         rep = pcd.install.install(modules=["utils.dis_utils_torch", "attack.CW.CW_utils.distance",
                                            "attack.CW.CW_utils.dist_utils", "attack.GeoA3.knn_utils",
-                                           "model.dgcnn", "model.pointnet2_utils"])
+                                           "model.dgcnn", "model.pointnet2_utils", "attack.AOF.TAOF_attack"])
         assert all(v == "patched" for v in rep.values()), rep
+        import attack.AOF.TAOF_attack as TA
+        assert TA.get_Laplace_from_pc is pcd.taof.get_Laplace_from_pc and TA.knn is pcd.dgcnn.knn
         import attack.CW.CW_utils.dist_utils as DU
         import attack.CW.CW_utils.distance as CD
         import model.dgcnn as MD

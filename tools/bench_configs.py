@@ -207,12 +207,13 @@ def config3(pcd, dev, rank, world, with_reference, global_B=128, N=2048, iters=4
     for x in feats:
         idx = pcd.dgcnn.knn(x, 20)
         xg = x.clone().requires_grad_(True)
+        gout = torch.ones((B, 2 * x.shape[1], N, 20), device=dev)          # a dense upstream gradient, as the victim's conv hands back
 
         def edge():
             xg.grad = None
-            pcd.dgcnn.get_graph_feature(xg, k=20, idx=idx).sum().backward()
+            torch.autograd.backward(pcd.dgcnn.get_graph_feature(xg, k=20, idx=idx), gout)
         ef.append(timed(edge, 3)[0])
-        del xg, idx
+        del xg, idx, gout
     out["edge_feature_fwd_bwd_ms_C3_64_64_128"] = ef
     R, mt = ctypes.c_int(0), ctypes.c_int(0)
     pcd._lib.load().pcd_nn1_query_tiling(B, N, N, ctypes.byref(R), ctypes.byref(mt))
