@@ -36,8 +36,8 @@ SIGNATURES = {
     "pcd_edge_feature_forward": (_I, [_P, _P, _I, _I, _I, _I, _I, _c.POINTER(_I), _P, _P]),
     "pcd_edge_feature_backward": (_I, [_P, _P, _I, _I, _I, _I, _I, _c.POINTER(_I), _P, _P]),
     "pcd_fps": (_I, [_P, _L, _L, _L, _I, _I, _I, _P, _P, _P]),
-    "pcd_knn_outlier_forward": (_I, [_P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P]),
-    "pcd_knn_outlier_backward": (_I, _CLOUD + [_P, _P, _P, _L, _I, _I, _I, _I, _P, _P]),
+    "pcd_knn_outlier_forward": (_I, [_P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P]),
+    "pcd_knn_outlier_backward": (_I, _CLOUD + [_P, _P, _P, _L, _I, _I, _I, _I, _P, _I, _P]),
     "pcd_local_frames": (_I, _CLOUD + [_P, _I, _I, _I, _I] + _CLOUD + [_P, _P, _P]),
     "pcd_kappa_forward": (_I, _CLOUD + _CLOUD + [_P, _P, _I, _I, _I, _I, _P, _P]),
     "pcd_kappa_backward": (_I, _CLOUD + _CLOUD + [_P, _P, _I, _I, _I, _I, _P, _P, _P]),

@@ -237,13 +237,15 @@ __device__ __noinline__ float warp_kth_bound(float v, int lane, int K) {
 __global__ void knn3_prep_kernel(const float *__restrict__ rows, int64_t r_sb, int64_t r_sp, int64_t r_sc,
                                  const float *__restrict__ cols, int64_t c_sb, int64_t c_sp, int64_t c_sc,
                                  int B, int N, int M, int Npad, int Mpad, int norm_kind, int swap_norms,
-                                 float4 *__restrict__ rowq, float4 *__restrict__ colq, float *__restrict__ colpk) {
+                                 float4 *__restrict__ rowq, float4 *__restrict__ colq, float *__restrict__ colpk,
+                                 int *__restrict__ ovf_cnt) {
     const long long per_b = (long long)Npad + Mpad;
     const long long total = per_b * B;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
          t += (long long)gridDim.x * blockDim.x) {
         const int b = (int)(t / per_b);
         const int p = (int)(t - (long long)b * per_b);
+        if (p == 0 && ovf_cnt) ovf_cnt[b] = 0;           // overflow list of the collect pipeline (was a separate memset)
         const bool is_row = p < Npad;
         const int i = is_row ? p : p - Npad;
         const int n_own = is_row ? N : M;
@@ -1172,7 +1174,8 @@ extern "C" int pcd_knn_forward(const float *rows, int64_t r_sb, int64_t r_sp, in
         float4 *rowq = (float4 *)(ws + L.a), *colq = (float4 *)(ws + L.b);
         float *colpk = (float *)(ws + L.c), *cm = (float *)(ws + L.d), *thr0 = (float *)(ws + L.e);
         knn3_prep_kernel<<<pgrid, 256, 0, st>>>(rows, r_sb, r_sp, r_sc, cols, c_sb, c_sp, c_sc, B, N, M, L.Npad, L.Mpad,
-                                                norm_kind, swap_norms, rowq, colq, colpk);
+                                                norm_kind, swap_norms, rowq, colq, colpk,
+                                                L.prepass ? (int *)(ws + L.ovf_cnt) : nullptr);
         PCD_CUDA_CHECK(cudaGetLastError());
         // strategy (per call; the library reads no environment): 0 = chunk-minima bound + collect + final,
         // 1 = bound + warp-per-row select (no collect pass), 2 = warp-per-row select alone.  Same results.
@@ -1207,7 +1210,6 @@ extern "C" int pcd_knn_forward(const float *rows, int64_t r_sb, int64_t r_sp, in
         if (collect) {
             unsigned long long *cand = (unsigned long long *)(ws + L.cand);
             unsigned int *cnt_g = (unsigned int *)(ws + L.cnt);
-            PCD_CUDA_CHECK(cudaMemsetAsync(ovf_cnt, 0, (size_t)B * 4, st));
             const dim3 cg((L.Npad / (128 * kPreR)) * L.nsplit, B);
             if (form == PCD_FORM_ROW_COL) knn3_collect_kernel<PCD_FORM_ROW_COL><<<cg, 128, 0, st>>>(rowq, (const float4 *)colpk, thr0, B, L.Npad, L.Mpad, M, L.nsplit, L.tps, L.caps, cand, cnt_g);
             else if (form == PCD_FORM_COL_ROW) knn3_collect_kernel<PCD_FORM_COL_ROW><<<cg, 128, 0, st>>>(rowq, (const float4 *)colpk, thr0, B, L.Npad, L.Mpad, M, L.nsplit, L.tps, L.caps, cand, cnt_g);

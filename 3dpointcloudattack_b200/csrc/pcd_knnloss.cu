@@ -30,9 +30,12 @@ __device__ __forceinline__ float block_sum(float v, float *sh) {
 
 __global__ void __launch_bounds__(kLossThreads) knn_outlier_fwd_kernel(const float *__restrict__ dists, int N, int K1, int first, float alpha,
                                                                        float *__restrict__ value, float *__restrict__ mask,
-                                                                       float *__restrict__ loss, float *__restrict__ thr_out) {
+                                                                       float *__restrict__ loss, float *__restrict__ thr_out,
+                                                                       float *__restrict__ zero, size_t nzero_per_sample) {
     __shared__ float sh[kLossThreads / 32];
     const int b = blockIdx.x;
+    if (zero)                                     // this sample's slice of the backward's gradient buffer
+        for (size_t i = threadIdx.x; i < nzero_per_sample; i += kLossThreads) zero[(size_t)b * nzero_per_sample + i] = 0.f;
     const float *d = dists + (size_t)b * N * K1;
     float *val = value + (size_t)b * N, *msk = mask + (size_t)b * N;
     const float k = (float)(K1 - first);
@@ -97,26 +100,27 @@ __global__ void __launch_bounds__(256) knn_outlier_bwd_kernel(const float *__res
 using namespace pcd;
 
 extern "C" int pcd_knn_outlier_forward(const float *dists, int B, int N, int K1, int skip_first, float alpha, float *value, float *mask,
-                                       float *loss, float *threshold, void *stream) {
+                                       float *loss, float *threshold, float *zero_grad, void *stream) {
     if (!dists || !value || !mask || !loss || B <= 0 || N <= 0 || K1 <= 0 || (skip_first ? 1 : 0) >= K1 || B > 2147483647 / 1) {
         set_error("pcd_knn_outlier_forward: bad argument");
         return PCD_ERR_ARG;
     }
-    knn_outlier_fwd_kernel<<<B, kLossThreads, 0, (cudaStream_t)stream>>>(dists, N, K1, skip_first ? 1 : 0, alpha, value, mask, loss, threshold);
+    knn_outlier_fwd_kernel<<<B, kLossThreads, 0, (cudaStream_t)stream>>>(dists, N, K1, skip_first ? 1 : 0, alpha, value, mask, loss, threshold,
+                                                                         zero_grad, (size_t)N * 3);
     PCD_CUDA_CHECK(cudaGetLastError());
     return PCD_OK;
 }
 
 extern "C" int pcd_knn_outlier_backward(const float *pc, int64_t sb, int64_t sp, int64_t sc, const int32_t *idx, const float *mask,
                                         const float *g_loss, int64_t g_stride, int B, int N, int K1, int skip_first, float *grad_pc,
-                                        void *stream) {
+                                        int grad_prezeroed, void *stream) {
     if (!pc || !idx || !mask || !g_loss || !grad_pc || B <= 0 || N <= 0 || K1 <= 0 || (skip_first ? 1 : 0) >= K1) {
         set_error("pcd_knn_outlier_backward: bad argument");
         return PCD_ERR_ARG;
     }
     cudaStream_t st = (cudaStream_t)stream;
     const long long total = (long long)B * N;
-    PCD_CUDA_CHECK(cudaMemsetAsync(grad_pc, 0, (size_t)total * 3 * sizeof(float), st));
+    if (!grad_prezeroed) PCD_CUDA_CHECK(cudaMemsetAsync(grad_pc, 0, (size_t)total * 3 * sizeof(float), st));
     knn_outlier_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(pc, sb, sp, sc, idx, mask, g_loss, g_stride, B, N, K1,
                                                                             skip_first ? 1 : 0, grad_pc);
     PCD_CUDA_CHECK(cudaGetLastError());

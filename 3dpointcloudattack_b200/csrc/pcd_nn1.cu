@@ -1157,11 +1157,16 @@ static cudaError_t launch_fixup_staged_fn(StagedArgs sa, int B, int max_parts, i
         if (e != cudaSuccess) return e;
         attr_set.v[dev] = 1;
     }
-    // residency for this staging size: 1 .. 3 CTAs per SM (register bound 3); the query is cheap next to the launch
-    int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nn1_fixup_staged_kernel<FORM, NORM>, kFixupThreads, smem);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
+    // residency for this staging size: 1 .. 3 CTAs per SM (register bound 3); queried once per (device, size)
+    static PerDeviceInt occ_smem = {}, occ_val = {};
+    if (occ_smem.v[dev] != (int)smem || occ_val.v[dev] == 0) {
+        int o = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, nn1_fixup_staged_kernel<FORM, NORM>, kFixupThreads, smem);
+        if (e != cudaSuccess) return e;
+        occ_val.v[dev] = o < 1 ? 1 : o;
+        occ_smem.v[dev] = (int)smem;
+    }
+    const int per_sm = occ_val.v[dev];
     // slices per sample, split between the sides in proportion to their scan work (32 candidates per row point, R per column point)
     const int urow = (sa.f.N + 31) / 32, ucol = (sa.f.M + 31) / 32;
     int total = sms * per_sm / B;

@@ -441,10 +441,12 @@ class _KnnOutlierLoss(torch.autograd.Function):
             mask = torch.empty((B, N), dtype=torch.float32, device=dev)
             loss = torch.empty((B,), dtype=torch.float32, device=dev)
             thr = torch.empty((B,), dtype=torch.float32, device=dev)
+            grad = torch.empty((B, N, 3), dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
             st = lib.pcd_knn_outlier_forward(dists.data_ptr(), B, N, K1, 1, float(alpha), value.data_ptr(), mask.data_ptr(),
-                                             loss.data_ptr(), thr.data_ptr(), _stream(dev))
+                                             loss.data_ptr(), thr.data_ptr(), _ptr(grad), _stream(dev))
             _lib.check(st, "pcd_knn_outlier_forward")
         _launch_count += 3
+        ctx.zeroed = grad                           # valid for ONE backward
         ctx.save_for_backward(pc, idx, mask)
         ctx.mark_non_differentiable(value, mask, thr)
         return loss, value, mask, thr
@@ -459,11 +461,14 @@ class _KnnOutlierLoss(torch.autograd.Function):
         B, N, _ = pc.shape
         dev = pc.device
         with _on(dev):
-            grad = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
+            grad, ctx.zeroed = ctx.zeroed, None
+            pre = grad is not None
+            if not pre:
+                grad = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
             st = lib.pcd_knn_outlier_backward(*_cloud_args(pc), idx.data_ptr(), mask.data_ptr(), g_loss.data_ptr(), g_loss.stride(0),
-                                              B, N, idx.shape[2], 1, grad.data_ptr(), _stream(dev))
+                                              B, N, idx.shape[2], 1, grad.data_ptr(), int(pre), _stream(dev))
             _lib.check(st, "pcd_knn_outlier_backward")
-        _launch_count += 2
+        _launch_count += 1
         return grad, None, None, None, None, None
 
 

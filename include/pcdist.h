@@ -246,13 +246,16 @@ int pcd_fps(const float *xyz, int64_t sb, int64_t sp, int64_t sc, int B, int N, 
  *   floats), loss [B], threshold [B] (optional).
  * backward: d(sum_b g_loss[b] loss[b]) / d cloud through idx (the comparison is non-differentiable in
  *   both reference variants); g_loss read with element stride g_stride (0 = one broadcast value);
- *   grad_pc [B,N,3] contiguous, written in full; one memset + one kernel, only masked points work.
+ *   grad_pc [B,N,3] contiguous, written in full; ONE kernel when the buffer was cleared by the forward
+ *   (zero_grad / grad_prezeroed), else one memset + one kernel; only masked points do any work.
  * ---------------------------------------------------------------------------------- */
 int pcd_knn_outlier_forward(const float *dists, int B, int N, int K1, int skip_first, float alpha,
-                            float *value, float *mask, float *loss, float *threshold, void *stream);
+                            float *value, float *mask, float *loss, float *threshold,
+                            float *zero_grad /* optional [B,N,3]: cleared on the way for the backward */, void *stream);
 int pcd_knn_outlier_backward(const float *pc, int64_t sb, int64_t sp, int64_t sc, const int32_t *idx,
                              const float *mask, const float *g_loss, int64_t g_stride,
-                             int B, int N, int K1, int skip_first, float *grad_pc, void *stream);
+                             int B, int N, int K1, int skip_first, float *grad_pc,
+                             int grad_prezeroed /* grad_pc was handed to the forward's zero_grad */, void *stream);
 
 /* ------------------------------------------------------------------------------------
  * Local geometry on a k-NN graph (the consumers of the k-NN select in GeoA3 / AOF), each ONE pass

@@ -600,6 +600,36 @@ def test_f4_graph_laplacian_vs_reference():
     np.testing.assert_allclose(npy(e), g["lap_e"], rtol=3e-4, atol=1e-4)
 
 
+def test_launch_counts_of_the_fused_chains():
+    """Device-side launch counts (torch profiler, kernels + memsets issued by this library): the Chamfer+Hausdorff forward is
+    three kernels and its backward one; KNNDist forward + backward is at most eight (k-NN select pipeline, ONE epilogue, ONE backward)."""
+    from torch.profiler import ProfilerActivity, profile
+    g = load_golden("a2_distance_face")
+    p, t = cu(g["preds"], True), cu(g["gts"])
+
+    def count(fn):
+        fn(); torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            fn(); torch.cuda.synchronize()
+        names = [e.name for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+        ours = [n for n in names if "pcd::" in n]
+        return ours, [n for n in names if "Memset" in n or "memset" in n]
+
+    def cd_hd():
+        p.grad = None
+        c1, c2 = pcd.distance.chamfer(p, t); h1, h2 = pcd.distance.hausdorff(p, t)
+        (c1.sum() + c2.sum() + h1.sum() + h2.sum()).backward()
+    ours, memsets = count(cd_hd)
+    assert len(ours) == 4 and not memsets, (ours, memsets)           # arm, sweep, fix-up | backward
+    pc = cu(g["preds"], True)
+
+    def knn_loss():
+        pc.grad = None
+        pcd.dist_utils.KNNDist(k=16, alpha=1.05)(pc, batch_avg=False).sum().backward()
+    ours, memsets = count(knn_loss)
+    assert len(ours) + len(memsets) <= 8, (ours, memsets)
+
+
 # ------------------------------------------------- robustness of the NN-1 chain (ADVICE r1)
 @pytest.mark.parametrize("n", [1024, 1022])          # 1024: streamed raw, 1022: packed through the workspace
 def test_nn1_nan_and_inf_points_do_not_fault(n):
