@@ -52,6 +52,21 @@ class GraphedLoss:
         return self.loss, self.aux, self.grad
 
 
+def tapered_edges(B, chunks):
+    """Slice boundaries of PipelinedLoss: the first slice is two thirds the size of the others (weights 2:3:3:...) --
+    nothing can run until the first upload has landed, so a short first slice starts the kernels earlier (B=32, three
+    slices: 8 + 12 + 12; measured 219 us per step vs 226 us for 10 + 11 + 11)."""
+    chunks = max(1, min(int(chunks), B))
+    w = [2] + [3] * (chunks - 1)
+    tot, acc, edges = sum(w), 0, [0]
+    for c in range(chunks):
+        acc += w[c]
+        e = B if c == chunks - 1 else int(round(B * acc / tot))
+        e = min(max(e, edges[-1] + 1), B - (chunks - 1 - c))       # every slice keeps at least one sample
+        edges.append(e)
+    return edges
+
+
 class PipelinedLoss:
     """Host-to-host step of a per-sample-separable distance loss as ONE CUDA graph with two (or more)
     internal branches: the batch is cut into `chunks` slices, every slice has its own stream inside the
@@ -69,13 +84,19 @@ class PipelinedLoss:
     results are valid after a synchronisation of the current stream.
     """
 
-    def __init__(self, fn, adv_host, ori_host, chunks=2, warmup=3, device=None):
+    def __init__(self, fn, adv_host, ori_host, chunks=2, warmup=3, device=None, slice_sizes=None, prioritize=True):
         if not (adv_host.is_pinned() and ori_host.is_pinned()):
             raise ValueError("PipelinedLoss needs pinned host tensors")
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         B = adv_host.shape[0]
-        chunks = max(1, min(int(chunks), B))
-        edges = [B * c // chunks for c in range(chunks + 1)]
+        if slice_sizes is not None:
+            if sum(slice_sizes) != B or min(slice_sizes) <= 0:
+                raise ValueError("slice_sizes must be positive and sum to the batch size")
+            edges = [0]
+            for s in slice_sizes:
+                edges.append(edges[-1] + int(s))
+        else:
+            edges = tapered_edges(B, chunks)
         self.slices = list(zip(edges[:-1], edges[1:]))
         self.adv_host, self.ori_host = adv_host, ori_host
         self.grad_host = torch.empty_like(adv_host).pin_memory()
@@ -83,7 +104,16 @@ class PipelinedLoss:
         self.ori_dev = [ori_host[lo:hi].to(dev) for lo, hi in self.slices]
         cur = torch.cuda.current_stream(dev)
         main = torch.cuda.Stream(dev)
-        sides = [torch.cuda.Stream(dev) for _ in self.slices]
+        # earlier slices get the higher stream priority: when SM slots free up, the tail of slice c (fix-up,
+        # reductions, backward -- which release its device->host copies) is placed before the sweep of c+1
+        try:
+            lo_pri, hi_pri = torch.cuda.Stream.priority_range()      # (least, greatest), e.g. (0, -5)
+        except Exception:
+            lo_pri, hi_pri = 0, -1
+        n_sl = len(self.slices)
+        sides = [torch.cuda.Stream(dev, priority=(max(hi_pri, lo_pri - (n_sl - 1 - c)) if prioritize else 0))
+                 for c in range(n_sl)]
+        copiers = [torch.cuda.Stream(dev, priority=st.priority) for st in sides]
         aux_shapes = [None] * len(sides)
         for c, st in enumerate(sides):                    # warm-up on the stream the slice will be captured on
             st.wait_stream(cur)
@@ -113,10 +143,16 @@ class PipelinedLoss:
                     prev_h2d = torch.cuda.Event()
                     prev_h2d.record(st)
                     loss, aux = fn(self.adv_dev[c], self.ori_dev[c])
+                    aux = tuple(a.detach() for a in aux)
+                    cp = copiers[c]                                        # forward results leave on a branch of
+                    cp.wait_stream(st)                                     # their own while the backward runs: only
+                    with torch.cuda.stream(cp):                            # the gradient copy trails the kernels
+                        for out, a in zip(self.aux_host[c], aux):
+                            out.copy_(a, non_blocking=True)
+                            a.record_stream(cp)
                     torch.autograd.backward(loss, grad_tensors=self._one.expand_as(loss))
-                    for out, a in zip(self.aux_host[c], aux):
-                        out.copy_(a.detach(), non_blocking=True)
                     self.grad_host[lo:hi].copy_(self.adv_dev[c].grad, non_blocking=True)
+                    st.wait_stream(cp)
             for st in sides:
                 main.wait_stream(st)                                       # join
         self._main = main

@@ -353,9 +353,9 @@ def run_ours(args):
     # ---------------- e2e: pinned host buffers, copies inside the timed region -------------------
     loss_h = torch.empty((4, B), dtype=torch.float32).pin_memory()
     grad_h = torch.empty_like(adv_h).pin_memory()
-    # public API: PipelinedLoss(host adv, host ori).replay() -- ONE graph whose four branches (8 samples each)
+    # public API: PipelinedLoss(host adv, host ori).replay() -- ONE graph whose three branches (8 + 12 + 12 samples)
     # upload, compute and download independently, so the copies overlap the kernels
-    piped = pcd.graph.PipelinedLoss(loss_fn, adv_h, ori_h, chunks=4)
+    piped = pcd.graph.PipelinedLoss(loss_fn, adv_h, ori_h, chunks=3)
     e2e_pipe_ms = []
     for k in range(args.warmup + args.steps):
         flush.zero_()
@@ -481,8 +481,9 @@ def run_ours(args):
                        "timed_step": "CUDA graph replay of forward+backward (captured once, bit-identical to the eager step)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_total_ms / args.steps,
-                    "api": "pcdist.graph.PipelinedLoss(loss_fn, pinned adv, pinned ori, chunks=4).replay(): one CUDA graph, per "
-                           "8-sample slice H2D -> forward+backward -> D2H of the 4 loss vectors and the gradient; slices overlap",
+                    "api": "pcdist.graph.PipelinedLoss(loss_fn, pinned adv, pinned ori, chunks=3).replay(): one CUDA graph, per "
+                           "slice (8 + 12 + 12 samples) H2D -> forward+backward -> D2H of the 4 loss vectors and the gradient; "
+                           "slices overlap, earlier slices on higher-priority streams",
                     "monolithic_ms_per_step": e2e_single_ms,
                     "monolithic_value": pairs_step_rank * world / (e2e_single_ms * 1e-3) / 1e9,
                     "eager_api_ms_per_step": sum(e2e_eager_ms) / len(e2e_eager_ms),

@@ -145,3 +145,18 @@ def test_install_patches_reference_modules():
         sys.path.remove("/root/reference")
         for m in [m for m in sys.modules if m.split(".")[0] in ("attack", "model", "utils")]:
             del sys.modules[m]
+
+
+def test_pipelined_loss_slice_layout():
+    """graph.tapered_edges: slices cover the batch exactly once, every slice is non-empty, the first one is the short one."""
+    g = importlib.import_module("3dpointcloudattack_b200.graph")
+    assert g.tapered_edges(32, 3) == [0, 8, 20, 32]
+    assert g.tapered_edges(32, 1) == [0, 32]
+    for B in (1, 2, 3, 5, 10, 32, 33, 257):
+        for chunks in (1, 2, 3, 4, 8, 300):
+            e = g.tapered_edges(B, chunks)
+            assert e[0] == 0 and e[-1] == B and len(e) == min(chunks, B) + 1
+            sizes = [b - a for a, b in zip(e[:-1], e[1:])]
+            assert min(sizes) >= 1
+            if B >= 4 * chunks:
+                assert sizes[0] == min(sizes)

@@ -1056,8 +1056,8 @@ def test_pipelined_loss_matches_eager():
     a = adv_h.cuda().requires_grad_(True)
     loss, (l_ref,) = loss_fn(a, ori_h.cuda())
     loss.backward()
-    for chunks in (1, 3):
-        p = pcd.graph.PipelinedLoss(loss_fn, adv_h, ori_h, chunks=chunks)
+    for kw in (dict(chunks=1), dict(slice_sizes=[3, 7], prioritize=False), dict(chunks=3)):
+        p = pcd.graph.PipelinedLoss(loss_fn, adv_h, ori_h, **kw)
         for _ in range(2):                                   # replay twice: static buffers, same answer
             aux, grad = p.replay()
             torch.cuda.synchronize()
