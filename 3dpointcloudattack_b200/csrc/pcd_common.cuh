@@ -248,16 +248,13 @@ static inline int num_sms() {
 }
 
 // Opt a kernel in to more than 48 KB of dynamic shared memory ONCE per (kernel, device) and size: the attribute call
-// costs microseconds and the entry points are meant to be allocation- and configuration-free in steady state.
+// costs microseconds and the entry points are meant to be allocation- and configuration-free in steady state.  The memo is
+// keyed by the kernel's ADDRESS (instantiations of one template share their pointer type, so a per-type static would
+// let one instantiation's opt-in stand for another's).
+cudaError_t opt_in_smem_fn(const void *kernel, size_t bytes);     // pcd_nn1.cu
 template <typename K>
 static inline cudaError_t opt_in_smem(K kernel, size_t bytes) {
-    static PerDeviceInt done = {};                 // one instance per kernel type K == per kernel
-    const int dev = current_device();
-    if (dev < 0) return cudaErrorInvalidDevice;
-    if (done.v[dev] >= (int)bytes) return cudaSuccess;
-    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (e == cudaSuccess) done.v[dev] = (int)bytes;
-    return e;
+    return opt_in_smem_fn(reinterpret_cast<const void *>(kernel), bytes);
 }
 
 }  // namespace pcd

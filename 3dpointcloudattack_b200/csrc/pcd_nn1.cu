@@ -28,6 +28,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <mutex>
 #include <type_traits>
 
 #include "pcd_common.cuh"
@@ -45,6 +46,27 @@ void set_error(const char *fmt, ...) {
 int cuda_fail(cudaError_t e, const char *what) {
     set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
     return PCD_ERR_CUDA;
+}
+
+// shared-memory opt-in memo, keyed by (kernel address, device); see pcd_common.cuh
+cudaError_t opt_in_smem_fn(const void *kernel, size_t bytes) {
+    struct Entry { const void *fn; int bytes[64]; };
+    static Entry table[128] = {};
+    static std::mutex mu;
+    const int dev = current_device();
+    if (dev < 0) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lock(mu);
+    Entry *slot = nullptr;
+    for (Entry &e : table) {
+        if (e.fn == kernel || e.fn == nullptr) { slot = &e; break; }
+    }
+    if (slot && slot->fn == kernel && slot->bytes[dev] >= (int)bytes) return cudaSuccess;
+    const cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (err == cudaSuccess && slot) {            // a full table only means the attribute is set again next time
+        slot->fn = kernel;
+        slot->bytes[dev] = (int)bytes;
+    }
+    return err;
 }
 
 // ---------------------------------------------------------------------------------- layout

@@ -16,7 +16,7 @@ from . import _lib
 from ._lib import (EDGE_CENTER, EDGE_DIFF, EDGE_NEIGHBOR, FORM_COL_ROW, FORM_ROW_COL, FORM_SUM_FIRST, NORM_FMA, NORM_MULSUM,
                    VALUE_SQRT_CLAMP, VALUE_SQUARED)
 
-__all__ = ["nn1", "NN1Result", "time_next_sweep", "clear_cache", "knn", "ball_query", "edge_feature", "farthest_point_sample", "fp32_peak_flops",
+__all__ = ["nn1", "NN1Result", "time_next_sweep", "clear_cache", "knn", "ball_query", "edge_feature", "deterministic_edge_backward", "farthest_point_sample", "fp32_peak_flops",
            "local_frames", "kappa", "graph_laplacian", "knn_outlier_loss",
            "EDGE_CENTER", "EDGE_NEIGHBOR", "EDGE_DIFF",
            "FORM_ROW_COL", "FORM_COL_ROW", "FORM_SUM_FIRST", "NORM_MULSUM", "NORM_FMA",
@@ -337,6 +337,19 @@ def ball_query(radius, nsample, xyz, new_xyz):
 
 
 # ------------------------------------------------ k-NN graph edge features, farthest point sampling
+_edge_bwd_gather = False
+
+
+def deterministic_edge_backward(enabled=True):
+    """Select the backward of edge_feature.  False (default): scatter with shared-memory atomics, 3.4 TB/s, summation
+    order not fixed (as the reference's index backward).  True: gather over the inverted graph, the same bits on every
+    run, ~1.8x the time of that kernel (shapes the gather form does not cover -- N > 4096, 4 not dividing N*k -- fall
+    back to the atomics).  Returns the previous setting."""
+    global _edge_bwd_gather
+    prev, _edge_bwd_gather = _edge_bwd_gather, bool(enabled)
+    return prev
+
+
 class _EdgeFeature(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, idx, ops):
@@ -370,10 +383,13 @@ class _EdgeFeature(torch.autograd.Function):
         with _on(dev):
             g = g.contiguous()
             gx = torch.empty((B, C, N), dtype=torch.float32, device=dev)
+            # gather form (inverted graph in a workspace) where the shape allows it, else shared-memory atomics
+            ws_bytes = int(lib.pcd_edge_feature_backward_workspace(B, N, k, len(ops))) if _edge_bwd_gather else 0
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
             st = lib.pcd_edge_feature_backward(g.data_ptr(), idx.data_ptr(), B, C, N, k, len(ops), c_ops,
-                                               gx.data_ptr(), _stream(dev))
+                                               gx.data_ptr(), ws.data_ptr() if ws_bytes else None, ws_bytes, _stream(dev))
             _lib.check(st, "pcd_edge_feature_backward")
-        _launch_count += 1
+        _launch_count += 2 if ws_bytes else 1
         return gx, None, None
 
 

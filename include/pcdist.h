@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define PCD_VERSION 200
+#define PCD_VERSION 201
 
 enum pcd_status {
     PCD_OK = 0,
@@ -216,13 +216,20 @@ int pcd_ball_query(const float *xyz, int64_t x_sb, int64_t x_sp, int64_t x_sc,
  * `ops` is a HOST array of nblocks (1..4) pcd_edge_op values.  The backward accumulates
  * gx[b,c,n] from g [B, nblocks*C, N, k] (own terms plus the scatter through idx); gx is
  * written in full; N <= 51200; g and idx 16-byte aligned.
+ * Backward workspace: with `workspace_bytes >= pcd_edge_feature_backward_workspace(B, N, k, nblocks)` (> 0 for
+ * N <= 4096, 4 | N*k and stages that fit shared memory) the call inverts the graph once per sample and GATHERS:
+ * no floating-point atomics, fixed summation order (bit-reproducible), ~0.8 of the HBM peak.  With workspace NULL
+ * (or a shape the gather form does not cover: the query returns 0) it scatters with shared-memory atomics
+ * (summation order not fixed, as in the reference's index backward).
  * ---------------------------------------------------------------------------------- */
 enum pcd_edge_op { PCD_EDGE_CENTER = 0, PCD_EDGE_NEIGHBOR = 1, PCD_EDGE_DIFF = 2 };
 
 int pcd_edge_feature_forward(const float *x, const int32_t *idx, int B, int C, int N, int k,
                              int nblocks, const int *ops, float *out, void *stream);
+size_t pcd_edge_feature_backward_workspace(int B, int N, int k, int nblocks);
 int pcd_edge_feature_backward(const float *g, const int32_t *idx, int B, int C, int N, int k,
-                              int nblocks, const int *ops, float *gx, void *stream);
+                              int nblocks, const int *ops, float *gx, void *workspace, size_t workspace_bytes,
+                              void *stream);
 
 /* ------------------------------------------------------------------------------------
  * Farthest point sampling.  Replaces the npoint-iteration Python loop of

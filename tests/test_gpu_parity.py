@@ -787,18 +787,72 @@ def test_f_lpfa_group_feature_vs_reference():
     assert rel_inf(g["lpfa9_gx"], npy(xyz.grad)) < RTOL
 
 
+@pytest.mark.parametrize("gather", [True, False])
 @pytest.mark.parametrize("B,C,N,k,ops", [(3, 64, 500, 20, (2, 0)), (2, 5, 1000, 9, (0, 1, 2)), (1, 128, 2048, 20, (2,)),
-                                         (2, 3, 4096, 32, (1, 2, 0, 2)), (2, 1, 33, 4, (2, 0))])
-def test_f_edge_feature_random(B, C, N, k, ops):
+                                         (2, 3, 4096, 32, (1, 2, 0, 2)), (2, 1, 33, 4, (2, 0)), (2, 4, 777, 12, (1,)),
+                                         (1, 2, 4100, 8, (2, 0)), (2, 3, 300, 5, (2, 0)), (1, 2, 64, 128, (0, 2, 1))])
+def test_f_edge_feature_random(B, C, N, k, ops, gather):
+    """Forward bit-exact, backward to RTOL against the oracle, through both backward forms (gather over the inverted
+    graph / shared-memory atomics); shapes cover ragged last chunks, N > 4096 and 4 !| N*k (atomics only), 1..4 blocks."""
     rs = np.random.RandomState(B * 1000 + C)
     x = rs.randn(B, C, N).astype(np.float32)
     idx = rs.randint(0, N, size=(B, N, k))
     xt = cu(x, True)
-    out = F.edge_feature(xt, cu(idx), ops)
-    assert np.array_equal(npy(out), O.edge_feature(x, idx, ops))
-    gw = rs.randn(*out.shape).astype(np.float32)
-    (out * cu(gw)).sum().backward()
+    prev = F.deterministic_edge_backward(gather)
+    try:
+        out = F.edge_feature(xt, cu(idx), ops)
+        assert np.array_equal(npy(out), O.edge_feature(x, idx, ops))
+        gw = rs.randn(*out.shape).astype(np.float32)
+        (out * cu(gw)).sum().backward()
+    finally:
+        F.deterministic_edge_backward(prev)
     assert rel_inf(O.edge_feature_grad(gw, idx, ops, C), npy(xt.grad)) < RTOL
+
+
+def test_f_edge_feature_backward_gather_is_reproducible_and_handles_hubs():
+    """The gather backward has a fixed summation order: two runs are bit-identical (the atomics form is not), also on a
+    graph where every point names the same few neighbours (in-degree N: the per-target lists are as long as a chunk)
+    and with out-of-range indices (clamped, as in the forward)."""
+    rs = np.random.RandomState(5)
+    B, C, N, k = 2, 6, 1500, 20
+    lib = importlib.import_module("3dpointcloudattack_b200._lib").load()
+    assert lib.pcd_edge_feature_backward_workspace(B, N, k, 2) > 0
+    assert lib.pcd_edge_feature_backward_workspace(B, 5000, k, 2) == 0          # N > 4096: atomics form only
+    assert lib.pcd_edge_feature_backward_workspace(B, 33, 5, 2) == 0            # 4 does not divide N*k
+    x = rs.randn(B, C, N).astype(np.float32)
+    hub = np.tile(np.arange(k)[None, None, :], (B, N, 1))                       # every row -> points 0..k-1
+    hub[1, :, 0] = 7                                                            # one column of sample 1 -> a single point
+    wild = rs.randint(-50, N + 50, size=(B, N, k))
+    prev = F.deterministic_edge_backward(True)
+    try:
+        for idx in (rs.randint(0, N, size=(B, N, k)), hub, wild):
+            grads = []
+            for _ in range(2):
+                xt = cu(x, True)
+                out = F.edge_feature(xt, cu(idx), (2, 0))
+                gw = np.random.RandomState(9).randn(*out.shape).astype(np.float32)
+                (out * cu(gw)).sum().backward()
+                grads.append(npy(xt.grad))
+            assert np.array_equal(grads[0], grads[1])
+            assert rel_inf(O.edge_feature_grad(gw, np.clip(idx, 0, N - 1), (2, 0), C), grads[0]) < RTOL
+    finally:
+        F.deterministic_edge_backward(prev)
+
+
+def test_smem_opt_in_is_per_kernel_instantiation():
+    """Kernels that are instantiations of one template share their pointer TYPE; the >48 KB shared-memory opt-in has
+    to be remembered per kernel ADDRESS.  Order that used to fail: the 128 KB instantiation first, then a 64 KB one."""
+    rs = np.random.RandomState(3)
+    big = rs.rand(1, 8000, 3).astype(np.float32)
+    mid = rs.rand(1, 4000, 3).astype(np.float32)
+    for xyz in (big, mid):
+        start = np.zeros(1, np.int64)
+        fps = F.farthest_point_sample(cu(xyz), 8, start=cu(start))
+        assert np.array_equal(npy(fps), O.farthest_point_sample(xyz, 8, start))
+    x = rs.randn(1, 2, 20000).astype(np.float32)                   # 80 KB of staged rows per channel
+    for k in (4, 3):                                               # vectorised instantiation first, scalar one second
+        idx = rs.randint(0, 20000, size=(1, 20000, k))
+        assert np.array_equal(npy(F.edge_feature(cu(x), cu(idx), (2, 0))), O.edge_feature(x, idx, (2, 0)))
 
 
 def test_f_farthest_point_sample_vs_reference():
