@@ -34,6 +34,10 @@ SIGNATURES = {
     "pcd_knn_backward": (_I, _CLOUD + _CLOUD + [_I, _I, _I, _I, _I, _P, _P] + _CLOUD + _CLOUD + [_P]),
     "pcd_ball_query": (_I, _CLOUD + _CLOUD + [_I, _I, _I, _F, _I, _P, _P]),
     "pcd_edge_feature_forward": (_I, [_P, _P, _I, _I, _I, _I, _I, _c.POINTER(_I), _P, _P]),
+    "pcd_clip_points": (_I, [_P, _P, _P, _I, _I, _I, _c.c_float, _P]),
+    "pcd_lp_clip": (_I, [_P, _I, _I, _c.c_float, _P, _P]),
+    "pcd_offset_proj": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
+    "pcd_find_offset": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "pcd_edge_feature_backward_workspace": (_c.c_size_t, [_I, _I, _I, _I]),
     "pcd_edge_feature_backward": (_I, [_P, _P, _I, _I, _I, _I, _I, _c.POINTER(_I), _P, _P, _c.c_size_t, _P]),
     "pcd_fps": (_I, [_P, _L, _L, _L, _I, _I, _I, _P, _P, _P]),

@@ -18,6 +18,8 @@ first, as every victim of the reference does.
 import torch
 import torch.nn as nn
 
+from . import functional as F
+
 
 class UntargetedLogitsAdvLoss(nn.Module):
     """attack/CW/CW_utils/adv_utils.py:52-78 without the hard-coded .cuda(); returns [B] when
@@ -36,7 +38,8 @@ class UntargetedLogitsAdvLoss(nn.Module):
 
 
 class ClipPointsLinf(nn.Module):
-    """attack/CW/CW_utils/dist_utils.py:162-186 (per-point L2 clip of the perturbation), in place."""
+    """attack/CW/CW_utils/clip_utils.py:32-56 (per-point L2 clip of the perturbation), IN PLACE, one launch
+    (functional.clip_points_) instead of the reference's nine elementwise ops; bit-identical to that chain."""
 
     def __init__(self, budget):
         super().__init__()
@@ -44,37 +47,35 @@ class ClipPointsLinf(nn.Module):
 
     @torch.no_grad()
     def forward(self, pc, ori_pc):
-        diff = pc - ori_pc                                   # [B, 3, K]
-        norm = torch.sum(diff ** 2, dim=1) ** 0.5
-        scale = torch.clamp(self.budget / (norm + 1e-9), max=1.)
-        pc.copy_(ori_pc + diff * scale[:, None, :])
-        return pc
+        return F.clip_points_(pc, ori_pc, self.budget, F.CLIP_LINF)
+
+
+class ClipPointsL2(nn.Module):
+    """attack/CW/CW_utils/clip_utils.py:5-29 (one scale per sample), IN PLACE, one launch."""
+
+    def __init__(self, budget):
+        super().__init__()
+        self.budget = budget
+
+    @torch.no_grad()
+    def forward(self, pc, ori_pc):
+        return F.clip_points_(pc, ori_pc, self.budget, F.CLIP_L2)
 
 
 class ProjectInnerClipLinf(nn.Module):
     """attack/CW/CW_utils/clip_utils.py:59-136: points pushed inside the surface (negative offset
-    along the normal) are projected back onto it, then the per-point L2 clip; in place, batch safe
-    (the reference's dim-less torch.cross picks the wrong axis for B == 3)."""
+    along the normal) are projected back onto it, then the per-point L2 clip; IN PLACE, one launch, batch safe
+    (the reference's dim-less torch.cross picks the wrong axis for B == 3).  normal=None: the clip alone."""
 
     def __init__(self, budget):
         super().__init__()
-        self.clip_linf = ClipPointsLinf(budget)
+        self.budget = budget
 
     @torch.no_grad()
     def forward(self, pc, ori_pc, normal=None):
-        if normal is not None:
-            diff = pc - ori_pc
-            inner = torch.sum(diff * normal, dim=1) < 0.                      # [B, K]
-            vng = torch.cross(normal, diff, dim=1)
-            vng_norm = torch.sum(vng ** 2, dim=1) ** 0.5
-            vref = torch.cross(vng, normal, dim=1)
-            vref_norm = torch.sum(vref ** 2, dim=1) ** 0.5
-            diff_proj = diff * vref / (vref_norm[:, None, :] + 1e-9)
-            opposite = inner & (vng_norm < 1e-6)
-            diff_proj = torch.where(opposite[:, None, :], torch.zeros_like(diff_proj), diff_proj)
-            diff = torch.where(inner[:, None, :], diff_proj, diff)
-            pc.copy_(ori_pc + diff)
-        return self.clip_linf(pc, ori_pc)
+        if normal is None:
+            return F.clip_points_(pc, ori_pc, self.budget, F.CLIP_LINF)
+        return F.clip_points_(pc, ori_pc, self.budget, F.CLIP_PROJECT_LINF, normal=normal)
 
 
 class CWAttack:

@@ -16,7 +16,7 @@ from . import _lib
 from ._lib import (EDGE_CENTER, EDGE_DIFF, EDGE_NEIGHBOR, FORM_COL_ROW, FORM_ROW_COL, FORM_SUM_FIRST, NORM_FMA, NORM_MULSUM,
                    VALUE_SQRT_CLAMP, VALUE_SQUARED)
 
-__all__ = ["nn1", "NN1Result", "time_next_sweep", "clear_cache", "knn", "ball_query", "edge_feature", "deterministic_edge_backward", "farthest_point_sample", "fp32_peak_flops",
+__all__ = ["nn1", "NN1Result", "time_next_sweep", "clear_cache", "knn", "ball_query", "edge_feature", "deterministic_edge_backward", "clip_points_", "lp_clip", "offset_proj", "find_offset", "farthest_point_sample", "fp32_peak_flops",
            "local_frames", "kappa", "graph_laplacian", "knn_outlier_loss",
            "EDGE_CENTER", "EDGE_NEIGHBOR", "EDGE_DIFF",
            "FORM_ROW_COL", "FORM_COL_ROW", "FORM_SUM_FIRST", "NORM_MULSUM", "NORM_FMA",
@@ -621,3 +621,85 @@ def fp32_peak_flops(iters=2048):
             if rep:
                 best = max(best, flop.value / (e0.elapsed_time(e1) * 1e-3))
     return best
+
+
+# ------------------------------------------------ projection / clipping epilogues of the attack loops
+CLIP_LINF, CLIP_PROJECT_LINF, CLIP_L2 = 0, 1, 2
+
+
+def _check_cf(t, name):
+    """channel-first contiguous fp32 CUDA cloud [B,3,K]"""
+    if not isinstance(t, torch.Tensor) or t.dim() != 3 or t.shape[1] != 3:
+        raise ValueError(f"{name} must be a [B, 3, K] tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} is on {t.device}: this path runs on CUDA only (no CPU fallback)")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+
+
+def clip_points_(pc, ori, budget, mode=CLIP_LINF, normal=None):
+    """IN PLACE clip of the perturbation pc - ori (pcd_clip_points in include/pcdist.h): CLIP_LINF = ClipPointsLinf,
+    CLIP_PROJECT_LINF = ProjectInnerClipLinf (needs normal), CLIP_L2 = ClipPointsL2 (clip_utils.py:5-136).
+    pc, ori, normal: [B,3,K] fp32 contiguous.  Returns pc.  Not differentiable (the reference clips under no_grad)."""
+    global _launch_count
+    _check_cf(pc, "pc"); _check_cf(ori, "ori")
+    if ori.shape != pc.shape or ori.device != pc.device:
+        raise ValueError("pc and ori must have the same shape and device")
+    if mode == CLIP_PROJECT_LINF:
+        if normal is None:
+            raise ValueError("CLIP_PROJECT_LINF needs the normals")
+        _check_cf(normal, "normal")
+        if normal.shape != pc.shape or normal.device != pc.device:
+            raise ValueError("normal must match pc")
+    lib = _lib.load()
+    B, _, K = pc.shape
+    with _on(pc.device):
+        st = lib.pcd_clip_points(pc.data_ptr(), ori.data_ptr(), _ptr(normal) if mode == CLIP_PROJECT_LINF else None, B, K,
+                                 int(mode), float(budget), _stream(pc.device))
+        _lib.check(st, "pcd_clip_points")
+    _launch_count += 1
+    return pc
+
+
+def lp_clip(offset, cc_linf):
+    """attack/GeoA3/GeoA3_attack.py:92-101 as one launch (pcd_lp_clip): offset [B,3,K] -> clipped copy.  No gradient."""
+    global _launch_count
+    _check_cf(offset, "offset")
+    lib = _lib.load()
+    B, _, K = offset.shape
+    with _on(offset.device):
+        out = torch.empty_like(offset)
+        st = lib.pcd_lp_clip(offset.data_ptr(), B, K, float(cc_linf), out.data_ptr(), _stream(offset.device))
+        _lib.check(st, "pcd_lp_clip")
+    _launch_count += 1
+    return out
+
+
+def _offset_gather(fn_name, a, table, idx):
+    global _launch_count
+    _check_cf(a, "offset"); _check_cf(table, "table")
+    B, _, K = a.shape
+    M = table.shape[2]
+    idx32 = _idx32(idx, a.device).reshape(B, -1)
+    if table.shape[0] != B or idx32.shape[1] != K or table.device != a.device:
+        raise ValueError(f"shapes do not match: {tuple(a.shape)}, {tuple(table.shape)}, idx {tuple(idx.shape)}")
+    lib = _lib.load()
+    with _on(a.device):
+        out = torch.empty_like(a)
+        st = getattr(lib, fn_name)(a.data_ptr(), table.data_ptr(), idx32.data_ptr(), B, K, M, out.data_ptr(), _stream(a.device))
+        _lib.check(st, fn_name)
+    _launch_count += 1
+    return out
+
+
+def offset_proj(offset, ori_normal, idx):
+    """GeoA3_attack.py:62-81 after its knn_points(K=1) (pcd_offset_proj): offset [B,3,K], ori_normal [B,3,M],
+    idx [B,K] or [B,K,1] integer (nearest original point) -> projected offsets [B,3,K].  No gradient."""
+    return _offset_gather("pcd_offset_proj", offset, ori_normal, idx)
+
+
+def find_offset(adv, ori, idx):
+    """GeoA3_attack.py:83-89 after its knn_points(K=1) (pcd_find_offset): adv - ori[:, :, idx].  No gradient."""
+    return _offset_gather("pcd_find_offset", adv, ori, idx)

@@ -24,36 +24,28 @@ to the OFFSET vector itself, :68).
 import torch
 
 from . import functional as F
-from .knn_utils import knn_gather, knn_points
+from .knn_utils import knn_points
 from .loss_utils import (_get_kappa_adv, _get_kappa_ori, chamfer_loss, curvature_loss, hausdorff_loss, norm_l2_loss,
                          pseudo_chamfer_loss)
 from .utility import estimate_normal
 
 
 def offset_proj(offset, ori_pc, ori_normal, project='dir'):
-    """GeoA3_attack.py:62-81: project every offset onto the normal of its nearest original point."""
+    """GeoA3_attack.py:62-81: project every offset onto the normal of its nearest original point (the K=1 select, then
+    ONE launch for gather + normalise + project: functional.offset_proj)."""
     intra_KNN = knn_points(offset.permute(0, 2, 1), ori_pc.permute(0, 2, 1), K=1)
-    normal = knn_gather(ori_normal.permute(0, 2, 1), intra_KNN.idx).permute(0, 3, 1, 2).squeeze(3).contiguous()
-    normal_len = (normal ** 2).sum(1, keepdim=True).sqrt()
-    normal_len_expand = normal_len.expand_as(offset)
-    return (offset * normal / (normal_len_expand + 1e-6)).sum(1, keepdim=True) * normal / (normal_len_expand + 1e-6)
+    return F.offset_proj(offset.contiguous(), ori_normal.contiguous(), intra_KNN.idx)
 
 
 def find_offset(ori_pc, adv_pc):
-    """GeoA3_attack.py:83-89."""
+    """GeoA3_attack.py:83-89: adv - (nearest original point), the K=1 select + one launch."""
     intra_KNN = knn_points(adv_pc.permute(0, 2, 1), ori_pc.permute(0, 2, 1), K=1)
-    knn_pc = knn_gather(ori_pc.permute(0, 2, 1), intra_KNN.idx).permute(0, 3, 1, 2).squeeze(3).contiguous()
-    return adv_pc - knn_pc
+    return F.find_offset(adv_pc.contiguous(), ori_pc.contiguous(), intra_KNN.idx)
 
 
 def lp_clip(offset, cc_linf):
-    """GeoA3_attack.py:92-101: per-point L2 clip of the offset to cc_linf."""
-    lengths = (offset ** 2).sum(1, keepdim=True).sqrt()
-    lengths_expand = lengths.expand_as(offset)
-    condition = lengths > 1e-6
-    offset_scaled = torch.where(condition, offset / lengths_expand * cc_linf, torch.zeros_like(offset))
-    condition = lengths < cc_linf
-    return torch.where(condition, offset, offset_scaled)
+    """GeoA3_attack.py:92-101: per-point L2 clip of the offset to cc_linf (one launch, bit-identical to the torch chain)."""
+    return F.lp_clip(offset.contiguous(), cc_linf)
 
 
 class GeoA3Attack:

@@ -304,6 +304,33 @@ int pcd_graph_laplacian(const float *pc, int64_t sb, int64_t sp, int64_t sc, con
                         int B, int N, int K, float *L, void *stream);
 
 /* ------------------------------------------------------------------------------------
+ * Projection / clipping epilogues of the attack loops, one launch each instead of the
+ * reference's chains of 8-25 elementwise torch ops; same fp32 operations in the same order.  All tensors are
+ * channel-first contiguous [B,3,K] fp32 (as the attack loops hold them).
+ * pcd_clip_points   in place on pc:
+ *     PCD_CLIP_LINF          attack/CW/CW_utils/clip_utils.py:32-56   ClipPointsLinf: every point's offset from ori is
+ *                            scaled by min(budget / (|offset| + 1e-9), 1)                        (bit-identical to torch)
+ *     PCD_CLIP_PROJECT_LINF  clip_utils.py:59-136  ProjectInnerClipLinf: points with offset . normal < 0 are projected
+ *                            (ProjectInnerPoints, normal [B,3,K] required), then PCD_CLIP_LINF
+ *     PCD_CLIP_L2            clip_utils.py:5-29    ClipPointsL2: one scale per sample from the norm of the whole
+ *                            perturbation (the 3K-term sum is in a fixed tree order: ~1e-7 from torch's, not bit-equal)
+ * pcd_lp_clip       attack/GeoA3/GeoA3_attack.py:92-101: offsets longer than cc_linf are rescaled to cc_linf.
+ * pcd_offset_proj   GeoA3_attack.py:62-81 after its knn_points(offset, ori_pc, K=1): idx [B,K] int32 = nearest original
+ *                   point; out = the offset's component along that point's normalised normal (ori_normal [B,3,M]).
+ * pcd_find_offset   GeoA3_attack.py:83-89 after its knn_points(adv_pc, ori_pc, K=1): out = adv - ori[:, :, idx].
+ * Indices outside [0,M) are clamped.  out may alias the first input.
+ * ---------------------------------------------------------------------------------- */
+enum pcd_clip_mode { PCD_CLIP_LINF = 0, PCD_CLIP_PROJECT_LINF = 1, PCD_CLIP_L2 = 2 };
+
+int pcd_clip_points(float *pc, const float *ori, const float *normal, int B, int K, int mode, float budget,
+                    void *stream);
+int pcd_lp_clip(const float *offset, int B, int K, float cc_linf, float *out, void *stream);
+int pcd_offset_proj(const float *offset, const float *ori_normal, const int32_t *idx, int B, int K, int M,
+                    float *out, void *stream);
+int pcd_find_offset(const float *adv, const float *ori, const int32_t *idx, int B, int K, int M, float *out,
+                    void *stream);
+
+/* ------------------------------------------------------------------------------------
  * Measurement helper (bench.py): launches ONE FFMA-only probe kernel on `stream` (variant 0 =
  * scalar FFMA, 1 = packed FFMA2) and stores the number of FLOPs that launch performs in
  * *flop_count (HOST pointer).  The caller times it with its own CUDA events: achieved FLOP/s =

@@ -350,9 +350,38 @@ def geoa3_loop():
     save("l4_geoa3_loop", **out)
 
 
+def clips():
+    """f-1 epilogues (added in round 2): the reference's clip / projection functions, unmodified, on CPU.
+    attack/CW/CW_utils/clip_utils.py:5-136 and attack/GeoA3/GeoA3_attack.py:62-101 (module import as in geoa3_loop)."""
+    sys.path.insert(0, os.path.join(REF, "attack", "GeoA3"))
+    torch.symeig = lambda A, eigenvectors=False, upper=True: torch.linalg.eigh(A, UPLO="U" if upper else "L")
+    from attack.CW.CW_utils import clip_utils as CU
+    from attack.GeoA3 import GeoA3_attack as GA
+    rs = np.random.RandomState(77)
+    ori = np.ascontiguousarray(np.stack([face_fixture(256, 11), face_fixture(256, 12)]).transpose(0, 2, 1))     # [2,3,256]
+    normal = ori - ori.mean(2, keepdims=True) + 0.05 * rs.randn(*ori.shape).astype(np.float32)                  # not unit length
+    normal = np.ascontiguousarray(normal.astype(np.float32))
+    adv = (ori + 0.03 * rs.randn(*ori.shape)).astype(np.float32)
+    adv[0, :, :4] = ori[0, :, :4]                                                    # untouched points
+    adv[1, :, 5:9] = ori[1, :, 5:9] - np.float32(0.01) * normal[1, :, 5:9]           # pushed straight inside: the "opposite" branch
+    adv[1, :, 9:12] = ori[1, :, 9:12] + np.float32(1e-8)                             # shorter than every epsilon
+    out = dict(ori=ori, adv=adv, normal=normal)
+    out["linf"] = n(CU.ClipPointsLinf(budget=0.03)(t(adv), t(ori)))
+    out["l2"] = n(CU.ClipPointsL2(budget=0.5)(t(adv), t(ori)))
+    out["project_linf"] = n(CU.ProjectInnerClipLinf(budget=0.03)(t(adv), t(ori), t(normal)))
+    off = adv - ori
+    out["lp_clip"] = n(GA.lp_clip(t(off), 0.02))
+    out["offset_proj"] = n(GA.offset_proj(t(off), t(ori), t(normal)))
+    out["find_offset"] = n(GA.find_offset(t(ori), t(adv)))
+    save("f1_clips", **out)
+
+
 def main():
     torch.set_num_threads(1)
     _prepare_reference()
+    if "--clips" in sys.argv:          # f-1 clip / projection epilogues (added in round 2)
+        clips()
+        return
     if "--geoa3" in sys.argv:          # the reference's GeoA3 loop at B = 1 (added in round 2)
         geoa3_loop()
         return

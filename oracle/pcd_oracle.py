@@ -502,3 +502,85 @@ def graph_laplacian(pc_pm, idx):
         A = np.where(mask, A, np.float32(0))
         L[b] = np.diag(A.sum(1, dtype=np.float64).astype(np.float32)) - A
     return L
+
+
+# ------------------------------------- f-1 epilogues: clip_utils.py:5-136, GeoA3_attack.py:62-101
+# numpy float32 arithmetic rounds every operation on its own (no contraction), which is the contract of the kernels.
+_F = np.float32
+
+
+def _sumsq3(d):                      # torch.sum(d ** 2, dim=1) on [B,3,K]: (x*x + y*y) + z*z
+    return (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+
+
+def _clip_scale(norm, budget):       # clamp(budget / (norm + 1e-9), max=1); scalar / tensor = reciprocal(tensor) * scalar
+    s = (_F(1.0) / (norm + _F(1e-9))) * _F(budget)
+    return np.where(s > _F(1.0), _F(1.0), s).astype(np.float32)
+
+
+def clip_points_linf(pc, ori, budget):
+    """attack/CW/CW_utils/clip_utils.py:32-56, pc/ori [B,3,K]."""
+    pc, ori = _f32(pc), _f32(ori)
+    d = pc - ori
+    with np.errstate(all="ignore"):
+        s = _clip_scale(np.sqrt(_sumsq3(d)), budget)
+    return ori + d * s[:, None, :]
+
+
+def clip_points_l2(pc, ori, budget):
+    """clip_utils.py:5-29 (the 3K-term sum in float32 pairwise order: agrees with torch / the kernel to rounding only)."""
+    pc, ori = _f32(pc), _f32(ori)
+    d = pc - ori
+    norm = np.sqrt((d * d).reshape(d.shape[0], -1).sum(1, dtype=np.float32))
+    return ori + d * _clip_scale(norm, budget)[:, None, None]
+
+
+def _cross3(a, b):                   # torch.cross(a, b, dim=1)
+    return np.stack([a[:, 1] * b[:, 2] - a[:, 2] * b[:, 1], a[:, 2] * b[:, 0] - a[:, 0] * b[:, 2],
+                     a[:, 0] * b[:, 1] - a[:, 1] * b[:, 0]], 1)
+
+
+def project_inner_clip_linf(pc, ori, normal, budget):
+    """clip_utils.py:59-136 (ProjectInnerPoints, then ClipPointsLinf)."""
+    pc, ori, normal = _f32(pc), _f32(ori), _f32(normal)
+    d = pc - ori
+    inner = ((d[:, 0] * normal[:, 0] + d[:, 1] * normal[:, 1]) + d[:, 2] * normal[:, 2]) < 0
+    vng = _cross3(normal, d)
+    vng_norm = np.sqrt(_sumsq3(vng))
+    vref = _cross3(vng, normal)
+    proj = d * vref / (np.sqrt(_sumsq3(vref)) + _F(1e-9))[:, None, :]
+    proj = np.where((inner & (vng_norm < _F(1e-6)))[:, None, :], _F(0), proj)
+    d = np.where(inner[:, None, :], proj, d).astype(np.float32)
+    return clip_points_linf(ori + d, ori, budget)
+
+
+def lp_clip(offset, cc_linf):
+    """attack/GeoA3/GeoA3_attack.py:92-101."""
+    o = _f32(offset)
+    ln = np.sqrt(_sumsq3(o))[:, None, :]
+    with np.errstate(all="ignore"):
+        scaled = np.where(ln > _F(1e-6), o / ln * _F(cc_linf), _F(0))
+    return np.where(ln < _F(cc_linf), o, scaled).astype(np.float32)
+
+
+def _nearest_ori(q_cf, ori_cf):
+    """the K=1 knn_points of GeoA3_attack.py:68 / :84 on channel-first clouds -> idx [B,K]"""
+    return knn_points(np.ascontiguousarray(q_cf.transpose(0, 2, 1)), np.ascontiguousarray(ori_cf.transpose(0, 2, 1)), K=1)[1][:, :, 0]
+
+
+def offset_proj(offset, ori_pc, ori_normal, idx=None):
+    """GeoA3_attack.py:62-81 (channel-first [B,3,K]); idx = the K=1 neighbour of every offset among ori_pc."""
+    o, nrm = _f32(offset), _f32(ori_normal)
+    idx = _nearest_ori(o, _f32(ori_pc)) if idx is None else np.asarray(idx)
+    g = np.take_along_axis(nrm, idx[:, None, :].repeat(3, 1), 2)
+    t = (np.sqrt(_sumsq3(g)) + _F(1e-6))[:, None, :]
+    a = o * g / t
+    dot = ((a[:, 0] + a[:, 1]) + a[:, 2])[:, None, :]
+    return (dot * g / t).astype(np.float32)
+
+
+def find_offset(ori_pc, adv_pc, idx=None):
+    """GeoA3_attack.py:83-89."""
+    ori, adv = _f32(ori_pc), _f32(adv_pc)
+    idx = _nearest_ori(adv, ori) if idx is None else np.asarray(idx)
+    return adv - np.take_along_axis(ori, idx[:, None, :].repeat(3, 1), 2)

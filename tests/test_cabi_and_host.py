@@ -81,17 +81,19 @@ def test_no_cpu_fallback():
         pcd.geoa3_loop.GeoA3Attack(torch.nn.Identity(), classes=3).attack(a, torch.zeros(1))
 
 
-def test_geoa3_lp_clip_matches_the_reference_formula():
-    """attack/GeoA3/GeoA3_attack.py:92-101 (pure torch, runs on CPU): offsets longer than cc_linf are scaled onto the ball,
-    shorter ones pass, (near-)zero ones stay zero."""
-    torch.manual_seed(0)
-    off = torch.randn(2, 3, 50) * 0.05
-    off[0, :, 3] = 0.0
-    out = pcd.geoa3_loop.lp_clip(off, 0.02)
-    ln = off.norm(dim=1, keepdim=True)
-    ref = torch.where(ln < 0.02, off, torch.where(ln > 1e-6, off / ln * 0.02, torch.zeros_like(off)))
-    assert torch.equal(out, ref)
-    assert float(out.norm(dim=1).max()) <= 0.02 * (1 + 1e-6) and float(out[0, :, 3].abs().max()) == 0.0
+def test_clip_epilogues_have_no_cpu_fallback():
+    """The fused clip / projection epilogues (functional.clip_points_, lp_clip, offset_proj, find_offset and the loop-level
+    wrappers) refuse CPU tensors like every other entry of the path."""
+    a = torch.zeros(1, 3, 8)
+    for call in (lambda: pcd.functional.clip_points_(a, a, 0.1), lambda: pcd.functional.lp_clip(a, 0.1),
+                 lambda: pcd.geoa3_loop.lp_clip(a, 0.1), lambda: pcd.cw_loop.ClipPointsLinf(0.1)(a, a),
+                 lambda: pcd.cw_loop.ClipPointsL2(0.1)(a, a), lambda: pcd.cw_loop.ProjectInnerClipLinf(0.1)(a, a, a),
+                 lambda: pcd.functional.offset_proj(a, a, torch.zeros(1, 8, dtype=torch.long)),
+                 lambda: pcd.functional.find_offset(a, a, torch.zeros(1, 8, dtype=torch.long))):
+        with pytest.raises(RuntimeError, match="CUDA only"):
+            call()
+    with pytest.raises(ValueError):
+        pcd.functional.clip_points_(torch.zeros(1, 8, 3), torch.zeros(1, 8, 3), 0.1)      # not channel-first
 
 
 def test_product_never_imports_the_oracle():

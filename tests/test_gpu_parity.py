@@ -839,6 +839,97 @@ def test_f_edge_feature_backward_gather_is_reproducible_and_handles_hubs():
         F.deterministic_edge_backward(prev)
 
 
+# ------------------------------------------------------------- f-1: fused clip / projection epilogues
+def _torch_clip_chains(adv, ori, normal, budget, cc):
+    """the reference's op chains (clip_utils.py:22-29, :50-56, :78-109; GeoA3_attack.py:92-101) on whatever device the
+    tensors are on, with dim=1 spelled out for torch.cross"""
+    d = adv - ori
+    linf = ori + d * torch.clamp(budget / (torch.sum(d ** 2, dim=1) ** 0.5 + 1e-9), max=1.)[:, None, :]
+    l2 = ori + d * torch.clamp(budget / (torch.sum(d ** 2, dim=[1, 2]) ** 0.5 + 1e-9), max=1.)[:, None, None]
+    inner = torch.sum(d * normal, dim=1) < 0.
+    vng = torch.cross(normal, d, dim=1)
+    vref = torch.cross(vng, normal, dim=1)
+    proj = d * vref / (torch.sum(vref ** 2, dim=1) ** 0.5 + 1e-9)[:, None, :]
+    proj = torch.where((inner & (torch.sum(vng ** 2, dim=1) ** 0.5 < 1e-6))[:, None, :], torch.zeros_like(proj), proj)
+    p1 = ori + torch.where(inner[:, None, :], proj, d)
+    d1 = p1 - ori
+    project_linf = ori + d1 * torch.clamp(budget / (torch.sum(d1 ** 2, dim=1) ** 0.5 + 1e-9), max=1.)[:, None, :]
+    ln = (d ** 2).sum(1, keepdim=True).sqrt()
+    lp = torch.where(ln < cc, d, torch.where(ln > 1e-6, d / ln.expand_as(d) * cc, torch.zeros_like(d)))
+    return linf, l2, project_linf, lp
+
+
+def test_f1_clip_epilogues_vs_oracle_torch_and_reference():
+    """One-launch clip / projection epilogues: bit-identical to the oracle (which is pinned on the reference's CPU outputs
+    in tests/test_oracle_golden.py); against the reference's golden to 2 ulp of the largest coordinate; against the same
+    torch chain run on THIS GPU bit-identical for the per-point clips (ClipPointsLinf, lp_clip, find_offset)."""
+    g = load_golden("f1_clips")
+    ori, adv, normal = g["ori"], g["adv"], g["normal"]
+    off = adv - ori
+    eps2 = 2 * np.finfo(np.float32).eps
+
+    def close(ours, ref):
+        return np.abs(ours - ref).max() <= eps2 * np.abs(ref).max()
+
+    ours = {
+        "linf": npy(F.clip_points_(cu(adv), cu(ori), 0.03, F.CLIP_LINF)),
+        "l2": npy(F.clip_points_(cu(adv), cu(ori), 0.5, F.CLIP_L2)),
+        "project_linf": npy(F.clip_points_(cu(adv), cu(ori), 0.03, F.CLIP_PROJECT_LINF, normal=cu(normal))),
+        "lp_clip": npy(pcd.geoa3_loop.lp_clip(cu(off), 0.02)),
+        "offset_proj": npy(pcd.geoa3_loop.offset_proj(cu(off), cu(ori), cu(normal))),
+        "find_offset": npy(pcd.geoa3_loop.find_offset(cu(ori), cu(adv))),
+    }
+    assert np.array_equal(ours["linf"], O.clip_points_linf(adv, ori, 0.03))
+    assert np.array_equal(ours["project_linf"], O.project_inner_clip_linf(adv, ori, normal, 0.03))
+    assert close(ours["l2"], O.clip_points_l2(adv, ori, 0.5))                  # the 3K-term sum: order differs
+    assert np.array_equal(ours["lp_clip"], O.lp_clip(off, 0.02))
+    assert np.array_equal(ours["offset_proj"], O.offset_proj(off, ori, normal))
+    assert np.array_equal(ours["find_offset"], O.find_offset(ori, adv))
+    for k, v in ours.items():
+        assert close(v, g[k]), k
+    t_linf, t_l2, t_proj, t_lp = (npy(x) for x in _torch_clip_chains(cu(adv), cu(ori), cu(normal), 0.03, 0.02))
+    assert np.array_equal(ours["linf"], t_linf) and np.array_equal(ours["lp_clip"], t_lp)
+    assert close(ours["project_linf"], t_proj)                                  # torch.cross contracts its products into FMAs
+    assert close(npy(F.clip_points_(cu(adv), cu(ori), 0.03, F.CLIP_L2)), npy(_torch_clip_chains(cu(adv), cu(ori), cu(normal), 0.03, 0.02)[1]))
+    # the module-level wrappers the loops call are the same kernels, in place
+    a = cu(adv)
+    assert pcd.cw_loop.ClipPointsLinf(0.03)(a, cu(ori)) is a and np.array_equal(npy(a), ours["linf"])
+    a = cu(adv)
+    pcd.cw_loop.ProjectInnerClipLinf(0.03)(a, cu(ori), cu(normal))
+    assert np.array_equal(npy(a), ours["project_linf"])
+    a = cu(adv)
+    pcd.cw_loop.ProjectInnerClipLinf(0.03)(a, cu(ori))                          # no normals: the clip alone
+    assert np.array_equal(npy(a), ours["linf"])
+
+
+@pytest.mark.parametrize("B,K", [(1, 1), (3, 257), (32, 1024), (2, 5000)])
+def test_f1_clip_epilogues_random_and_degenerate(B, K):
+    """Random clouds with NaN / inf / zero offsets planted: kernel == oracle bit for bit (NaN positions included)."""
+    rs = np.random.RandomState(B * 7 + K)
+    ori = rs.randn(B, 3, K).astype(np.float32)
+    adv = (ori + 0.05 * rs.randn(B, 3, K)).astype(np.float32)
+    normal = rs.randn(B, 3, K).astype(np.float32)
+    if K > 8:
+        adv[0, :, 1] = ori[0, :, 1]
+        adv[0, 0, 2] = np.nan
+        adv[0, 1, 3] = np.inf
+        normal[0, :, 4] = 0.0
+        adv[0, :, 5] = ori[0, :, 5] - 0.01 * normal[0, :, 5]
+    off = adv - ori
+    with np.errstate(all="ignore"):
+        assert np.array_equal(npy(F.clip_points_(cu(adv), cu(ori), 0.04)), O.clip_points_linf(adv, ori, 0.04), equal_nan=True)
+        assert np.array_equal(npy(F.clip_points_(cu(adv), cu(ori), 0.04, F.CLIP_PROJECT_LINF, normal=cu(normal))),
+                              O.project_inner_clip_linf(adv, ori, normal, 0.04), equal_nan=True)
+        assert np.array_equal(npy(F.lp_clip(cu(off), 0.03)), O.lp_clip(off, 0.03), equal_nan=True)
+        idx = rs.randint(0, K, size=(B, K))
+        assert np.array_equal(npy(F.offset_proj(cu(off), cu(normal), cu(idx))), O.offset_proj(off, ori, normal, idx), equal_nan=True)
+        assert np.array_equal(npy(F.find_offset(cu(adv), cu(ori), cu(idx))), O.find_offset(ori, adv, idx), equal_nan=True)
+        fin = np.isfinite(adv).all((1, 2))
+        l2 = npy(F.clip_points_(cu(adv), cu(ori), 0.5, F.CLIP_L2))
+        ref = O.clip_points_l2(adv, ori, 0.5)
+        assert np.abs(l2[fin] - ref[fin]).max() <= 4 * np.finfo(np.float32).eps * np.abs(ref[fin]).max() if fin.any() else True
+
+
 def test_smem_opt_in_is_per_kernel_instantiation():
     """Kernels that are instantiations of one template share their pointer TYPE; the >48 KB shared-memory opt-in has
     to be remembered per kernel ADDRESS.  Order that used to fail: the 128 KB instantiation first, then a 64 KB one."""

@@ -247,3 +247,29 @@ def test_f4_local_geometry_oracle_vs_reference():
     L = O.graph_laplacian(O._cf_to_pm(small), O.dgcnn_knn(small, 30))
     np.testing.assert_allclose(L, g["lap_L"], rtol=0, atol=1e-5)
     assert ((L != 0) == (g["lap_L"] != 0)).all()                            # identical sparsity: same symmetrised graph
+
+
+def test_f1_clip_epilogues():
+    """oracle restatements of clip_utils.py:5-136 and GeoA3_attack.py:62-101 vs the reference's own CPU outputs
+    (oracle/make_golden.py --clips).  The bar is 2 ulp of the largest coordinate, not bit equality, because torch's CPU
+    kernels are not a bit-level specification: its vectorised sqrt is not correctly rounded (3 of 512 lengths of the
+    fixture are one ulp off the IEEE result numpy and sqrt.rn give), its cross product is compiled with FMA contraction,
+    tensor * python-scalar may multiply in double, and ClipPointsL2's 3K-term sum has an order of its own.  The kernels
+    are held bit-for-bit to THIS oracle (tests/test_gpu_parity.py) and to torch's own GPU chain where that is exact."""
+    g = load_golden("f1_clips")
+    ori, adv, normal = g["ori"], g["adv"], g["normal"]
+    off = adv - ori
+
+    def close(ours, ref):
+        return np.abs(ours - ref).max() <= 2 * np.finfo(np.float32).eps * np.abs(ref).max()
+
+    assert close(O.clip_points_linf(adv, ori, 0.03), g["linf"])
+    assert close(O.project_inner_clip_linf(adv, ori, normal, 0.03), g["project_linf"])
+    assert close(O.clip_points_l2(adv, ori, 0.5), g["l2"])
+    assert close(O.lp_clip(off, 0.02), g["lp_clip"])
+    assert close(O.offset_proj(off, ori, normal), g["offset_proj"])
+    assert np.array_equal(O.find_offset(ori, adv), g["find_offset"])
+    # the fixture exercises every branch
+    d = g["linf"] - ori
+    assert (np.abs(np.sqrt((d ** 2).sum(1)) - 0.03) < 1e-6).sum() > 100 and (g["linf"] == adv).all(1).sum() > 10
+    assert (g["project_linf"][1, :, 5:9] == ori[1, :, 5:9]).all() and (g["lp_clip"] == off).all(1).sum() > 10
