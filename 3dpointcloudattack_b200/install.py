@@ -10,7 +10,7 @@ patched.  Modules that cannot be imported (missing open3d etc.) are skipped and 
 """
 import importlib
 
-from . import (curvenet_util, dgcnn, dis_utils_torch, dist_utils, distance, knn_utils, loss_utils,
+from . import (curvenet_util, cw_loop, dgcnn, dis_utils_torch, dist_utils, distance, geoa3_loop, knn_utils, loss_utils,
                pointnet2_utils, set_distance, taof, utility)
 
 # reference module -> (our module, names)
@@ -23,6 +23,7 @@ PATCHES = {
     "attack.CW.CW_utils.dist_utils": (dist_utils, ["ChamferDist", "HausdorffDist", "KNNDist", "ChamferkNNDist"]),
     "attack.Gen3DAdv.utils.dist_utils": (dist_utils, ["ChamferDist", "HausdorffDist", "KNNDist", "ChamferkNNDist"]),
     "attack.SIadv.baselines.attack.util.dist_utils": (dist_utils, ["ChamferDist", "HausdorffDist", "KNNDist", "ChamferkNNDist"]),
+    "attack.CW.CW_utils.clip_utils": (cw_loop, ["ClipPointsL2", "ClipPointsLinf", "ProjectInnerClipLinf"]),   # one launch each
     "attack.GeoA3.knn_utils": (knn_utils, ["knn_points", "knn_gather"]),
     "attack.GeoA3.loss_utils": (loss_utils, ["knn_points", "knn_gather", "chamfer_loss", "pseudo_chamfer_loss",
                                             "hausdorff_loss", "_get_kappa_ori", "_get_kappa_adv", "curvature_loss",
@@ -68,6 +69,8 @@ def install(modules=None, strict=False):
             for n in ("estimate_normal", "estimate_perpendicular", "estimate_normal_via_ori_normal"):
                 if hasattr(ref, n):
                     setattr(ref, n, getattr(utility, n))
+            for n in ("offset_proj", "find_offset", "lp_clip"):              # GeoA3_attack.py:62-101, fused epilogues
+                setattr(ref, n, getattr(geoa3_loop, n))
         if name.endswith("dist_utils") and hasattr(ref, "chamfer"):
             ref.chamfer, ref.hausdorff = distance.chamfer, distance.hausdorff
         report[name] = "patched"

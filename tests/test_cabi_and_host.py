@@ -133,8 +133,12 @@ def test_install_patches_reference_modules():
     try:
         rep = pcd.install.install(modules=["utils.dis_utils_torch", "attack.CW.CW_utils.distance",
                                            "attack.CW.CW_utils.dist_utils", "attack.GeoA3.knn_utils",
-                                           "model.dgcnn", "model.pointnet2_utils", "attack.AOF.TAOF_attack"])
+                                           "model.dgcnn", "model.pointnet2_utils", "attack.AOF.TAOF_attack",
+                                           "attack.CW.CW_utils.clip_utils"])
         assert all(v == "patched" for v in rep.values()), rep
+        import attack.CW.CW_utils.clip_utils as CU
+        assert CU.ClipPointsLinf is pcd.cw_loop.ClipPointsLinf and CU.ProjectInnerClipLinf is pcd.cw_loop.ProjectInnerClipLinf
+        assert hasattr(CU, "ProjectInnerPoints")
         import attack.AOF.TAOF_attack as TA
         assert TA.get_Laplace_from_pc is pcd.taof.get_Laplace_from_pc and TA.knn is pcd.dgcnn.knn
         import attack.CW.CW_utils.dist_utils as DU
