@@ -10,6 +10,6 @@ ncu --set full --clock-control none --import-source on -k regex:nn1_sweep -c 1 -
 python tools/nn1_one.py && ncu --set full --clock-control none --import-source on -k regex:"nn1_(arm|fixup|bwd)" -c 3 -o $O/${R}_prof_nn1_small -f python tools/nn1_one.py > $O/${R}_ncu_nn1_small.log 2>&1
 python tools/knn_one.py 32 2048 64 20 && ncu --set full --clock-control none --import-source on -k regex:knnc_kernel -c 1 -o $O/${R}_prof_knnc -f python tools/knn_one.py 32 2048 64 20 > $O/${R}_ncu_knnc.log 2>&1
 python tools/knn_one.py 32 2048 3 20 && ncu --set full --clock-control none --import-source on -k regex:"knn3_|knn_threshold" -c 5 -o $O/${R}_prof_knn3 -f python tools/knn_one.py 32 2048 3 20 > $O/${R}_ncu_knn3.log 2>&1
-python tools/graph_one.py 32 64 2048 20 && ncu --set full --clock-control none --import-source on -k regex:"edge_feature|fps_kernel" -c 6 -o $O/${R}_prof_graph -f python tools/graph_one.py 32 64 2048 20 > $O/${R}_ncu_graph.log 2>&1
+python tools/graph_one.py 32 64 2048 20 && ncu --set full --clock-control none --import-source on -k regex:"edge_feature|edge_csr|fps_kernel|clip_|offset_gather" -c 14 -o $O/${R}_prof_graph -f python tools/graph_one.py 32 64 2048 20 > $O/${R}_ncu_graph.log 2>&1
 python tools/geom_one.py 32 2048 && ncu --set full --clock-control none --import-source on -k regex:"local_frames|kappa_|knn_outlier" -c 5 -o $O/${R}_prof_geom -f python tools/geom_one.py 32 2048 > $O/${R}_ncu_geom.log 2>&1
 ls -la $O/${R}_prof_*.ncu-rep
