@@ -154,6 +154,24 @@ def config2(pcd, dev, rank, with_reference, B=64, N=1024, iters=30):
         torch.manual_seed(9); adv_ref, _ = atk.attack(data, target, seed=1)
         out["reference_torch_same_gpu_iters_per_s"] = iters / (atk.loop_ms * 1e-3)
         out["coordinates_agreeing_1e-4"] = float(((adv_ours - adv_ref).abs() < 1e-4).float().mean())
+    # the same two loops with torch's DEFAULT convolution precision (cudnn.allow_tf32 = True), which is what a user of the
+    # reference gets; the numbers above pin fp32 convolutions so that the two loops can be compared coordinate by coordinate
+    torch.backends.cudnn.allow_tf32 = True
+    try:
+        atk = CL.KNNAttack(ours_v, CL.UntargetedLogitsAdvLoss(kappa=15.), pcd.dist_utils.ChamferkNNDist(knn_k=16),
+                           CL.ProjectInnerClipLinf(0.1), attack_lr=1e-3, num_iter=iters)
+        torch.manual_seed(9); atk.attack(data, target, seed=1)
+        torch.manual_seed(9); atk.attack(data, target, seed=1)
+        out["iters_per_s_eager_cudnn_tf32_default"] = iters / (atk.loop_ms * 1e-3)
+        if with_reference:
+            atk = CL.KNNAttack(ref_v, CL.UntargetedLogitsAdvLoss(kappa=15.), TorchChamferkNN(16), CL.ProjectInnerClipLinf(0.1),
+                               attack_lr=1e-3, num_iter=iters)
+            torch.manual_seed(9); atk.attack(data, target, seed=1)
+            torch.manual_seed(9); atk.attack(data, target, seed=1)
+            out["reference_torch_same_gpu_iters_per_s_cudnn_tf32_default"] = iters / (atk.loop_ms * 1e-3)
+    finally:
+        torch.backends.cudnn.allow_tf32 = False
+    if with_reference:
         del ref_v
     del ours_v
     torch.cuda.empty_cache()
@@ -186,6 +204,12 @@ def config3(pcd, dev, rank, world, with_reference, global_B=128, N=2048, iters=4
     atk.attack(data, label, seed=1, first_sample=start)
     atk.attack(data, label, seed=1, first_sample=start)
     out["ms_per_iteration"] = atk.loop_ms / iters
+    torch.backends.cudnn.allow_tf32 = True                 # torch's default convolution precision (what a user of the reference gets)
+    try:
+        atk.attack(data, label, seed=1, first_sample=start)
+        out["ms_per_iteration_cudnn_tf32_default"] = atk.loop_ms / iters
+    finally:
+        torch.backends.cudnn.allow_tf32 = False
 
     # the path inside one iteration, at this per-GPU batch
     ori = data.transpose(1, 2).contiguous()
