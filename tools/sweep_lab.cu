@@ -26,7 +26,9 @@ __device__ __forceinline__ float min2n(float a, float b) {
 
 // ROWM: 0 none, 2 two-input, 3 three-input.   COLM: 0 none, 2 two-input chain, 3 three-input tree,
 // 4 = two-input tree.  COLRED: 0 no warp reduction, 1 CREDUX + ballot + STS.
-template <int R, int ROWM, int COLM, int COLRED, int OCC>
+// MATH: 0 = the reference's five-instruction form; 1 = four instructions: v = fma(qz,cz, fma(qy,cy, fma(qx,cx, ncol))) feeds the
+// row minima, d = v + nrow the column minima (approximate sweep + exact fix-up); the column ballot then takes every lane within a window
+template <int R, int ROWM, int COLM, int COLRED, int OCC, int MATH = 0>
 __global__ void __launch_bounds__(128, OCC) lab(float *out, int iters) {
     __shared__ __align__(128) float4 tile[kCols + 2];
     __shared__ uint2 colpart[4][kCols];
@@ -58,6 +60,14 @@ __global__ void __launch_bounds__(128, OCC) lab(float *out, int iters) {
                 float lo[R], hi[R];
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
+                    if (MATH == 1) {
+                        const f32x2 v = fma2_s(qz[r], Z, fma2_s(qy[r], Y, fma2_s(qx[r], X, Nn)));
+                        float vl, vh;
+                        unpack2(v, vl, vh);
+                        m[r] = min3(m[r], vl, vh);
+                        unpack2(add2_s(qn[r], v), lo[r], hi[r]);
+                        continue;
+                    }
                     const f32x2 d = pair_dist_x2<PCD_FORM_SUM_FIRST>(qx[r], qy[r], qz[r], qn[r], X, Y, Z, Nn);
                     unpack2(d, lo[r], hi[r]);
                     if (ROWM == 3) m[r] = min3(m[r], lo[r], hi[r]);
@@ -85,8 +95,13 @@ __global__ void __launch_bounds__(128, OCC) lab(float *out, int iters) {
                 if (COLRED) {
                     if (pend_at >= 0) *reinterpret_cast<uint4 *>(&cp[pend_at]) = make_uint4(pend_lo.x, pend_lo.y, pend_hi.x, pend_hi.y);
                     const float vlo = warp_min_f32(clo), vhi = warp_min_f32(chi);
+                    if (MATH == 1) {
+                        pend_lo = make_uint2(__float_as_uint(vlo), __ballot_sync(0xffffffffu, clo <= vlo + qn[0]));
+                        pend_hi = make_uint2(__float_as_uint(vhi), __ballot_sync(0xffffffffu, chi <= vhi + qn[0]));
+                    } else {
                     pend_lo = make_uint2(__float_as_uint(vlo), __ballot_sync(0xffffffffu, clo == vlo));
                     pend_hi = make_uint2(__float_as_uint(vhi), __ballot_sync(0xffffffffu, chi == vhi));
+                    }
                     pend_at = 2 * step;
                 } else if (COLM) {
                     m[0] = min2(m[0], clo); m[1] = min2(m[1], chi);
@@ -108,16 +123,16 @@ __global__ void __launch_bounds__(128, OCC) lab(float *out, int iters) {
     if (iters == -12345) out[tid] = s;
 }
 
-template <int R, int ROWM, int COLM, int COLRED, int OCC>
+template <int R, int ROWM, int COLM, int COLRED, int OCC, int MATH = 0>
 void run(const char *name, int sms, float *d) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     const int iters = 64, grid = sms * OCC;
     float best = 1e9;
     for (int r = 0; r < 5; ++r) {
-        cudaEventRecord(e0); lab<R, ROWM, COLM, COLRED, OCC><<<grid, 128>>>(d, iters); cudaEventRecord(e1); cudaEventSynchronize(e1);
+        cudaEventRecord(e0); lab<R, ROWM, COLM, COLRED, OCC, MATH><<<grid, 128>>>(d, iters); cudaEventRecord(e1); cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1); if (r && ms < best) best = ms;
     }
-    cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, lab<R, ROWM, COLM, COLRED, OCC>);
+    cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, lab<R, ROWM, COLM, COLRED, OCC, MATH>);
     // pairs per SMSP = OCC CTAs * 1 warp each (4 warps per CTA over 4 SMSPs) * 32 lanes * R rows * kCols * iters
     const double pairs_per_smsp_lane = (double)OCC * R * kCols * iters;
     const double cyc = best * 1e-3 * 1.965e9;
@@ -133,6 +148,9 @@ int main() {
     run<16, 2, 0, 0, 2>("row min2", sms, d);
     run<16, 3, 3, 0, 2>("row min3 + col min3 tree (no warp red)", sms, d);
     run<16, 3, 3, 1, 2>("row min3 + col min3 tree + CREDUX (current)", sms, d);
+    run<16, 3, 3, 1, 2, 1>("FOUR-instruction math + window ballot", sms, d);
+    run<16, 3, 3, 0, 2, 1>("FOUR-instruction math, no warp red", sms, d);
+    run<16, 3, 3, 1, 1, 1>("FOUR-instruction math, one CTA per SM", sms, d);
     run<16, 3, 3, 1, 1>("current, ONE CTA per SM (1 warp per scheduler)", sms, d);
     run<16, 2, 2, 1, 2>("row min2 + col min2 chain + CREDUX", sms, d);
     run<16, 2, 4, 1, 2>("row min2 + col min2 tree + CREDUX", sms, d);
