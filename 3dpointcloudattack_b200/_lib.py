@@ -27,7 +27,7 @@ SIGNATURES = {
     "pcd_nn1_workspace_bytes": (_Z, [_I, _I, _I]),
     "pcd_nn1_query_tiling": (_I, [_I, _I, _I, _c.POINTER(_I), _c.POINTER(_I)]),
     "pcd_nn1_forward": (_I, _CLOUD + _CLOUD + [_I, _I, _I, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P,
-                                               _P, _Z, _P, _Z, _P, _Z, _I, _I, _P, _P, _P]),
+                                               _P, _Z, _P, _Z, _P, _Z, _I, _I, _I, _P, _P, _P]),
     "pcd_nn1_backward": (_I, _CLOUD + _CLOUD + [_I, _I, _I, _I, _I] + [_P] * 12 + [_c.POINTER(_L), _F, _F] + _CLOUD + _CLOUD + [_I, _P]),
     "pcd_knn_workspace_bytes": (_Z, [_I, _I, _I, _I, _I]),
     "pcd_knn_forward": (_I, _CLOUD + _CLOUD + [_I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _Z, _I, _P]),

@@ -81,8 +81,9 @@ constexpr int kFixupMaxWarps = 16384;             // upper bound of the persiste
 
 struct Nn1Layout {
     int Npad, Mpad;
-    size_t rowkey, colkey, counters, partials, rowpk, rowpp, colpk, total;
+    size_t rowkey, colkey, rowsec, colsec, maxnorm, counters, partials, rowpk, rowpp, colpk, total;
     size_t nkeys;
+    size_t arm_bytes;      // [rowkey .. maxnorm] is one contiguous region armed with all-ones
     int partial_slots;     // fix-up partials per sample (one per 32-point unit)
 };
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -96,6 +97,12 @@ static Nn1Layout nn1_layout(int B, int N, int M) {
     L.rowkey = off; off += (size_t)B * L.Npad * 8;
     L.colkey = off; off += (size_t)B * L.Mpad * 8;
     L.nkeys = (size_t)B * L.Npad + (size_t)B * L.Mpad;
+    // approximate sweep only: ordered bits of the second-best value per row / column, and per sample the
+    // complemented bits of the largest row and column norm (all three start as all-ones and are lowered with atomicMin)
+    L.rowsec = off; off += (size_t)B * L.Npad * 4;
+    L.colsec = off; off += (size_t)B * L.Mpad * 4;
+    L.maxnorm = off; off = align_up(off + (size_t)B * 8, 16);
+    L.arm_bytes = off - L.rowkey;
     L.counters = off; off = align_up(off + (size_t)B * 4, 256);
     L.partial_slots = (N + 31) / 32 + (M + 31) / 32;          // one partial per unit of 32 points: rows first, then columns
     L.partials = off; off = align_up(off + (size_t)B * L.partial_slots * 16, 256);       // (sum, max, bits of argmax, -)
@@ -215,6 +222,7 @@ struct SweepSmem {
     float rraw[kSweepWarps * 32 * R * 3];            // RAW: xyz of the CTA's row tile
     uint64_t full[2];                                // mbarriers: tile[s] / craw[s] has landed
     uint64_t rfull;                                  // mbarrier: rraw has landed
+    uint32_t colmax[3];                              // APX: bits of the largest column norm of tile it (slot it % 3)
 };
 template <int R>
 struct SweepSmemPacked {
@@ -235,11 +243,28 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 }
 #endif
 
-template <int FORM, int R, bool RAW>
+// APX (RAW only): the APPROXIMATE sweep.  Only the fix-up has to reproduce the reference's roundings; the sweep may rank the
+// pairs with any value that is provably close.  v = fma(qz,cz, fma(qy,cy, fma(qx,cx, ncol))) feeds the row minima and
+// a = v + nrow the column minima: FOUR packed instructions per two pairs instead of five (6.45 vs 7.26 cycles per pair in
+// tools/sweep_lab.cu).  Both a and the reference's d are within (4 + 5) * 2^-24 * T of the real value, T = nrow + ncol +
+// 2|q.c| <= 2 (nrow + ncol), so the reference's arg-min lies in a chunk (lane group) whose approximate minimum is within
+//     W = kApxWindow * (largest row norm + largest column norm)
+// of the best one.  The sweep therefore publishes, next to the best key, the SECOND-best value of every row / column
+// (rowsec / colsec; a row's near ties inside one CTA are found per chunk, across CTAs through the value the key atomic
+// returns; a column's ballot takes every lane within the window) and the norm maxima; the fix-up rescans the tagged
+// candidates with the reference's arithmetic and, where the second-best is within W, the whole row (column).
+constexpr float kApxWindow = 40.0f * 5.9604644775390625e-08f;      // 40 * 2^-24 (needed: 36)
+#ifndef PCD_APX_LEVEL      // development builds only (tools/apx_levels.sh): 1 = the cheaper math alone (NOT exact), 2 = + window ballot,
+#define PCD_APX_LEVEL 4    // 3 = + per-chunk near-tie flags, 4 = + second-best publishing (the product)
+#endif
+
+template <int FORM, int R, bool RAW, bool APX>
 __global__ void __launch_bounds__(kSweepThreads, (R >= 16) ? 2 : ((R >= 8) ? 4 : ((R >= 4) ? 5 : 6)))
 nn1_sweep_kernel(SweepSrc src, unsigned long long *__restrict__ rowkey, unsigned long long *__restrict__ colkey,
+                 uint32_t *__restrict__ rowsec, uint32_t *__restrict__ colsec, uint32_t *__restrict__ maxnorm,
                  int N, int Npad, int Mpad, int qpt /* quads per TMA tile */, int nqt, int nq /* quads per row tile */,
                  int units) {
+    static_assert(RAW || !APX, "the approximate sweep streams raw operands");
     constexpr int QW = 32 * R;            // rows per warp
     constexpr int QT = kSweepWarps * QW;  // rows per CTA tile
     constexpr int kQuadsPerChunk = kColChunk / kQuad;
@@ -317,7 +342,8 @@ nn1_sweep_kernel(SweepSrc src, unsigned long long *__restrict__ rowkey, unsigned
         }
     };
     // RAW: craw[s] (ncols raw columns) -> pair records {x0,x1,y0,y1},{z0,z1,n0,n1} in tile[d]
-    auto convert = [&](int s, int d, int ncols) {
+    auto convert = [&](int s, int d, int ncols, int slot) {
+        (void)slot;
         if constexpr (RAW) {
             const int p = tid;                               // pair record index; ncols is a multiple of 4
             if (2 * p < ncols) {
@@ -332,8 +358,13 @@ nn1_sweep_kernel(SweepSrc src, unsigned long long *__restrict__ rowkey, unsigned
                     const float2 a = f[0], bb = f[1], c = f[2];
                     x0 = a.x; y0 = a.y; z0 = bb.x; x1 = bb.y; y1 = c.x; z1 = c.y;
                 }
+                const float n0 = sq_norm3(src.norm_kind, x0, y0, z0), n1 = sq_norm3(src.norm_kind, x1, y1, z1);
                 sm.tile[d][2 * p] = make_float4(x0, x1, y0, y1);
-                sm.tile[d][2 * p + 1] = make_float4(z0, z1, sq_norm3(src.norm_kind, x0, y0, z0), sq_norm3(src.norm_kind, x1, y1, z1));
+                sm.tile[d][2 * p + 1] = make_float4(z0, z1, n0, n1);
+                if constexpr (APX) {      // norms are >= +0 (or NaN / inf): their bit patterns order like unsigned integers
+                    const uint32_t b0 = __float_as_uint(n0), b1 = __float_as_uint(n1);
+                    atomicMax(&sm.colmax[slot], b0 > b1 ? b0 : b1);
+                }
             }
         }
     };
@@ -341,6 +372,7 @@ nn1_sweep_kernel(SweepSrc src, unsigned long long *__restrict__ rowkey, unsigned
         mbar_init(&sm.full[0], 1);
         mbar_init(&sm.full[1], 1);
         if constexpr (RAW) mbar_init(&sm.rfull, 1);
+        if constexpr (APX) { sm.colmax[0] = 0u; sm.colmax[1] = 0u; sm.colmax[2] = 0u; }
         fence_mbar_init();
         fence_proxy_async();
         issue(0);
@@ -351,7 +383,7 @@ nn1_sweep_kernel(SweepSrc src, unsigned long long *__restrict__ rowkey, unsigned
     if constexpr (RAW) {
         // tile 0: convert in front of the loop; its raw buffer is then free for tile 2
         mbar_wait(&sm.full[0], 0);
-        convert(0, 0, seg_len(u0) * kQuad);
+        convert(0, 0, seg_len(u0) * kQuad, 0);
         __syncthreads();
         if (tid == 0) issue(0);
     }
@@ -362,6 +394,30 @@ nn1_sweep_kernel(SweepSrc src, unsigned long long *__restrict__ rowkey, unsigned
     size_t row_base = 0;
     uint32_t rpar = 0;
     bool armed = !RAW;     // RAW: griddepcontrol.wait not executed yet (keys are armed by our predecessor)
+    // APX: near-tie flags of this lane's rows (bit r), bits of the warp's largest row norm, the window of the current
+    // segment and its running maximum over the segments of the current row tile
+    uint32_t flags = 0u, wrow_bits = 0u;
+    float Wc = 0.f, wrun = 0.f;
+    const float pinf = __int_as_float(0x7f800000);
+    // publish the running row minima of the current row tile
+    auto flush_rows = [&]() {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const unsigned long long key = make_key(best[r], btag[r]);
+            if constexpr (APX && PCD_APX_LEVEL >= 4) {
+                const unsigned long long old = atomicMin(&rowkey[row_base + r * 32], key);
+                const uint32_t mine = (uint32_t)(key >> 32), prev = (uint32_t)(old >> 32);
+                uint32_t sv = prev > mine ? prev : mine;                 // the loser of (previous holder, this CTA): a second-best value
+                if ((flags >> r) & 1u) sv = sv < mine ? sv : mine;       // two chunks of this CTA within the window of each other
+                if (sv != 0xffffffffu) atomicMin(&rowsec[row_base + r * 32], sv);
+            } else {
+                atomicMin(&rowkey[row_base + r * 32], key);
+            }
+        }
+        if constexpr (APX) {
+            if (lane == 0) atomicMin(&maxnorm[2 * (cur_bq / nqt)], ~wrow_bits);
+        }
+    };
 
 #ifdef PCD_SWEEP_TRACE
     long long t_row = 0, t_comp = 0, t_bar = 0, t_flush = 0, t_mark = clock64();
@@ -378,10 +434,7 @@ nn1_sweep_kernel(SweepSrc src, unsigned long long *__restrict__ rowkey, unsigned
         bool pulled = false;
 
         if (bq != cur_bq) {
-            if (cur_bq >= 0) {
-#pragma unroll
-                for (int r = 0; r < R; ++r) atomicMin(&rowkey[row_base + r * 32], make_key(best[r], btag[r]));
-            }
+            if (cur_bq >= 0) flush_rows();
             cur_bq = bq;
             row_base = (size_t)b * Npad + (size_t)qt * QT + warp * QW + lane;    // key slot of row r: + r*32
             if constexpr (RAW) {
@@ -389,6 +442,7 @@ nn1_sweep_kernel(SweepSrc src, unsigned long long *__restrict__ rowkey, unsigned
                 rpar ^= 1u;
                 pulled = true;
                 const int l0 = warp * QW + lane * R;            // first of this lane's rows inside the tile
+                uint32_t mxb = 0u;
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     float x = 0.f, y = 0.f, z = 0.f, n = __int_as_float(0x7f800000);
@@ -396,10 +450,16 @@ nn1_sweep_kernel(SweepSrc src, unsigned long long *__restrict__ rowkey, unsigned
                         if (src.row_cm) { x = sm.rraw[l0 + r]; y = sm.rraw[QT + l0 + r]; z = sm.rraw[2 * QT + l0 + r]; }
                         else { x = sm.rraw[(l0 + r) * 3]; y = sm.rraw[(l0 + r) * 3 + 1]; z = sm.rraw[(l0 + r) * 3 + 2]; }
                         n = sq_norm3(src.norm_kind, x, y, z);
+                        if constexpr (APX) mxb = max(mxb, __float_as_uint(n));
                     }
                     qx[r] = -2.f * x; qy[r] = -2.f * y; qz[r] = -2.f * z; qn[r] = n;
                     best[r] = __int_as_float(0x7f800000);
                     btag[r] = 0;
+                }
+                if constexpr (APX) {
+                    wrow_bits = __reduce_max_sync(0xffffffffu, mxb);      // the live rows of the whole warp (padding excluded)
+                    flags = 0u;
+                    wrun = 0.f;
                 }
             } else {
 #pragma unroll
@@ -418,6 +478,14 @@ nn1_sweep_kernel(SweepSrc src, unsigned long long *__restrict__ rowkey, unsigned
 #endif
         PCD_PHASE(t_row);
 
+        uint32_t cmax_bits = 0u;
+        if constexpr (APX) {
+            cmax_bits = sm.colmax[it % 3];
+            if (tid == 0) sm.colmax[(it + 2) % 3] = 0u;          // read one iteration ago, written again in the next one
+            Wc = __fmul_ru(kApxWindow, __fadd_ru(__uint_as_float(wrow_bits), __uint_as_float(cmax_bits)));
+            if (!(Wc >= 0.f)) Wc = pinf;                         // NaN norms: everything is a candidate
+            wrun = fmaxf(wrun, Wc);
+        }
         const float4 *t4 = sm.tile[buf];
         uint2 *cp = sm.colpart[buf][warp];
         float4 A = t4[0], Bv = t4[1];                       // operands of the step about to run
@@ -442,9 +510,17 @@ nn1_sweep_kernel(SweepSrc src, unsigned long long *__restrict__ rowkey, unsigned
                     float lo[R], hi[R];
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
-                        const f32x2 d = pair_dist_x2<FORM>(qx[r], qy[r], qz[r], qn[r], X, Y, Z, Nn);
-                        unpack2(d, lo[r], hi[r]);
-                        m[r] = min3(m[r], lo[r], hi[r]);
+                        if constexpr (APX) {
+                            const f32x2 v = fma2_s(qz[r], Z, fma2_s(qy[r], Y, fma2_s(qx[r], X, Nn)));
+                            float vl, vh;
+                            unpack2(v, vl, vh);
+                            m[r] = min3(m[r], vl, vh);                       // rows rank by v (their own norm is a constant offset)
+                            unpack2(add2_s(qn[r], v), lo[r], hi[r]);
+                        } else {
+                            const f32x2 d = pair_dist_x2<FORM>(qx[r], qy[r], qz[r], qn[r], X, Y, Z, Nn);
+                            unpack2(d, lo[r], hi[r]);
+                            m[r] = min3(m[r], lo[r], hi[r]);
+                        }
                     }
                     float clo = lo[0], chi = hi[0];
 #pragma unroll
@@ -459,14 +535,23 @@ nn1_sweep_kernel(SweepSrc src, unsigned long long *__restrict__ rowkey, unsigned
                     // retire the previous step's column results (their CREDUX latency is long gone)
                     if (pend_at >= 0) *reinterpret_cast<uint4 *>(&cp[pend_at]) = make_uint4(pend_lo.x, pend_lo.y, pend_hi.x, pend_hi.y);
                     const float vlo = warp_min_f32(clo), vhi = warp_min_f32(chi);
-                    pend_lo = make_uint2(__float_as_uint(vlo), __ballot_sync(0xffffffffu, clo == vlo));
-                    pend_hi = make_uint2(__float_as_uint(vhi), __ballot_sync(0xffffffffu, chi == vhi));
+                    if constexpr (APX && PCD_APX_LEVEL >= 2) {      // every lane whose partial minimum is within the window of the warp's
+                        pend_lo = make_uint2(__float_as_uint(vlo), __ballot_sync(0xffffffffu, clo <= __fadd_ru(vlo, Wc)));
+                        pend_hi = make_uint2(__float_as_uint(vhi), __ballot_sync(0xffffffffu, chi <= __fadd_ru(vhi, Wc)));
+                    } else {
+                        pend_lo = make_uint2(__float_as_uint(vlo), __ballot_sync(0xffffffffu, clo == vlo));
+                        pend_hi = make_uint2(__float_as_uint(vhi), __ballot_sync(0xffffffffu, chi == vhi));
+                    }
                     pend_at = 2 * step;
                     A = An; Bv = Bn;
                 }
             }
 #pragma unroll
             for (int r = 0; r < R; ++r) {
+                if constexpr (APX && PCD_APX_LEVEL >= 3) {      // is the loser of (chunk minimum, running best) within the window of the winner?
+                    const float nb = fminf(m[r], best[r]), ob = fmaxf(m[r], best[r]);
+                    if (ob <= __fadd_ru(nb, wrun)) flags |= 1u << r;
+                }
                 if (m[r] < best[r]) {
                     best[r] = m[r];
                     btag[r] = (uint32_t)chunk;
@@ -481,7 +566,7 @@ nn1_sweep_kernel(SweepSrc src, unsigned long long *__restrict__ rowkey, unsigned
             // (tile[buf^1] was last read one barrier ago)
             if (u + nseg < u1) {
                 mbar_wait(&sm.full[buf ^ 1], ((it + 1) >> 1) & 1);
-                convert(buf ^ 1, buf ^ 1, seg_len(u + nseg) * kQuad);
+                convert(buf ^ 1, buf ^ 1, seg_len(u + nseg) * kQuad, (it + 1) % 3);
             }
         }
         __syncthreads();  // tile[buf] fully read, colpart[buf] fully written, RAW: tile[buf^1] converted, craw[buf^1] and rraw free
@@ -501,18 +586,35 @@ nn1_sweep_kernel(SweepSrc src, unsigned long long *__restrict__ rowkey, unsigned
         }
         // column flush: min over the CTA's warps (lowest warp on ties), lowest lane of its ballot
         const int ncols = nseg * kQuad;
+        if constexpr (APX) {
+            if (tid == 0) atomicMin(&maxnorm[2 * b + 1], ~cmax_bits);
+        }
         for (int col = tid; col < ncols; col += kSweepThreads) {
             uint2 e = sm.colpart[buf][0][col];
-            float v = __uint_as_float(e.x);
+            float v = __uint_as_float(e.x), second = pinf;
             uint32_t w = 0, msk = e.y;
 #pragma unroll
             for (int k = 1; k < kSweepWarps; ++k) {
                 const uint2 o = sm.colpart[buf][k][col];
-                if (__uint_as_float(o.x) < v) { v = __uint_as_float(o.x); w = k; msk = o.y; }
+                const float ov = __uint_as_float(o.x);
+                if (ov < v) { second = fminf(second, v); v = ov; w = k; msk = o.y; }
+                else second = fminf(second, ov);
             }
-            if (v < __int_as_float(0x7f800000))
-                atomicMin(&colkey[(size_t)b * Mpad + (size_t)q0 * kQuad + col],
-                          make_key(v, (((uint32_t)qt * kSweepWarps + w) << 5) + (uint32_t)(__ffs(msk) - 1)));
+            if (v < pinf) {
+                const size_t slot = (size_t)b * Mpad + (size_t)q0 * kQuad + col;
+                const unsigned long long key = make_key(v, (((uint32_t)qt * kSweepWarps + w) << 5) + (uint32_t)(__ffs(msk) - 1));
+                if constexpr (APX && PCD_APX_LEVEL >= 4) {
+                    if (__popc(msk) > 1) second = v;                     // several lanes of the winning warp are candidates
+                    const unsigned long long old = atomicMin(&colkey[slot], key);
+                    const uint32_t mine = (uint32_t)(key >> 32), prev = (uint32_t)(old >> 32);
+                    uint32_t sv = prev > mine ? prev : mine;             // the loser of (previous holder, this CTA)
+                    const uint32_t so = f32_to_ordered(second);
+                    sv = sv < so ? sv : so;
+                    if (sv != 0xffffffffu) atomicMin(&colsec[slot], sv);
+                } else {
+                    atomicMin(&colkey[slot], key);
+                }
+            }
         }
         u += nseg;
         PCD_PHASE(t_flush);
@@ -525,8 +627,7 @@ nn1_sweep_kernel(SweepSrc src, unsigned long long *__restrict__ rowkey, unsigned
         trace[blockIdx.x * 8 + 7] = ((unsigned long long)t_bar << 32) | (unsigned long long)(t_flush & 0xffffffffll);
     }
 #endif
-#pragma unroll
-    for (int r = 0; r < R; ++r) atomicMin(&rowkey[row_base + r * 32], make_key(best[r], btag[r]));
+    flush_rows();
 #ifdef PCD_SWEEP_TRACE
     __syncthreads();
     if (trace && tid == 0) trace[blockIdx.x * 8 + 2] = globaltimer_ns();
@@ -834,9 +935,15 @@ struct StagedArgs {
     int parts_row, parts_col;   // slices per (sample, side): a row point scans 32 candidates, a column point R, so the
                                 // sides get slice counts in proportion to their work
     int stage_stride;           // channel-major staging: floats between the channel rows (multiple of 32)
+    const uint32_t *rowsec, *colsec, *maxnorm;    // APX: what the approximate sweep published next to the keys
 };
 
-template <int FORM, int NORM>
+// APX: the keys come from the approximate sweep (see nn1_sweep_kernel).  The tagged candidates are evaluated with the
+// reference's arithmetic and the exact (minimum, lowest index) is taken over them -- not an equality match with the
+// sweep's value.  Where the second-best approximate value of the point is within the sample's window of the best one the
+// tagged candidates may miss the reference's arg-min: the warp then rescans the whole row (column) of that point
+// together, 32 lanes over the staged cloud, and the lane keeps the exact result.
+template <int FORM, int NORM, bool APX>
 __global__ void __launch_bounds__(kFixupThreads, 3)
 nn1_fixup_staged_kernel(StagedArgs sa) {
     const FixupArgs &a = sa.f;
@@ -882,35 +989,80 @@ nn1_fixup_staged_kernel(StagedArgs sa) {
     const int units = (n_own + 31) >> 5;
     const int u0 = (int)((long long)units * q / parts), u1 = (int)((long long)units * (q + 1) / parts);
     const unsigned long long *keys = side ? a.colkey + (size_t)b * a.Mpad : a.rowkey + (size_t)b * a.Npad;
+    const uint32_t *secs = nullptr;
+    float Wb = 0.f;                                   // the sample's window (see kApxWindow)
+    if constexpr (APX) {
+        secs = side ? sa.colsec + (size_t)b * a.Mpad : sa.rowsec + (size_t)b * a.Npad;
+        const float mr = __uint_as_float(~__ldcg(&sa.maxnorm[2 * b])), mc = __uint_as_float(~__ldcg(&sa.maxnorm[2 * b + 1]));
+        Wb = __fmul_ru(kApxWindow, __fadd_ru(mr, mc));
+        if (!(Wb >= 0.f)) Wb = __int_as_float(0x7f800000);
+    }
     float *out_min = side ? a.col_min + (size_t)b * M : a.row_min + (size_t)b * N;
     int32_t *out_arg = side ? a.col_arg + (size_t)b * M : a.row_arg + (size_t)b * N;
 
     // software pipeline over this warp's units: key and own coordinates of the next unit are requested first
     unsigned long long key = 0ull;
+    uint32_t sec = 0xffffffffu;
     float px = 0.f, py = 0.f, pz = 0.f;
-    auto fetch = [&](int u, unsigned long long &k, float &x, float &y, float &z) {
+    auto fetch = [&](int u, unsigned long long &k, uint32_t &sc2, float &x, float &y, float &z) {
         const int p = u * 32 + lane;
-        k = 0ull; x = y = z = 0.f;
+        k = 0ull; sc2 = 0xffffffffu; x = y = z = 0.f;
         if (u < u1 && p < n_own) {
-            k = keys[side ? p : row_slot(p, R)];
+            const int slot = side ? p : row_slot(p, R);
+            k = keys[slot];
+            if constexpr (APX) sc2 = secs[slot];
             const float *s = own + (size_t)p * own_sp;
             x = __ldg(s); y = __ldg(s + own_sc); z = __ldg(s + 2 * own_sc);
         }
     };
-    fetch(u0 + warp, key, px, py, pz);
+    // four candidates j .. j+3 against one fixed point (m2 = -2 * its coordinates, fn = its norm): exact distances
+    auto eval4 = [&](int j, float m2x, float m2y, float m2z, float fn, float &e0, float &e1, float &e2, float &e3) {
+        f32x2 X0, X1, Y0, Y1, Z0, Z1;
+        if (opp_cm) {
+            const float4 fx = *reinterpret_cast<const float4 *>(stage + j);
+            const float4 fy = *reinterpret_cast<const float4 *>(stage + sa.stage_stride + j);
+            const float4 fz = *reinterpret_cast<const float4 *>(stage + 2 * sa.stage_stride + j);
+            X0 = pack2(fx.x, fx.y); X1 = pack2(fx.z, fx.w);
+            Y0 = pack2(fy.x, fy.y); Y1 = pack2(fy.z, fy.w);
+            Z0 = pack2(fz.x, fz.y); Z1 = pack2(fz.z, fz.w);
+        } else {
+            const float4 *g = reinterpret_cast<const float4 *>(stage + (size_t)j * 3);
+            const float4 f0 = g[0], f1 = g[1], f2 = g[2];
+            X0 = pack2(f0.x, f0.w); X1 = pack2(f1.z, f2.y);
+            Y0 = pack2(f0.y, f1.x); Y1 = pack2(f1.w, f2.z);
+            Z0 = pack2(f0.z, f1.y); Z1 = pack2(f2.x, f2.w);
+        }
+        const f32x2 d0 = pair_dist_fixed_x2<FORM>(side == 0, m2x, m2y, m2z, fn, X0, Y0, Z0, sq_norm3_x2(NORM, X0, Y0, Z0));
+        const f32x2 d1 = pair_dist_fixed_x2<FORM>(side == 0, m2x, m2y, m2z, fn, X1, Y1, Z1, sq_norm3_x2(NORM, X1, Y1, Z1));
+        unpack2(d0, e0, e1); unpack2(d1, e2, e3);
+    };
+    // exact (minimum, lowest index) over the candidates seen so far
+    auto take = [](float e, int j, float &bv, int &arg) {
+        if (e < bv) { bv = e; arg = j; }
+        else if (e == bv) arg = min(arg, j);
+    };
+    fetch(u0 + warp, key, sec, px, py, pz);
     for (int u = u0 + warp; u < u1; u += kFixupThreads / 32) {
-        unsigned long long nkey; float nx, ny, nz;
-        fetch(u + kFixupThreads / 32, nkey, nx, ny, nz);
+        unsigned long long nkey; uint32_t nsec; float nx, ny, nz;
+        fetch(u + kFixupThreads / 32, nkey, nsec, nx, ny, nz);
         const int p = u * 32 + lane;
         float val = 0.f;
+        const float pn = sq_norm3(NORM, px, py, pz);
+        const float m2x = -2.f * px, m2y = -2.f * py, m2z = -2.f * pz;
+        float bv = __int_as_float(0x7f800000);         // APX: exact minimum over the candidates
+        int arg = 0x7fffffff;
+        bool amb = false;
         if (p < n_own) {
             const float v = ordered_to_f32((uint32_t)(key >> 32));
             const uint32_t tag = (uint32_t)key;
-            const float pn = sq_norm3(NORM, px, py, pz);
-            int arg = 0x7fffffff;
+            if constexpr (APX) {      // second-best within the window of the best (or no usable window): rescan everything
+                amb = sec != 0xffffffffu && !(ordered_to_f32(sec) > __fadd_ru(v, Wb));
+#ifdef PCD_APX_DEBUG
+                if (amb) atomicAdd(&a.counters[a.B + side], 1);          // development build: flagged points per side
+#endif
+            }
             // Candidates come in groups of four (three LDS.128 in either dense layout) and are evaluated two at a time with the
             // sweep's packed instruction sequence; the fixed point carries the exact factor -2 whichever side it is on.
-            const float m2x = -2.f * px, m2y = -2.f * py, m2z = -2.f * pz;
             int c0 = 0, ngroups = 0;                         // first candidate, groups of 4
             if (side == 0) {
                 if (tag < (uint32_t)a.nchunks) { c0 = (int)tag * kColChunk; ngroups = 8; }              // the 32 columns of the winning chunk
@@ -923,29 +1075,16 @@ nn1_fixup_staged_kernel(StagedArgs sa) {
                 for (int i = 0; i < ngroups; ++i) {
                     const int k = (lane + i) & (ngroups - 1), j = c0 + 4 * k;                             // rotated start: conflict-free banks
                     if (j < n_opp) {                                                                      // n_opp % 4 == 0: whole groups
-                        f32x2 X0, X1, Y0, Y1, Z0, Z1;
-                        if (opp_cm) {
-                            const float4 fx = *reinterpret_cast<const float4 *>(stage + j);
-                            const float4 fy = *reinterpret_cast<const float4 *>(stage + sa.stage_stride + j);
-                            const float4 fz = *reinterpret_cast<const float4 *>(stage + 2 * sa.stage_stride + j);
-                            X0 = pack2(fx.x, fx.y); X1 = pack2(fx.z, fx.w);
-                            Y0 = pack2(fy.x, fy.y); Y1 = pack2(fy.z, fy.w);
-                            Z0 = pack2(fz.x, fz.y); Z1 = pack2(fz.z, fz.w);
-                        } else {
-                            const float4 *g = reinterpret_cast<const float4 *>(stage + (size_t)j * 3);
-                            const float4 f0 = g[0], f1 = g[1], f2 = g[2];
-                            X0 = pack2(f0.x, f0.w); X1 = pack2(f1.z, f2.y);
-                            Y0 = pack2(f0.y, f1.x); Y1 = pack2(f1.w, f2.z);
-                            Z0 = pack2(f0.z, f1.y); Z1 = pack2(f2.x, f2.w);
-                        }
-                        const f32x2 d0 = pair_dist_fixed_x2<FORM>(side == 0, m2x, m2y, m2z, pn, X0, Y0, Z0, sq_norm3_x2(NORM, X0, Y0, Z0));
-                        const f32x2 d1 = pair_dist_fixed_x2<FORM>(side == 0, m2x, m2y, m2z, pn, X1, Y1, Z1, sq_norm3_x2(NORM, X1, Y1, Z1));
                         float e0, e1, e2, e3;
-                        unpack2(d0, e0, e1); unpack2(d1, e2, e3);
-                        if (e3 == v) arg = min(arg, j + 3);
-                        if (e2 == v) arg = min(arg, j + 2);
-                        if (e1 == v) arg = min(arg, j + 1);
-                        if (e0 == v) arg = min(arg, j);
+                        eval4(j, m2x, m2y, m2z, pn, e0, e1, e2, e3);
+                        if constexpr (APX) {
+                            take(e0, j, bv, arg); take(e1, j + 1, bv, arg); take(e2, j + 2, bv, arg); take(e3, j + 3, bv, arg);
+                        } else {
+                            if (e3 == v) arg = min(arg, j + 3);
+                            if (e2 == v) arg = min(arg, j + 2);
+                            if (e1 == v) arg = min(arg, j + 1);
+                            if (e0 == v) arg = min(arg, j);
+                        }
                     }
                 }
             } else if (side == 1 && R < 4 && (tag >> 5) < (uint32_t)a.nrowgroups) {
@@ -955,16 +1094,45 @@ nn1_fixup_staged_kernel(StagedArgs sa) {
                         float x, y, z;
                         if (opp_cm) { x = stage[i]; y = stage[sa.stage_stride + i]; z = stage[2 * sa.stage_stride + i]; }
                         else { x = stage[3 * i]; y = stage[3 * i + 1]; z = stage[3 * i + 2]; }
-                        if (pair_dist_scalar<FORM>(-2.f * x, -2.f * y, -2.f * z, sq_norm3(NORM, x, y, z), px, py, pz, pn) == v) arg = min(arg, i);
+                        const float e = pair_dist_scalar<FORM>(-2.f * x, -2.f * y, -2.f * z, sq_norm3(NORM, x, y, z), px, py, pz, pn);
+                        if constexpr (APX) take(e, i, bv, arg);
+                        else if (e == v) arg = min(arg, i);
                     }
                 }
             }
+            if constexpr (!APX) bv = v;
+        }
+        if constexpr (APX) {
+            // near ties: the whole warp rescans every candidate of the flagged point (rare: a few points per thousand)
+            unsigned todo = __ballot_sync(0xffffffffu, amb);
+            while (todo) {
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const float fx = __shfl_sync(0xffffffffu, m2x, src), fy = __shfl_sync(0xffffffffu, m2y, src);
+                const float fz = __shfl_sync(0xffffffffu, m2z, src), fn = __shfl_sync(0xffffffffu, pn, src);
+                float fbv = __int_as_float(0x7f800000);
+                int farg = 0x7fffffff;
+                for (int j = 4 * lane; j < n_opp; j += 128) {
+                    float e0, e1, e2, e3;
+                    eval4(j, fx, fy, fz, fn, e0, e1, e2, e3);
+                    take(e0, j, fbv, farg); take(e1, j + 1, fbv, farg); take(e2, j + 2, fbv, farg); take(e3, j + 3, fbv, farg);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ov = __shfl_xor_sync(0xffffffffu, fbv, o);
+                    const int oa = __shfl_xor_sync(0xffffffffu, farg, o);
+                    if (ov < fbv || (ov == fbv && oa < farg)) { fbv = ov; farg = oa; }
+                }
+                if (lane == src) { bv = fbv; arg = farg; }
+            }
+        }
+        if (p < n_own) {
             if (arg == 0x7fffffff) arg = 0;        // no finite minimum (NaN / inf inputs)
-            val = apply_transform(a.transform, v);
+            val = apply_transform(a.transform, bv);
             out_min[p] = val; out_arg[p] = arg;
         }
         store_unit_partial(a, b, (side ? (N + 31) >> 5 : 0) + u, p < n_own, val, p, lane);
-        key = nkey; px = nx; py = ny; pz = nz;
+        key = nkey; sec = nsec; px = nx; py = ny; pz = nz;
     }
     if (lane == 0) __threadfence();       // this warp's unit partials are visible before the CTA reports completion
     __syncthreads();
@@ -1095,8 +1263,13 @@ __global__ void __launch_bounds__(256) nn1_bwd_kernel(BwdArgs a) {
 }
 
 // ----------------------------------------------------------------------------- host helpers
-template <int FORM, int R, bool RAW>
-static cudaError_t launch_sweep(const SweepSrc &src, unsigned long long *rowkey, unsigned long long *colkey, int B, int N,
+struct SweepOut {
+    unsigned long long *rowkey, *colkey;
+    uint32_t *rowsec, *colsec, *maxnorm;
+};
+
+template <int FORM, int R, bool RAW, bool APX>
+static cudaError_t launch_sweep(const SweepSrc &src, const SweepOut &o, int B, int N,
                                 int M, int Npad, int Mpad, int mt, int sms, cudaStream_t st) {
     using Smem = typename std::conditional<RAW, SweepSmem<R>, SweepSmemPacked<R>>::type;
     const int QT = kSweepWarps * 32 * R;
@@ -1108,42 +1281,44 @@ static cudaError_t launch_sweep(const SweepSrc &src, unsigned long long *rowkey,
     const int dev = current_device();
     if (dev < 0) return cudaErrorInvalidDevice;
     if (occ_cache.v[dev] == 0) {
-        cudaError_t e = cudaFuncSetAttribute(nn1_sweep_kernel<FORM, R, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(nn1_sweep_kernel<FORM, R, RAW, APX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)sizeof(Smem));
         if (e != cudaSuccess) return e;
         // ask for the shared-memory carve-out explicitly: the register-limited residency (2 CTAs at R = 16) needs
         // 2 x 55 KB, more than the default split provides
-        e = cudaFuncSetAttribute(nn1_sweep_kernel<FORM, R, RAW>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        e = cudaFuncSetAttribute(nn1_sweep_kernel<FORM, R, RAW, APX>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  (int)cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
-        int o = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, nn1_sweep_kernel<FORM, R, RAW>, kSweepThreads, sizeof(Smem));
+        int occ = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nn1_sweep_kernel<FORM, R, RAW, APX>, kSweepThreads, sizeof(Smem));
         if (e != cudaSuccess) return e;
-        occ_cache.v[dev] = o < 1 ? 1 : o;
+        occ_cache.v[dev] = occ < 1 ? 1 : occ;
     }
     long long grid = (long long)sms * occ_cache.v[dev];
     if (grid > units) grid = units;
-    return launch_kernel(nn1_sweep_kernel<FORM, R, RAW>, dim3((unsigned)grid), dim3(kSweepThreads), sizeof(Smem), st, true,
-                         src, rowkey, colkey, N, Npad, Mpad, mt / kQuad, nqt, nq, (int)units);
+    return launch_kernel(nn1_sweep_kernel<FORM, R, RAW, APX>, dim3((unsigned)grid), dim3(kSweepThreads), sizeof(Smem), st, true,
+                         src, o.rowkey, o.colkey, o.rowsec, o.colsec, o.maxnorm, N, Npad, Mpad, mt / kQuad, nqt, nq, (int)units);
 }
 
-template <int FORM, bool RAW>
-static cudaError_t launch_sweep_r(int R, const SweepSrc &src, unsigned long long *rowkey, unsigned long long *colkey, int B,
+template <int FORM, bool RAW, bool APX>
+static cudaError_t launch_sweep_r(int R, const SweepSrc &src, const SweepOut &o, int B,
                                   int N, int M, int Npad, int Mpad, int mt, int sms, cudaStream_t st) {
     switch (R) {
-    case 16: return launch_sweep<FORM, 16, RAW>(src, rowkey, colkey, B, N, M, Npad, Mpad, mt, sms, st);
-    case 8: return launch_sweep<FORM, 8, RAW>(src, rowkey, colkey, B, N, M, Npad, Mpad, mt, sms, st);
-    case 4: return launch_sweep<FORM, 4, RAW>(src, rowkey, colkey, B, N, M, Npad, Mpad, mt, sms, st);
-    default: return launch_sweep<FORM, 2, RAW>(src, rowkey, colkey, B, N, M, Npad, Mpad, mt, sms, st);
+    case 16: return launch_sweep<FORM, 16, RAW, APX>(src, o, B, N, M, Npad, Mpad, mt, sms, st);
+    case 8: return launch_sweep<FORM, 8, RAW, APX>(src, o, B, N, M, Npad, Mpad, mt, sms, st);
+    case 4: return launch_sweep<FORM, 4, RAW, APX>(src, o, B, N, M, Npad, Mpad, mt, sms, st);
+    default: return launch_sweep<FORM, 2, RAW, APX>(src, o, B, N, M, Npad, Mpad, mt, sms, st);
     }
 }
 
-template <bool RAW>
-static cudaError_t launch_sweep_f(int form, int R, const SweepSrc &src, unsigned long long *rowkey, unsigned long long *colkey,
+// the approximate sweep ranks with ONE instruction sequence whatever the reference's form is (the form only matters to the fix-up)
+template <bool RAW, bool APX>
+static cudaError_t launch_sweep_f(int form, int R, const SweepSrc &src, const SweepOut &o,
                                   int B, int N, int M, int Npad, int Mpad, int mt, int sms, cudaStream_t st) {
-    if (form == PCD_FORM_ROW_COL) return launch_sweep_r<PCD_FORM_ROW_COL, RAW>(R, src, rowkey, colkey, B, N, M, Npad, Mpad, mt, sms, st);
-    if (form == PCD_FORM_COL_ROW) return launch_sweep_r<PCD_FORM_COL_ROW, RAW>(R, src, rowkey, colkey, B, N, M, Npad, Mpad, mt, sms, st);
-    return launch_sweep_r<PCD_FORM_SUM_FIRST, RAW>(R, src, rowkey, colkey, B, N, M, Npad, Mpad, mt, sms, st);
+    if constexpr (APX) return launch_sweep_r<PCD_FORM_SUM_FIRST, RAW, true>(R, src, o, B, N, M, Npad, Mpad, mt, sms, st);
+    if (form == PCD_FORM_ROW_COL) return launch_sweep_r<PCD_FORM_ROW_COL, RAW, false>(R, src, o, B, N, M, Npad, Mpad, mt, sms, st);
+    if (form == PCD_FORM_COL_ROW) return launch_sweep_r<PCD_FORM_COL_ROW, RAW, false>(R, src, o, B, N, M, Npad, Mpad, mt, sms, st);
+    return launch_sweep_r<PCD_FORM_SUM_FIRST, RAW, false>(R, src, o, B, N, M, Npad, Mpad, mt, sms, st);
 }
 
 template <bool RAW, int NORM>
@@ -1166,15 +1341,15 @@ constexpr size_t kStageMaxBytes = 200 * 1024;
 
 // One CTA per (sample, side, slice); `parts` slices per job are chosen so that the whole grid is resident at once
 // (a second wave of CTAs would wait for the first one to drain: +40 % at BASELINE config 2).
-template <int FORM, int NORM>
+template <int FORM, int NORM, bool APX>
 static cudaError_t launch_fixup_staged_fn(StagedArgs sa, int B, int max_parts, int sms, size_t smem, cudaStream_t st) {
     static PerDeviceInt attr_set = {};
     const int dev = current_device();
     if (dev < 0) return cudaErrorInvalidDevice;
     if (!attr_set.v[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(nn1_fixup_staged_kernel<FORM, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageMaxBytes);
+        cudaError_t e = cudaFuncSetAttribute(nn1_fixup_staged_kernel<FORM, NORM, APX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageMaxBytes);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(nn1_fixup_staged_kernel<FORM, NORM>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        e = cudaFuncSetAttribute(nn1_fixup_staged_kernel<FORM, NORM, APX>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  (int)cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
         attr_set.v[dev] = 1;
@@ -1183,7 +1358,7 @@ static cudaError_t launch_fixup_staged_fn(StagedArgs sa, int B, int max_parts, i
     static PerDeviceInt occ_smem = {}, occ_val = {};
     if (occ_smem.v[dev] != (int)smem || occ_val.v[dev] == 0) {
         int o = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, nn1_fixup_staged_kernel<FORM, NORM>, kFixupThreads, smem);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, nn1_fixup_staged_kernel<FORM, NORM, APX>, kFixupThreads, smem);
         if (e != cudaSuccess) return e;
         occ_val.v[dev] = o < 1 ? 1 : o;
         occ_smem.v[dev] = (int)smem;
@@ -1204,13 +1379,18 @@ static cudaError_t launch_fixup_staged_fn(StagedArgs sa, int B, int max_parts, i
     if (pc > (ucol + wpc - 1) / wpc) pc = (ucol + wpc - 1) / wpc;
     (void)max_parts;
     sa.parts_row = pr; sa.parts_col = pc;
-    return launch_kernel(nn1_fixup_staged_kernel<FORM, NORM>, dim3((unsigned)(B * (pr + pc))), dim3(kFixupThreads), smem, st, true, sa);
+    return launch_kernel(nn1_fixup_staged_kernel<FORM, NORM, APX>, dim3((unsigned)(B * (pr + pc))), dim3(kFixupThreads), smem, st, true, sa);
 }
-template <int NORM>
+template <int NORM, bool APX>
 static cudaError_t launch_fixup_staged_n(int form, const StagedArgs &sa, int B, int max_parts, int sms, size_t smem, cudaStream_t st) {
-    if (form == PCD_FORM_ROW_COL) return launch_fixup_staged_fn<PCD_FORM_ROW_COL, NORM>(sa, B, max_parts, sms, smem, st);
-    if (form == PCD_FORM_COL_ROW) return launch_fixup_staged_fn<PCD_FORM_COL_ROW, NORM>(sa, B, max_parts, sms, smem, st);
-    return launch_fixup_staged_fn<PCD_FORM_SUM_FIRST, NORM>(sa, B, max_parts, sms, smem, st);
+    if (form == PCD_FORM_ROW_COL) return launch_fixup_staged_fn<PCD_FORM_ROW_COL, NORM, APX>(sa, B, max_parts, sms, smem, st);
+    if (form == PCD_FORM_COL_ROW) return launch_fixup_staged_fn<PCD_FORM_COL_ROW, NORM, APX>(sa, B, max_parts, sms, smem, st);
+    return launch_fixup_staged_fn<PCD_FORM_SUM_FIRST, NORM, APX>(sa, B, max_parts, sms, smem, st);
+}
+template <bool APX>
+static cudaError_t launch_fixup_staged(int form, int norm_kind, const StagedArgs &sa, int B, int max_parts, int sms, size_t smem, cudaStream_t st) {
+    return norm_kind == PCD_NORM_FMA ? launch_fixup_staged_n<PCD_NORM_FMA, APX>(form, sa, B, max_parts, sms, smem, st)
+                                     : launch_fixup_staged_n<PCD_NORM_MULSUM, APX>(form, sa, B, max_parts, sms, smem, st);
 }
 
 // Tile-shape heuristic.  R rows per lane (register blocking: the per-step overhead -- operand
@@ -1283,16 +1463,16 @@ extern "C" int pcd_nn1_forward(const float *rows, int64_t r_sb, int64_t r_sp, in
                                float *row_min, int32_t *row_arg, float *col_min, int32_t *col_arg,
                                float *stats_f, int32_t *stats_i,
                                float *zero0, size_t zero0_floats, float *zero1, size_t zero1_floats,
-                               void *workspace, size_t workspace_bytes, int rows_per_lane, int col_tile,
+                               void *workspace, size_t workspace_bytes, int rows_per_lane, int col_tile, int sweep_mode,
                                void *sweep_start_event, void *sweep_stop_event, void *stream) {
     if (!rows || !cols || !row_min || !row_arg || !col_min || !col_arg || !stats_f || !stats_i || !workspace) {
         set_error("pcd_nn1_forward: NULL pointer argument");
         return PCD_ERR_ARG;
     }
     if (B <= 0 || N <= 0 || M <= 0 || form < 0 || form > 2 || norm_kind < 0 || norm_kind > 1 || transform < 0 ||
-        transform > 1 || B > 65535) {
-        set_error("pcd_nn1_forward: bad argument B=%d N=%d M=%d form=%d norm=%d transform=%d", B, N, M, form,
-                  norm_kind, transform);
+        transform > 1 || B > 65535 || sweep_mode < PCD_SWEEP_AUTO || sweep_mode > PCD_SWEEP_APPROX) {
+        set_error("pcd_nn1_forward: bad argument B=%d N=%d M=%d form=%d norm=%d transform=%d sweep_mode=%d", B, N, M, form,
+                  norm_kind, transform, sweep_mode);
         return PCD_ERR_ARG;
     }
     if (swap_norms && N != M) {
@@ -1334,9 +1514,14 @@ extern "C" int pcd_nn1_forward(const float *rows, int64_t r_sb, int64_t r_sp, in
                  rowpp, (const float4 *)colpk};
 
     if (raw) {
-        const size_t npairs = L.nkeys / 2;      // Npad, Mpad are even
+        const size_t npairs = L.arm_bytes / 16;   // keys, second-best values and norm maxima: one run of all-ones
+#ifdef PCD_APX_DEBUG
+        const int ncnt = B + 2;      // development build: two debug counters behind the completion counters (B % 64 != 0)
+#else
+        const int ncnt = B;
+#endif
         PCD_CUDA_CHECK(launch_kernel(nn1_arm_kernel, dim3((unsigned)(sms * 2)), dim3(256), 0, st, false,
-                                     (ulonglong2 *)rowkey, npairs, counters, B));
+                                     (ulonglong2 *)rowkey, npairs, counters, ncnt));
     } else {
         const long long total = (long long)B * (L.Npad + L.Mpad);
         const int grid = (int)((total + 255) / 256 < (long long)sms * 8 ? (total + 255) / 256 : (long long)sms * 8);
@@ -1346,9 +1531,24 @@ extern "C" int pcd_nn1_forward(const float *rows, int64_t r_sb, int64_t r_sp, in
     }
     // an event between two kernels turns the programmatic edge into a full dependency: timing the sweep
     // alone (bench.py's roofline) costs the overlap, nothing else
+    // approximate sweep + exact fix-up: dense operands whose clouds the staged fix-up can hold (its near-tie rescans read
+    // the staged cloud); everything else ranks with the reference's own instruction sequence
+    const int nmax = N > M ? N : M;
+    const size_t stage_stride = align_up((size_t)nmax, 32);
+    const size_t stage_bytes = stage_stride * 12;
+    const bool staged = raw && stage_bytes <= kStageMaxBytes;
+    // AUTO is EXACT for now: the approximate sweep alone is faster (121 vs 129 us at BASELINE config 2) but its publish path
+    // (returning atomics, +20 us) and the per-warp near-tie rescans of the fix-up (unbalanced, +68 us) are not
+    const bool apx = staged && sweep_mode == PCD_SWEEP_APPROX;
+    const SweepOut so{rowkey, colkey, (uint32_t *)(ws + L.rowsec), (uint32_t *)(ws + L.colsec), (uint32_t *)(ws + L.maxnorm)};
     if (sweep_start_event) PCD_CUDA_CHECK(cudaEventRecord((cudaEvent_t)sweep_start_event, st));
-    PCD_CUDA_CHECK(raw ? launch_sweep_f<true>(form, R, src, rowkey, colkey, B, N, M, L.Npad, L.Mpad, mt, sms, st)
-                       : launch_sweep_f<false>(form, R, src, rowkey, colkey, B, N, M, L.Npad, L.Mpad, mt, sms, st));
+    {
+        cudaError_t e;
+        if (apx) e = launch_sweep_f<true, true>(form, R, src, so, B, N, M, L.Npad, L.Mpad, mt, sms, st);
+        else if (raw) e = launch_sweep_f<true, false>(form, R, src, so, B, N, M, L.Npad, L.Mpad, mt, sms, st);
+        else e = launch_sweep_f<false, false>(form, R, src, so, B, N, M, L.Npad, L.Mpad, mt, sms, st);
+        PCD_CUDA_CHECK(e);
+    }
     if (sweep_stop_event) PCD_CUDA_CHECK(cudaEventRecord((cudaEvent_t)sweep_stop_event, st));
     {
         // persistent grid: every warp of every resident CTA owns a contiguous range of units (32 points of one side)
@@ -1366,15 +1566,12 @@ extern "C" int pcd_nn1_forward(const float *rows, int64_t r_sb, int64_t r_sp, in
                     (N + 32 * R - 1) / (32 * R), (M + kColChunk - 1) / kColChunk, N, M, L.Npad, L.Mpad, R, transform, B, row_min, row_arg, col_min, col_arg,
                     row_sum_scale, col_sum_scale, stats_f, stats_i,
                     (float4 *)zero0, zero0_floats / 4, (float4 *)zero1, zero1_floats / 4};
-        const int nmax = N > M ? N : M;
-        const size_t stage_stride = align_up((size_t)nmax, 32);
-        const size_t stage_bytes = stage_stride * 12;
-        if (raw && stage_bytes <= kStageMaxBytes) {
+        if (staged) {
             // one CTA per (sample, side, slice): the re-scanned cloud is staged in shared memory
-            StagedArgs sa{a, 1, 1, (int)stage_stride};
-            PCD_CUDA_CHECK(norm_kind == PCD_NORM_FMA
-                               ? launch_fixup_staged_n<PCD_NORM_FMA>(form, sa, B, L.partial_slots, sms, stage_bytes, st)
-                               : launch_fixup_staged_n<PCD_NORM_MULSUM>(form, sa, B, L.partial_slots, sms, stage_bytes, st));
+            StagedArgs sa{a, 1, 1, (int)stage_stride, so.rowsec, so.colsec, so.maxnorm};
+            const cudaError_t e = apx ? launch_fixup_staged<true>(form, norm_kind, sa, B, L.partial_slots, sms, stage_bytes, st)
+                                      : launch_fixup_staged<false>(form, norm_kind, sa, B, L.partial_slots, sms, stage_bytes, st);
+            PCD_CUDA_CHECK(e);
         } else {
             const dim3 grid((unsigned)((nwarps + kFixupThreads / 32 - 1) / (kFixupThreads / 32)));
             PCD_CUDA_CHECK(raw ? launch_fixup<true>(form, a, grid, st) : launch_fixup<false>(form, a, grid, st));

@@ -98,6 +98,21 @@ def force_tiling(rows_per_lane=0, col_tile=0):
     _tiling = (int(rows_per_lane), int(col_tile))
 
 
+_keep_workspace = False      # development aid (tools/apx_debug.py): keep the last NN-1 workspace in _last_workspace
+_last_workspace = None
+SWEEP_AUTO, SWEEP_EXACT, SWEEP_APPROX = 0, 1, 2
+_sweep_mode = SWEEP_AUTO
+
+
+def force_sweep_mode(mode=SWEEP_AUTO):
+    """Tests / measurements: SWEEP_EXACT ranks the pairs with the reference's instruction sequence, SWEEP_APPROX with the
+    cheaper provably-close one (the fix-up settles value and index exactly either way: identical results; experimental,
+    slower end to end for now); SWEEP_AUTO = exact (pcd_sweep_mode in include/pcdist.h).  Returns the previous setting."""
+    global _sweep_mode
+    prev, _sweep_mode = _sweep_mode, int(mode)
+    return prev
+
+
 class _NN1(torch.autograd.Function):
     @staticmethod
     def forward(ctx, rows, cols, form, norm, swap_norms, transform, row_scale, col_scale, token):
@@ -127,10 +142,12 @@ class _NN1(torch.autograd.Function):
                                      stats.data_ptr(), stats_i.data_ptr(),
                                      _ptr(grad_rows), 0 if grad_rows is None else grad_rows.numel(),
                                      _ptr(grad_cols), 0 if grad_cols is None else grad_cols.numel(),
-                                     ws.data_ptr(), ws_bytes, _tiling[0], _tiling[1],
+                                     ws.data_ptr(), ws_bytes, _tiling[0], _tiling[1], _sweep_mode,
                                      None if ev is None else ev[0].cuda_event, None if ev is None else ev[1].cuda_event,
                                      _stream(dev))
             _lib.check(st, "pcd_nn1_forward")
+            if _keep_workspace:
+                globals()["_last_workspace"] = ws
         _launch_count += 3
         ctx.save_for_backward(rows, cols, row_arg, col_arg, row_min, col_min, stats_i)
         ctx.cfg = (int(swap_norms), transform, row_scale, col_scale)

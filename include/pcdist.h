@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define PCD_VERSION 201
+#define PCD_VERSION 202
 
 enum pcd_status {
     PCD_OK = 0,
@@ -66,6 +66,8 @@ enum pcd_transform { PCD_VALUE_SQUARED = 0, PCD_VALUE_SQRT_CLAMP = 1 };
  * the library reads no environment): the default four-pass pipeline, the chunk-minima bound followed by the
  * warp-per-row select, or the warp-per-row select alone. */
 enum pcd_knn_strategy { PCD_KNN_AUTO = 0, PCD_KNN_BOUND_SELECT = 1, PCD_KNN_SELECT_ONLY = 2 };
+/* pcd_nn1_forward `sweep_mode` (identical results; see pcd_nn1_forward) */
+enum pcd_sweep_mode { PCD_SWEEP_AUTO = 0, PCD_SWEEP_EXACT = 1, PCD_SWEEP_APPROX = 2 };
 
 int pcd_version(void);
 const char *pcd_last_error(void);
@@ -110,6 +112,11 @@ const char *pcd_last_error(void);
  * rows_per_lane / col_tile: 0 = the built-in tile-shape heuristic; 2, 4, 8, 16 / a power of two in
  * 32..256 force the sweep's register blocking / TMA stage width (tests, tuning sweeps; results
  * are identical for every tiling).
+ * sweep_mode (pcd_sweep_mode; results are identical bit for bit in every mode): PCD_SWEEP_EXACT ranks the pairs with the
+ * reference's own instruction sequence; PCD_SWEEP_APPROX ranks them with a cheaper sequence that is provably within a
+ * window of it and lets the fix-up settle value and index with the reference's arithmetic (dense operands whose clouds fit
+ * the fix-up's shared-memory stage; silently EXACT otherwise) -- experimental: its sweep is faster, its publish path and
+ * near-tie rescans are not yet; PCD_SWEEP_AUTO = EXACT.
  * sweep_start_event / sweep_stop_event (optional cudaEvent_t): recorded on `stream` immediately
  * before / after the sweep kernel launch so a caller can time the dominant kernel live with
  * CUDA events (bench.py's roofline); per call, no global state.
@@ -128,7 +135,7 @@ int pcd_nn1_forward(const float *rows, int64_t r_sb, int64_t r_sp, int64_t r_sc,
                     float *row_min, int32_t *row_arg, float *col_min, int32_t *col_arg,
                     float *stats_f, int32_t *stats_i,
                     float *zero0, size_t zero0_floats, float *zero1, size_t zero1_floats,
-                    void *workspace, size_t workspace_bytes, int rows_per_lane, int col_tile,
+                    void *workspace, size_t workspace_bytes, int rows_per_lane, int col_tile, int sweep_mode,
                     void *sweep_start_event, void *sweep_stop_event, void *stream);
 
 /* Backward of everything derived from the NN-1 minima, through the saved argmins

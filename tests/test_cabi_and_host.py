@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     out = subprocess.check_output(["nm", "-D", "--defined-only", pcd._lib.LIB_PATH], text=True)
     exported = sorted(set(re.findall(r" T (pcd_[a-z0-9_]+)", out)))
     assert exported == syms
-    assert lib.pcd_version() == 201
+    assert lib.pcd_version() == 202
 
 
 def test_library_is_sm100a_and_uses_blackwell_instructions():

@@ -655,6 +655,49 @@ def test_nn1_nan_and_inf_points_do_not_fault(n):
         assert (ra[1] == 0).all() and (ca[1] == 0).all()
 
 
+@pytest.mark.parametrize("B,N,M,kind", [(3, 1024, 1024, "perturbed"), (2, 4096, 2048, "random"), (2, 512, 1500 // 4 * 4, "duplicates"),
+                                         (1, 2048, 2048, "identical"), (2, 1024, 1024, "nan"), (4, 260, 36, "tiny")])
+def test_nn1_approximate_sweep_is_bit_identical(B, N, M, kind):
+    """pcd_sweep_mode: the approximate sweep (four packed instructions per two pairs, candidate sets, near-tie rescans) and
+    the exact one give the same bits -- minima, indices, per-sample statistics -- for every form, on perturbed clouds (a few
+    per cent of the points take the rescan path), unrelated clouds, clouds full of exact duplicates (every point rescans),
+    NaN / inf coordinates, and against the oracle."""
+    rs = np.random.RandomState(B * N + M)
+    cols = rs.randn(B, M, 3).astype(np.float32)
+    if kind == "perturbed":
+        rows = (cols[:, :N] + 0.01 * rs.randn(B, N, 3)).astype(np.float32)
+    elif kind == "duplicates":
+        rows = cols[:, rs.randint(0, M, size=N)].copy()
+        cols[:, M // 2:] = cols[:, :M - M // 2]                      # every column exists twice
+    elif kind == "identical":
+        rows = np.tile(cols[:, :1], (1, N, 1)); cols = np.tile(cols[:, :1], (1, M, 1))
+    else:
+        rows = rs.randn(B, N, 3).astype(np.float32)
+    if kind == "nan":
+        rows[0, 5] = np.nan; cols[0, 7, 1] = np.inf; cols[1] = np.nan
+    for form_key in FORMS:
+        form, norm, oform, onorm = FORMS[form_key]
+        outs = []
+        for mode in (F.SWEEP_EXACT, F.SWEEP_APPROX):
+            prev = F.force_sweep_mode(mode)
+            try:
+                r = F.nn1(cu(rows), cu(cols), form, norm, cache=False)
+                outs.append([npy(x) for x in (r.row_min, r.row_arg, r.col_min, r.col_arg, r.row_sum, r.col_sum, r.row_max, r.col_max,
+                                              r.row_argmax, r.col_argmax)])
+            finally:
+                F.force_sweep_mode(prev)
+        if kind == "nan":          # non-finite minima may come out as NaN or +inf; the finite ones and all indices must agree
+            fin = [np.isfinite(a) & np.isfinite(b) for a, b in zip(outs[0], outs[1])]
+            assert all(np.array_equal(a[f], b[f]) for a, b, f in zip(outs[0][:4], outs[1][:4], fin[:4]))
+            assert np.array_equal(np.isfinite(outs[0][0]), np.isfinite(outs[1][0])) and np.array_equal(np.isfinite(outs[0][2]), np.isfinite(outs[1][2]))
+            continue
+        for a, b in zip(outs[0], outs[1]):
+            assert np.array_equal(a, b)
+        o = oracle_nn1(rows, cols, oform, onorm)
+        assert np.array_equal(outs[1][0], o.row_min) and np.array_equal(outs[1][1], o.row_arg)
+        assert np.array_equal(outs[1][2], o.col_min) and np.array_equal(outs[1][3], o.col_arg)
+
+
 def test_nn1_raw_and_packed_paths_agree():
     """The same clouds through the dense (streamed) and the strided (packed) path: identical outputs and gradients."""
     rs = np.random.RandomState(12)
@@ -726,7 +769,7 @@ def test_errors_are_loud():
         F.knn(torch.zeros(1, 4, 3, device="cuda"), torch.zeros(1, 4, 3, device="cuda"), 5)       # K > M
     lib = pcd._lib.load()
     assert lib.pcd_nn1_forward(None, 0, 0, 0, None, 0, 0, 0, 1, 1, 1, 0, 0, 0, 0, 1.0, 1.0,
-                               None, None, None, None, None, None, None, 0, None, 0, None, 0, 0, 0,
+                               None, None, None, None, None, None, None, 0, None, 0, None, 0, 0, 0, 0,
                                None, None, None) == 1
     assert b"NULL" in lib.pcd_last_error()
 
