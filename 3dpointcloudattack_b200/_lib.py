@@ -24,7 +24,7 @@ _CLOUD = [_P, _L, _L, _L]
 SIGNATURES = {
     "pcd_version": (_I, []),
     "pcd_last_error": (_c.c_char_p, []),
-    "pcd_nn1_workspace_bytes": (_Z, [_I, _I, _I]),
+    "pcd_nn1_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "pcd_nn1_query_tiling": (_I, [_I, _I, _I, _c.POINTER(_I), _c.POINTER(_I)]),
     "pcd_nn1_forward": (_I, _CLOUD + _CLOUD + [_I, _I, _I, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P,
                                                _P, _Z, _P, _Z, _P, _Z, _I, _I, _I, _P, _P, _P]),

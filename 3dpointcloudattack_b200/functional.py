@@ -130,7 +130,7 @@ class _NN1(torch.autograd.Function):
             col_arg = torch.empty((B, M), dtype=torch.int32, device=dev)
             stats = torch.empty((4, B), dtype=torch.float32, device=dev)
             stats_i = torch.empty((2, B), dtype=torch.int32, device=dev)
-            ws_bytes = lib.pcd_nn1_workspace_bytes(B, N, M)
+            ws_bytes = lib.pcd_nn1_workspace_bytes(B, N, M, _sweep_mode)
             ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
             # gradient buffers of the coming backward: the forward's last kernel clears them on the way, so the
             # backward is ONE launch (atomics into zeroed memory) instead of memset + memset + kernel
@@ -148,7 +148,7 @@ class _NN1(torch.autograd.Function):
             _lib.check(st, "pcd_nn1_forward")
             if _keep_workspace:
                 globals()["_last_workspace"] = ws
-        _launch_count += 3
+        _launch_count += 4 if _sweep_mode == SWEEP_APPROX else 3
         ctx.save_for_backward(rows, cols, row_arg, col_arg, row_min, col_min, stats_i)
         ctx.cfg = (int(swap_norms), transform, row_scale, col_scale)
         ctx.token = token

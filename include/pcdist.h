@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define PCD_VERSION 202
+#define PCD_VERSION 203
 
 enum pcd_status {
     PCD_OK = 0,
@@ -115,13 +115,14 @@ const char *pcd_last_error(void);
  * sweep_mode (pcd_sweep_mode; results are identical bit for bit in every mode): PCD_SWEEP_EXACT ranks the pairs with the
  * reference's own instruction sequence; PCD_SWEEP_APPROX ranks them with a cheaper sequence that is provably within a
  * window of it and lets the fix-up settle value and index with the reference's arithmetic (dense operands whose clouds fit
- * the fix-up's shared-memory stage; silently EXACT otherwise) -- experimental: its sweep is faster, its publish path and
- * near-tie rescans are not yet; PCD_SWEEP_AUTO = EXACT.
+ * the fix-up's shared-memory stage; silently EXACT otherwise; pass the same mode to pcd_nn1_workspace_bytes, the slot
+ * arrays and the near-tie queue live in the workspace) -- experimental: its sweep is 5 % faster, its fix-up chain slower
+ * (DESIGN.md section 4.1); PCD_SWEEP_AUTO = EXACT.
  * sweep_start_event / sweep_stop_event (optional cudaEvent_t): recorded on `stream` immediately
  * before / after the sweep kernel launch so a caller can time the dominant kernel live with
  * CUDA events (bench.py's roofline); per call, no global state.
  * ---------------------------------------------------------------------------------- */
-size_t pcd_nn1_workspace_bytes(int B, int N, int M);
+size_t pcd_nn1_workspace_bytes(int B, int N, int M, int sweep_mode);
 
 /* The tile shape the heuristic of pcd_nn1_forward picks for this problem on the current device
  * (HOST out-pointers): rows per lane R (2, 4, 8, 16) and the TMA stage width.  For reports. */

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     out = subprocess.check_output(["nm", "-D", "--defined-only", pcd._lib.LIB_PATH], text=True)
     exported = sorted(set(re.findall(r" T (pcd_[a-z0-9_]+)", out)))
     assert exported == syms
-    assert lib.pcd_version() == 202
+    assert lib.pcd_version() == 203
 
 
 def test_library_is_sm100a_and_uses_blackwell_instructions():
@@ -43,8 +43,8 @@ def test_library_is_sm100a_and_uses_blackwell_instructions():
 
 def test_workspace_sizes_without_gpu():
     lib = pcd._lib.load()
-    assert lib.pcd_nn1_workspace_bytes(32, 4096, 4096) >= 32 * 4096 * (16 + 16 + 8 + 8)
-    assert lib.pcd_nn1_workspace_bytes(0, 1, 1) == 0
+    assert lib.pcd_nn1_workspace_bytes(32, 4096, 4096, 0) >= 32 * 4096 * (16 + 16 + 8 + 8)
+    assert lib.pcd_nn1_workspace_bytes(0, 1, 1, 0) == 0
     assert lib.pcd_knn_workspace_bytes(2, 100, 100, 3, 5) > 0
 
 

@@ -21,8 +21,8 @@ for (B, N, sigma) in [(32, 4096, 0.01), (32, 4096, 1e-7), (8, 4096, 0.01), (32, 
     r = F.nn1(adv, ori, F.FORM_SUM_FIRST, F.NORM_FMA, cache=False)
     torch.cuda.synchronize()
     Npad, Mpad = al(N, 2048), al(N, 256)
-    off = B * Npad * 8 + B * Mpad * 8 + B * Npad * 4 + B * Mpad * 4 + al(B * 8, 16)
-    cnt = F._last_workspace[off + 4 * B: off + 4 * B + 8].view(torch.int32).tolist()
+    off = al(B * Npad * 8 + B * Mpad * 8 + B * 8, 16)
+    cnt = F._last_workspace[off + 4 * (B + 1): off + 4 * (B + 1) + 8].view(torch.int32).tolist()
     norms = (ori ** 2).sum(-1)
     print(f"B={B} N={N} sigma={sigma}: flagged rows {cnt[0]} / {B * N}  columns {cnt[1]} / {B * N}   max |p|^2 {float(norms.max()):.3f}  "
           f"median row min {float(r.row_min.median()):.3e}", flush=True)
