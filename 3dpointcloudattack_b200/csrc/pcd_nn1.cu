@@ -282,8 +282,8 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // The fix-up reads the few slots of a point, finds best and second-best itself, rescans the tagged candidates with the
 // reference's arithmetic and, where a second candidate is within the sample's window, the whole row (column).
 constexpr float kApxWindow = 40.0f * 5.9604644775390625e-08f;      // 40 * 2^-24 (needed: 36)
-#ifndef PCD_APX_LEVEL      // development builds only (tools/apx_levels.sh): 1 = the cheaper math alone (NOT exact), 2 = + window ballot,
-#define PCD_APX_LEVEL 4    // 3 = + per-chunk near-tie flags, 4 = + second-best publishing (the product)
+#ifndef PCD_APX_LEVEL      // development builds only (tools/apx_levels.py, TIMING of the sweep only -- the results are not valid below 4):
+#define PCD_APX_LEVEL 4    // 1 = the cheaper math alone, 2 = + window ballot, 3 = + per-chunk near-tie flags, 4 = + slot stores (the product)
 #endif
 
 template <int FORM, int R, bool RAW, bool APX>
