@@ -79,6 +79,16 @@ __global__ void __launch_bounds__(128, OCC) lab(float *out, int iters) {
 #pragma unroll
                     for (int r = 1; r + 1 < R; r += 2) { clo = min3(clo, lo[r], lo[r + 1]); chi = min3(chi, hi[r], hi[r + 1]); }
                     clo = min2(clo, lo[R - 1]); chi = min2(chi, hi[R - 1]);
+                } else if (COLM == 5) {        // balanced three-input tree (depth 3 for R = 16 instead of a chain of 8)
+                    static_assert(COLM != 5 || R == 16, "hand-unrolled for R = 16");
+                    const float a0 = min3(lo[0], lo[1], lo[2]), a1 = min3(lo[3], lo[4], lo[5]), a2 = min3(lo[6], lo[7], lo[8]);
+                    const float a3 = min3(lo[9], lo[10], lo[11]), a4 = min3(lo[12], lo[13], lo[14]);
+                    const float b0 = min3(a0, a1, a2), b1 = min3(a3, a4, lo[15]);
+                    clo = min2(b0, b1);
+                    const float c0 = min3(hi[0], hi[1], hi[2]), c1 = min3(hi[3], hi[4], hi[5]), c2 = min3(hi[6], hi[7], hi[8]);
+                    const float c3 = min3(hi[9], hi[10], hi[11]), c4 = min3(hi[12], hi[13], hi[14]);
+                    const float d0 = min3(c0, c1, c2), d1 = min3(c3, c4, hi[15]);
+                    chi = min2(d0, d1);
                 } else if (COLM == 2) {
 #pragma unroll
                     for (int r = 1; r < R; ++r) { clo = (r & 1) ? min2n(clo, lo[r]) : min2(clo, lo[r]); chi = (r & 1) ? min2n(chi, hi[r]) : min2(chi, hi[r]); }
@@ -148,6 +158,8 @@ int main() {
     run<16, 2, 0, 0, 2>("row min2", sms, d);
     run<16, 3, 3, 0, 2>("row min3 + col min3 tree (no warp red)", sms, d);
     run<16, 3, 3, 1, 2>("row min3 + col min3 tree + CREDUX (current)", sms, d);
+    run<16, 3, 5, 1, 2>("row min3 + col BALANCED min3 tree + CREDUX", sms, d);
+    run<16, 3, 5, 1, 2, 1>("four-instruction math, balanced tree + window ballot", sms, d);
     run<16, 3, 3, 1, 2, 1>("FOUR-instruction math + window ballot", sms, d);
     run<16, 3, 3, 0, 2, 1>("FOUR-instruction math, no warp red", sms, d);
     run<16, 3, 3, 1, 1, 1>("FOUR-instruction math, one CTA per SM", sms, d);
